@@ -1,0 +1,299 @@
+"""bench.py -- headline benchmark: sampled trajectories / second for a full ``sample()`` call.
+
+Workload (BASELINE.json configs[1], SURVEY 8d "cfg2"): JannerUNet1d(in 14, model_dim 32, dim_mult [1,2,2,2], k=5),
+H=32, d=14, DiscreteDiffusionSDE(predict_noise=False, 100 diffusion steps, cosine), DDPM solver with 100 sampling
+steps, temperature 0.5, fix_mask on the first observation, batch 4096 candidate trajectories PER GPU (weak scaling),
+synthetic weights (seed 0) / inputs (seed 1) / noise (seed 2 + rank).
+
+One "step" = one complete ``sample()`` call (initial noise, 100 reverse iterations, final all-gather when N > 1).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3              # this framework (CUDA engine through the C ABI)
+  python bench.py --impl reference --steps 2 --warmup 1      # CPU arm: the reference's algorithm (oracle port) on host cores
+  torchrun ... bench.py --gpus N ...                         # one rank per GPU, NCCL
+
+Prints ONE JSON line (rank 0).  See the task contract for the keys; additionally:
+  roofline      live per-kernel measurement of the dominant kernel family (fused conv GEMM) via cds_plan_profile
+  cpu_baseline  the oracle port timed on the host cores on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H, D, T_DIFF, S_STEPS, BATCH = 32, 14, 100, 100, 4096
+OBS = 11
+WORKLOAD = "cfg2: JannerUNet1d H=32 d=14, DiscreteDiffusionSDE DDPM 100 steps, batch 4096/GPU"
+# canonical algorithmic HBM bytes per trajectory for a full 100-step sample() (per-fused-conv
+# activation traffic + x_t/noise + amortised weights)
+ALG_BYTES_PER_TRAJ = 33.82e6
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_agent(device, seed=0):
+    from cleandiffuser_b200.diffusion import DiscreteDiffusionSDE
+    from cleandiffuser_b200.nn_diffusion import JannerUNet1d
+    from cleandiffuser_b200.testing import load_synth
+    net = load_synth(JannerUNet1d(D, model_dim=32, emb_dim=32, kernel_size=5, dim_mult=[1, 2, 2, 2]), seed=seed)
+    mask = torch.zeros(H, D)
+    mask[0, :OBS] = 1.
+    agent = DiscreteDiffusionSDE(net, None, fix_mask=mask, predict_noise=False, diffusion_steps=T_DIFF, device=device)
+    return agent, net, mask
+
+
+def make_prior(batch, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    prior = torch.zeros(batch, H, D)
+    prior[:, 0, :OBS] = torch.randn(batch, OBS, generator=g)
+    return prior
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_arm(steps, warmup, sample_batch=256):
+    """The reference's algorithm on the host cores: oracle port of JannerUNet1d + DiscreteDiffusionSDE.sample
+    (PyTorch CPU primitives, exactly what the reference executes on CPU), on a bounded sample of the workload."""
+    import oracle.nets as onets
+    import oracle.sampler as osamp
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, net, mask = build_agent("cpu")
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    fn = lambda x, t, c=None: onets.janner_unet(sd, x, t, c, emb_dim=32, kernel_size=5, n_stages=4)  # noqa: E731
+    prior = make_prior(sample_batch)
+    g = torch.Generator().manual_seed(2)
+
+    def one():
+        tape = lambda like: torch.randn(like.shape, generator=g)  # noqa: E731
+        with torch.no_grad():
+            return osamp.sample_discrete(fn, prior, tape, T=T_DIFF, steps=S_STEPS, solver="ddpm", temperature=0.5,
+                                         fix_mask=mask[None], predict_noise=False)
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return sample_batch * steps / dt, dt / steps, sample_batch
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="trajectories per GPU (default: the BASELINE config)")
+    ap.add_argument("--math", default=os.environ.get("CDS_MATH", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": WORKLOAD, "backbone": "JannerUNet1d(14,32,[1,2,2,2],k5)", "horizon": H, "dim": D,
+              "solver": "ddpm", "sample_steps": S_STEPS, "batch_per_gpu": args.batch,
+              "global_batch": args.batch * world, "parallelism": f"dp{world}",
+              "l2": "working set (activations + 100-slot noise tape, ~1 GB) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        warm = max(1, min(args.warmup, 1))
+        steps = max(1, min(args.steps, 3))
+        value, sec, sb = cpu_reference_arm(steps, warm)
+        cores = torch.get_num_threads()
+        line = {"impl": "reference", "metric": "sampled trajectories/sec (H=32, 100 DDPM steps)", "value": value,
+                "unit": "trajectories/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                                 "sample": f"full 100-step sample() on {sb} trajectories per step (oracle port, "
+                                           f"torch CPU fp32, {cores} threads)"},
+                "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device"
+    os.environ["CDS_BACKEND"] = "cuda"          # a silent PyTorch fallback would invalidate the number
+    os.environ["CDS_MATH"] = args.math
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    from cleandiffuser_b200.engine import runtime
+    agent, net, mask = build_agent(device)
+    B = args.batch
+    prior_host = make_prior(B, seed=1 + rank).pin_memory()
+    prior_dev = prior_host.to(device)
+    gathered = torch.empty(world * B, H, D, device=device) if world > 1 else None
+    kw = dict(solver="ddpm", n_samples=B, sample_steps=S_STEPS, temperature=0.5)
+    torch.manual_seed(2 + rank)
+
+    def step_resident():
+        x0, _ = agent.sample(prior_dev, **kw)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, x0)      # the one collective of the path: finished samples
+        return x0
+
+    def step_e2e():
+        x0, _ = agent.sample(prior_host.to(device, non_blocking=True), **kw)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, x0)
+            return gathered[rank * B:(rank + 1) * B].cpu()
+        return x0.cpu()
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        with ClockSampler(local_rank) as clk:
+            ms = timed(step_resident, args.steps)
+        launches = runtime.STATS["launches"] * args.steps
+        step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+
+    value = world * B * args.steps / (ms / 1e3)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    hbm_peak, peak_src = peaks()
+
+    # ---- live per-kernel roofline of the dominant kernel family (fused conv GEMM) -----------------------------
+    roofline = None
+    if rank == 0:
+        plan = next(iter(agent._engine_plans.values()))
+        ops = plan.program.ops
+        plan.x.copy_(torch.randn_like(plan.x) * 0.5)
+        stream = torch.cuda.current_stream().cuda_stream
+        plan.handle.profile(50, stream, len(ops))                     # warm
+        per_op = [0.0] * len(ops)
+        reps = 5
+        for _ in range(reps):
+            for i, v in enumerate(plan.handle.profile(50, stream, len(ops))):
+                per_op[i] += v / reps
+        conv_ms, conv_bytes, conv_flops, n_conv = 0.0, 0.0, 0.0, 0
+        for op, t_ms in zip(ops, per_op):
+            if op.kind != 0:
+                continue
+            c = op.u.conv
+            n_conv += 1
+            conv_ms += t_ms
+            conv_bytes += 4.0 * c.batch * (c.L_in * c.C_in + c.L_out * c.C_out * c.phases
+                                           + (c.L_out * c.res_C if c.res_w else 0) + (c.L_out * c.C_out if c.res else 0))
+            conv_flops += 2.0 * c.batch * c.L_out * c.C_out * c.phases * (c.taps * c.C_in + (c.res_C if c.res_w else 0))
+        iter_ms = sum(per_op)
+        achieved = conv_bytes / (conv_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "conv_gemm (fused Conv1d+GN+Mish+FiLM+residual), all launches of one iteration",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "peak_source": peak_src, "traffic": None,
+                    "launches_per_iter": n_conv, "avg_launch_us": conv_ms / max(n_conv, 1) * 1e3,
+                    "alg_bytes_per_iter": conv_bytes, "conv_share_of_iter": conv_ms / iter_ms,
+                    "tflops_effective": conv_flops / (conv_ms * 1e-3) / 1e12,
+                    "sample_level": {"alg_bytes_per_traj": ALG_BYTES_PER_TRAJ,
+                                     "achieved_GBs": ALG_BYTES_PER_TRAJ * value / world / 1e9,
+                                     "frac": ALG_BYTES_PER_TRAJ * value / world / 1e9 / hbm_peak}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, sb = cpu_reference_arm(1, 1, sample_batch=256)
+        cpu_baseline = {"value": v, "unit": "trajectories/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"one full 100-step sample() on {sb} trajectories ({sec:.1f} s), oracle port of the "
+                                  f"reference algorithm on torch CPU fp32"}
+
+    if rank == 0:
+        line = {"metric": "sampled trajectories/sec (H=32, 100 DDPM steps)", "value": value, "unit": "trajectories/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.math == "fp32" else "bf16 operands / f32 accumulate", "data": "synthetic",
+                "config": config, "clocks": clk.summary(),
+                "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": prior_host.numel() * 4,
+                        "d2h_bytes_per_step": B * H * D * 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "engine": {"calls": runtime.STATS["engine_calls"], "fallbacks": runtime.STATS["fallbacks"]}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,302 @@
+// libcds: C ABI (include/cds.h) over the sm_100a kernels.  Plans, validation, CUDA-graph replay.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cds.h"
+#include "attention.cuh"
+#include "conv_simt.cuh"
+#include "elementwise.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CDS_CUDA(call)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess) return fail(CDS_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+struct Step {            // one validated operator + its kernel choice
+  cds_op op;
+  int conv_bn = 0;
+};
+
+int elementwise_grid(int64_t total, int sm_count) {
+  int64_t blocks = (total + 255) / 256;
+  int64_t cap = (int64_t)sm_count * 8;     // grid sized in multiples of the SM count; grid-stride loop inside
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+int validate(const cds_op& op, Step* out) {
+  out->op = op;
+  switch (op.kind) {
+    case CDS_OP_CONV: {
+      const cds_conv_op& c = op.u.conv;
+      if (c.batch <= 0 || c.L_in <= 0 || c.L_out <= 0 || c.C_in <= 0 || c.C_out <= 0 || c.taps <= 0 ||
+          c.stride <= 0 || c.phases <= 0)
+        return fail(CDS_ERR_INVALID, "conv: non-positive geometry");
+      if (!c.in || !c.w || !c.out) return fail(CDS_ERR_INVALID, "conv: null in/w/out");
+      if (c.groups > 8) return fail(CDS_ERR_UNSUPPORTED, "conv: more than 8 GroupNorm groups");
+      if (c.groups > 0 && (!c.gn_gamma || !c.gn_beta)) return fail(CDS_ERR_INVALID, "conv: GroupNorm without affine");
+      if (c.res_w && (!c.res_in || c.res_C <= 0)) return fail(CDS_ERR_INVALID, "conv: shortcut conv without input");
+      if (c.res_w && (c.stride != 1 || c.phases != 1)) return fail(CDS_ERR_INVALID, "conv: shortcut conv needs stride 1");
+      if (c.math != CDS_MATH_FP32) return fail(CDS_ERR_UNSUPPORTED, "conv: math mode %d not built", c.math);
+      out->conv_bn = cds::conv_simt_pick_bn(c);
+      if (out->conv_bn == 0)
+        return fail(CDS_ERR_UNSUPPORTED, "conv: GroupNorm tile does not fit (L_out=%d C_out=%d groups=%d)", c.L_out,
+                    c.C_out, c.groups);
+      return CDS_OK;
+    }
+    case CDS_OP_UPDATE: {
+      const cds_update_op& u = op.u.update;
+      if (u.batch <= 0 || u.row <= 0 || !u.x || !u.pred || !u.coef) return fail(CDS_ERR_INVALID, "update: bad arguments");
+      if (u.mask && !u.prior) return fail(CDS_ERR_INVALID, "update: mask without prior");
+      return CDS_OK;
+    }
+    case CDS_OP_LNMOD: {
+      const cds_lnmod_op& l = op.u.lnmod;
+      if (l.batch <= 0 || l.L <= 0 || l.C <= 0 || !l.in || !l.out || !l.shift || !l.scale)
+        return fail(CDS_ERR_INVALID, "lnmod: bad arguments");
+      return CDS_OK;
+    }
+    case CDS_OP_ATTN: {
+      const cds_attn_op& a = op.u.attn;
+      if (a.batch <= 0 || a.L <= 0 || a.heads <= 0 || a.C % a.heads != 0 || !a.qkv || !a.out)
+        return fail(CDS_ERR_INVALID, "attn: bad arguments");
+      int hd = a.C / a.heads;
+      if (hd != 16 && hd != 32 && hd != 64) return fail(CDS_ERR_UNSUPPORTED, "attn: head_dim %d", hd);
+      if ((size_t)a.L * hd * 8 > 200 * 1024) return fail(CDS_ERR_UNSUPPORTED, "attn: L=%d too long", a.L);
+      return CDS_OK;
+    }
+    case CDS_OP_PREP: {
+      const cds_prep_op& p = op.u.prep;
+      if (p.batch <= 0 || p.row <= 0 || !p.x || !p.xin || !p.coef) return fail(CDS_ERR_INVALID, "prep: bad arguments");
+      return CDS_OK;
+    }
+    default:
+      return fail(CDS_ERR_INVALID, "unknown operator kind %d", op.kind);
+  }
+}
+
+int launch(const Step& s, const int* iter_ptr, int sm_count, cudaStream_t st) {
+  switch (s.op.kind) {
+    case CDS_OP_CONV:
+      CDS_CUDA(cds::conv_simt_launch(s.op.u.conv, s.conv_bn, iter_ptr, st));
+      return CDS_OK;
+    case CDS_OP_UPDATE: {
+      const cds_update_op& u = s.op.u.update;
+      cds::solver_update_kernel<<<elementwise_grid((int64_t)u.batch * u.row, sm_count), 256, 0, st>>>(u, iter_ptr);
+      CDS_CUDA(cudaGetLastError());
+      return CDS_OK;
+    }
+    case CDS_OP_PREP: {
+      const cds_prep_op& p = s.op.u.prep;
+      cds::cm_prep_kernel<<<elementwise_grid((int64_t)p.batch * p.row, sm_count), 256, 0, st>>>(p, iter_ptr);
+      CDS_CUDA(cudaGetLastError());
+      return CDS_OK;
+    }
+    case CDS_OP_LNMOD: {
+      const cds_lnmod_op& l = s.op.u.lnmod;
+      int64_t rows = (int64_t)l.batch * l.L;
+      int64_t blocks = (rows + 7) / 8;
+      int64_t cap = (int64_t)sm_count * 8;
+      cds::ln_modulate_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(l);
+      CDS_CUDA(cudaGetLastError());
+      return CDS_OK;
+    }
+    case CDS_OP_ATTN:
+      CDS_CUDA(cds::attention_launch(s.op.u.attn, st));
+      return CDS_OK;
+  }
+  return fail(CDS_ERR_INVALID, "unknown operator kind");
+}
+
+// Touch every kernel once so that lazy module loading never happens inside a stream capture.
+int preload_kernels() {
+  cudaFuncAttributes a;
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<32>));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<64>));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<128>));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<16>));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<32>));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<64>));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::solver_update_kernel));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::cm_prep_kernel));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::ln_modulate_kernel));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::set_iter_kernel));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::advance_iter_kernel));
+  return CDS_OK;
+}
+
+}  // namespace
+
+struct cds_plan {
+  int device = 0;
+  int sm_count = 0;
+  int n_iters = 0;
+  bool finalized = false;
+  std::vector<Step> steps;
+  int* d_iter = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+extern "C" {
+
+int cds_version(void) { return CDS_ABI_VERSION; }
+int cds_op_size(void) { return (int)sizeof(cds_op); }
+const char* cds_last_error(void) { return g_err.c_str(); }
+
+int cds_device_sm_count(int device) {
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+  return n;
+}
+
+int cds_plan_create(int device, cds_plan** out) {
+  if (!out) return fail(CDS_ERR_INVALID, "plan_create: null out");
+  int n_dev = 0;
+  CDS_CUDA(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) return fail(CDS_ERR_INVALID, "plan_create: device %d of %d", device, n_dev);
+  cds_plan* p = new cds_plan();
+  p->device = device;
+  p->sm_count = cds_device_sm_count(device);
+  *out = p;
+  return CDS_OK;
+}
+
+int cds_plan_destroy(cds_plan* p) {
+  if (!p) return CDS_OK;
+  cudaSetDevice(p->device);
+  if (p->exec) cudaGraphExecDestroy(p->exec);
+  if (p->graph) cudaGraphDestroy(p->graph);
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+  if (p->d_iter) cudaFree(p->d_iter);
+  delete p;
+  return CDS_OK;
+}
+
+int cds_plan_append(cds_plan* p, const cds_op* ops, int32_t n_ops) {
+  if (!p || (!ops && n_ops > 0)) return fail(CDS_ERR_INVALID, "plan_append: null argument");
+  if (p->finalized) return fail(CDS_ERR_STATE, "plan_append after finalize");
+  for (int i = 0; i < n_ops; ++i) {
+    Step s;
+    int rc = validate(ops[i], &s);
+    if (rc != CDS_OK) {
+      std::string inner = g_err;
+      return fail(rc, "op %d: %s", (int)p->steps.size(), inner.c_str());
+    }
+    p->steps.push_back(s);
+  }
+  return CDS_OK;
+}
+
+int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
+  if (!p) return fail(CDS_ERR_INVALID, "plan_finalize: null plan");
+  if (p->finalized) return fail(CDS_ERR_STATE, "plan already finalized");
+  if (n_iters <= 0 || p->steps.empty()) return fail(CDS_ERR_INVALID, "plan_finalize: empty program");
+  CDS_CUDA(cudaSetDevice(p->device));
+  { int rc = preload_kernels(); if (rc != CDS_OK) return rc; }
+  CDS_CUDA(cudaMalloc(&p->d_iter, sizeof(int)));
+  CDS_CUDA(cudaMemset(p->d_iter, 0, sizeof(int)));
+  CDS_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+  p->n_iters = n_iters;
+  p->finalized = true;
+  return CDS_OK;
+}
+
+static int enqueue_iteration(cds_plan* p, cudaStream_t st) {
+  for (const Step& s : p->steps) {
+    int rc = launch(s, p->d_iter, p->sm_count, st);
+    if (rc != CDS_OK) return rc;
+  }
+  cds::advance_iter_kernel<<<1, 1, 0, st>>>(p->d_iter);
+  CDS_CUDA(cudaGetLastError());
+  return CDS_OK;
+}
+
+int cds_plan_run(cds_plan* p, int32_t first, int32_t count, void* stream, int32_t use_graph) {
+  if (!p || !p->finalized) return fail(CDS_ERR_STATE, "plan_run before finalize");
+  if (first < 0 || count < 0 || first + count > p->n_iters)
+    return fail(CDS_ERR_INVALID, "plan_run: iterations [%d, %d) outside [0, %d)", first, first + count, p->n_iters);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CDS_CUDA(cudaSetDevice(p->device));
+  if (use_graph && !p->exec) {
+    // capture on a private stream (the caller's may be the legacy default stream, which cannot capture);
+    // capture itself never executes anything.
+    CDS_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_iteration(p, p->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(p->cap_stream, &p->graph);
+    if (rc != CDS_OK) return rc;
+    if (e != cudaSuccess) return fail(CDS_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    CDS_CUDA(cudaGraphInstantiate(&p->exec, p->graph, 0));
+  }
+  cds::set_iter_kernel<<<1, 1, 0, st>>>(p->d_iter, first);
+  CDS_CUDA(cudaGetLastError());
+  for (int i = 0; i < count; ++i) {
+    if (use_graph) {
+      CDS_CUDA(cudaGraphLaunch(p->exec, st));
+    } else {
+      int rc = enqueue_iteration(p, st);
+      if (rc != CDS_OK) return rc;
+    }
+  }
+  return CDS_OK;
+}
+
+int cds_plan_profile(cds_plan* p, int32_t iter, void* stream, float* ms_per_op, int32_t n_ops) {
+  if (!p || !p->finalized) return fail(CDS_ERR_STATE, "plan_profile before finalize");
+  if (!ms_per_op || n_ops != (int)p->steps.size()) return fail(CDS_ERR_INVALID, "plan_profile: n_ops != %d", (int)p->steps.size());
+  if (iter < 0 || iter >= p->n_iters) return fail(CDS_ERR_INVALID, "plan_profile: bad iteration");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CDS_CUDA(cudaSetDevice(p->device));
+  std::vector<cudaEvent_t> ev(n_ops + 1);
+  for (auto& e : ev) CDS_CUDA(cudaEventCreate(&e));
+  cds::set_iter_kernel<<<1, 1, 0, st>>>(p->d_iter, iter);
+  CDS_CUDA(cudaEventRecord(ev[0], st));
+  for (int i = 0; i < n_ops; ++i) {
+    int rc = launch(p->steps[i], p->d_iter, p->sm_count, st);
+    if (rc != CDS_OK) return rc;
+    CDS_CUDA(cudaEventRecord(ev[i + 1], st));
+  }
+  CDS_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < n_ops; ++i) CDS_CUDA(cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  return CDS_OK;
+}
+
+int cds_plan_launches_per_iter(const cds_plan* p) { return p ? (int)p->steps.size() + 1 : 0; }
+
+int cds_run_op(int device, const cds_op* op, int32_t iter, void* stream) {
+  if (!op) return fail(CDS_ERR_INVALID, "run_op: null op");
+  CDS_CUDA(cudaSetDevice(device));
+  Step s;
+  int rc = validate(*op, &s);
+  if (rc != CDS_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int* d_iter = nullptr;
+  CDS_CUDA(cudaMallocAsync(&d_iter, sizeof(int), st));
+  cds::set_iter_kernel<<<1, 1, 0, st>>>(d_iter, iter);
+  rc = launch(s, d_iter, cds_device_sm_count(device), st);
+  cudaFreeAsync(d_iter, st);
+  return rc;
+}
+
+}  // extern "C"

@@ -235,8 +235,8 @@ class ContinuousConsistencyModel(DiffusionModel):
         sigmas = karras_sigmas(sample_steps, self.sigma_min, self.sigma_max, self.rho, xp=torch, device=self.device)
         order = list(reversed([1] * diffusion_x_sampling_steps + list(range(1, sample_steps))))
 
-        if not (requires_grad or preserve_history) and torch.device(self.device).type == "cuda":
-            from ..engine import runtime
+        from ..engine import runtime
+        if not (requires_grad or preserve_history) and runtime._device_ok(torch.device(self.device)):
             out = runtime.try_sample_consistency(self, model=model, xt=xt, prior=prior, sigmas=sigmas, order=order,
                                                  cond_emb=cvec, n_samples=n_samples)
             if out is not None:

@@ -191,7 +191,8 @@ class BaseDiffusionSDE(DiffusionModel):
             return False
         if self.classifier is not None and w_cg != 0.0:
             return False
-        return torch.device(self.device).type == "cuda"
+        from ..engine import runtime
+        return runtime._device_ok(torch.device(self.device))
 
     def _finish(self, xt, log, n_samples, condition_vec_cg, w_cg):
         if self.classifier is not None and self._final_logp_wanted(w_cg):

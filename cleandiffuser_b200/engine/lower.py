@@ -1,0 +1,469 @@
+"""Lower a denoiser ``nn.Module`` to the fused-operator program libcds executes.
+
+The module tree (same names/shapes as the reference's, so user checkpoints load) is walked once per
+(model, batch, option set); the result is a ``Program``:
+
+* ``ops``        -- ``cabi.Op`` list for ONE reverse iteration (denoiser + solver update)
+* ``packers``    -- re-run when parameter versions change (training mutates weights between calls):
+                    copy/transpose parameters into the K-major layouts the kernels read
+* ``per_call``   -- run at every ``sample()``: fill the per-iteration tables (time-conditioning rows evaluated
+                    with the model's OWN ``map_noise`` / ``map_emb`` / ``emb_mlp`` modules on one row per
+                    iteration -- inside ``sample()`` t is batch-constant, diffusionsde.py:528/:874 -- and the
+                    per-trajectory condition terms)
+* ``keep``       -- every device tensor the ops point into (workspace, packed weights, tables)
+
+What is hoisted out of the iteration loop:
+  JannerUNet1d w/o condition : the whole map_noise -> map_emb -> emb_mlp chain is a [n_iters, sum C_out] table.
+  ChiUNet1d                  : cond_encoder = Linear(Mish(cat[time, obs])) splits exactly into a per-iteration
+                               row plus a per-trajectory, iteration-invariant row (Mish is elementwise).
+  DQLMlp                     : the first Linear over cat[x, time_mlp(t), obs] splits the same way.
+  DiT1d / Janner + condition : map_emb(map_noise(t) + cond) is nonlinear in the sum -> small per-trajectory
+                               GEMMs stay inside the iteration (0.5 % of the FLOPs).
+"""
+import ctypes as C
+from typing import Callable, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import cabi
+from ..nn_diffusion import ChiUNet1d, DiT1d, DQLMlp, JannerUNet1d
+from ..utils import GroupNorm1d
+
+
+class Unsupported(Exception):
+    """The module / option set is outside what the kernels cover -> caller uses the PyTorch path."""
+
+
+class View:
+    """A channels-last activation: element (b, l, c) at base + b*bstride + l*lstride + c (floats)."""
+
+    def __init__(self, tensor: torch.Tensor, L: int, Cn: int, offset: int = 0, bstride: Optional[int] = None,
+                 lstride: Optional[int] = None):
+        # module dims may be numpy ints (np.cumprod(dim_mult)); ctypes wants python ints
+        self.t, self.L, self.C, self.offset = tensor, int(L), int(Cn), int(offset)
+        self.lstride = self.C if lstride is None else int(lstride)
+        self.bstride = self.L * self.lstride if bstride is None else int(bstride)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + 4 * self.offset
+
+    def channels(self, start: int, count: int) -> "View":
+        return View(self.t, self.L, count, self.offset + int(start), self.bstride, self.lstride)
+
+
+def _vec(step: Optional[torch.Tensor] = None, sample: Optional[torch.Tensor] = None, col: int = 0) -> cabi.Vec:
+    """step: [n_iters, W] table, sample: [rows, W] table; the vector is columns col.. of both."""
+    v = cabi.Vec()
+    col = int(col)
+    if step is not None:
+        v.step, v.step_stride = step.data_ptr() + 4 * col, step.stride(0)
+    if sample is not None:
+        v.sample, v.sample_stride = sample.data_ptr() + 4 * col, sample.stride(0)
+    return v
+
+
+def _const_vec(t: Optional[torch.Tensor]) -> cabi.Vec:
+    v = cabi.Vec()
+    if t is not None:
+        v.step, v.step_stride = t.data_ptr(), 0
+    return v
+
+
+class Program:
+    def __init__(self, device: torch.device, rows: int, n_iters: int, math: int = cabi.MATH_FP32):
+        self.device, self.rows, self.n_iters, self.math = device, rows, n_iters, math
+        self.ops: List[cabi.Op] = []
+        self.keep: List[torch.Tensor] = []
+        self.packers: List[Callable[[], None]] = []
+        self.per_call: List[Callable[[object], None]] = []
+
+    # ---- memory ---------------------------------------------------------------------------
+    def buf(self, *shape) -> torch.Tensor:
+        t = torch.zeros(tuple(int(s) for s in shape), device=self.device, dtype=torch.float32)
+        self.keep.append(t)
+        return t
+
+    def act(self, L: int, Cn: int) -> View:
+        return View(self.buf(self.rows, L, Cn), L, Cn)
+
+    def packed(self, make: Callable[[], torch.Tensor]) -> torch.Tensor:
+        """Persistent packed copy of parameters; ``make`` is re-evaluated into it when weights change."""
+        with torch.no_grad():
+            t = make().detach().to(device=self.device, dtype=torch.float32).contiguous().clone()
+        self.keep.append(t)
+
+        def refresh():
+            with torch.no_grad():
+                t.copy_(make())
+        self.packers.append(refresh)
+        return t
+
+    # ---- weight layouts ---------------------------------------------------------------------
+    def conv_w(self, conv: nn.Conv1d) -> torch.Tensor:            # [Cout, Cin, k] -> [k*Cin, Cout]
+        return self.packed(lambda: conv.weight.permute(2, 1, 0).reshape(-1, conv.weight.shape[0]))
+
+    def linear_w(self, lin_weight: torch.Tensor, cols: Optional[slice] = None) -> torch.Tensor:   # [out, in] -> [in, out]
+        return self.packed(lambda: (lin_weight if cols is None else lin_weight[:, cols]).t())
+
+    def convT_w(self, conv: nn.ConvTranspose1d) -> torch.Tensor:
+        """ConvTranspose1d(k=4, s=2, p=1) as a 3-tap conv with two output phases:
+        out[2m]   = x[m-1] W[..,3] + x[m] W[..,1]        out[2m+1] = x[m] W[..,2] + x[m+1] W[..,0]"""
+        def make():
+            w = conv.weight                                  # [Cin, Cout, 4]
+            cin, cout, _ = w.shape
+            p = torch.zeros(3, cin, 2 * cout, device=w.device, dtype=w.dtype)
+            p[0, :, :cout] = w[:, :, 3]
+            p[1, :, :cout] = w[:, :, 1]
+            p[1, :, cout:] = w[:, :, 2]
+            p[2, :, cout:] = w[:, :, 0]
+            return p.reshape(3 * cin, 2 * cout)
+        return self.packed(make)
+
+    # ---- operator emitters --------------------------------------------------------------------
+    def conv(self, x: View, w: torch.Tensor, out: View, *, taps=1, stride=1, pad=0, phases=1, L_out=None,
+             bias: Optional[cabi.Vec] = None, gn: Optional[GroupNorm1d] = None, act=cabi.ACT_NONE,
+             scale: Optional[cabi.Vec] = None, shift: Optional[cabi.Vec] = None, res: Optional[View] = None,
+             res_conv=None, in_batch_mod=0, res_batch_mod=0, rows=None):
+        op = cabi.Op()
+        op.kind = cabi.OP_CONV
+        c = op.u.conv
+        c.batch = self.rows if rows is None else rows
+        c.L_in, c.L_out = x.L, int(out.L // phases if L_out is None else L_out)
+        c.C_in, c.C_out = x.C, out.C
+        c.taps, c.stride, c.pad, c.phases = int(taps), int(stride), int(pad), int(phases)
+        c.in_batch_mod = int(in_batch_mod)
+        c.in_, c.in_bstride, c.in_lstride = x.ptr, x.bstride, x.lstride
+        c.w = w.data_ptr()
+        assert w.shape == (taps * x.C, out.C * phases), (w.shape, taps, x.C, out.C, phases)
+        if bias is not None:
+            c.bias = bias
+        if gn is not None:
+            gamma, beta = self.packed(lambda: gn.weight), self.packed(lambda: gn.bias)
+            c.groups, c.gn_gamma, c.gn_beta, c.gn_eps = int(gn.num_groups), gamma.data_ptr(), beta.data_ptr(), gn.eps
+        c.act = act
+        if scale is not None:
+            c.scale = scale
+        if shift is not None:
+            c.shift = shift
+        if res is not None:
+            c.res, c.res_bstride, c.res_lstride = res.ptr, res.bstride, res.lstride
+        c.res_batch_mod = int(res_batch_mod)
+        if res_conv is not None:
+            rx, rw, rb = res_conv
+            c.res_in, c.res_in_bstride, c.res_in_lstride, c.res_C = rx.ptr, rx.bstride, rx.lstride, rx.C
+            c.res_w, c.res_bias = rw.data_ptr(), rb.data_ptr()
+        c.out, c.out_bstride, c.out_lstride = out.ptr, out.bstride, out.lstride
+        c.math = self.math
+        self.ops.append(op)
+        return out
+
+    def lnmod(self, x: View, out: View, mod: torch.Tensor, shift_col: int, scale_col: int, eps: float):
+        op = cabi.Op()
+        op.kind = cabi.OP_LNMOD
+        m = op.u.lnmod
+        m.batch, m.L, m.C, m.eps = self.rows, x.L, x.C, eps
+        m.in_, m.out = x.ptr, out.ptr
+        m.shift, m.scale = mod.data_ptr() + 4 * int(shift_col), mod.data_ptr() + 4 * int(scale_col)
+        m.mod_bstride = mod.stride(0)
+        self.ops.append(op)
+
+    def attn(self, qkv: View, out: View, heads: int):
+        op = cabi.Op()
+        op.kind = cabi.OP_ATTN
+        a = op.u.attn
+        a.batch, a.L, a.C, a.heads = self.rows, out.L, out.C, int(heads)
+        a.qkv, a.out = qkv.ptr, out.ptr
+        self.ops.append(op)
+
+
+# =============================================================================== UNets
+def _lower_conv_block(p: Program, seq: nn.Sequential, x: View, out: View, k: int, **kw):
+    """Conv1d -> GroupNorm1d -> Mish as ONE operator."""
+    conv, gn = seq[0], seq[1]
+    if not isinstance(gn, GroupNorm1d):
+        raise Unsupported("norm_type other than groupnorm")
+    return p.conv(x, p.conv_w(conv), out, taps=k, pad=k // 2, bias=_const_vec(p.packed(lambda: conv.bias)),
+                  gn=gn, act=cabi.ACT_MISH, **kw)
+
+
+def _lower_resblock(p: Program, blk, x: View, out: View, k: int, cond: dict):
+    """(Chi)ResidualBlock = 2 operators: conv1+GN+Mish+FiLM, then conv2+GN+Mish+shortcut."""
+    h = p.act(out.L, out.C)
+    _lower_conv_block(p, blk.conv1, x, h, k, **cond)
+    if isinstance(blk.residual_conv, nn.Conv1d):
+        rc = blk.residual_conv
+        shortcut = dict(res_conv=(x, p.packed(lambda: rc.weight[:, :, 0].t()), p.packed(lambda: rc.bias)))
+    else:
+        shortcut = dict(res=x)
+    return _lower_conv_block(p, blk.conv2, h, out, k, **shortcut)
+
+
+def _unet_body(p: Program, net, x: View, horizon: int, k: int, film_of: Callable, stage_len: int, final_k: int):
+    """Shared down / mid / up walk of both UNets.  ``film_of(block)`` gives the conditioning kwargs.
+    Skip connections are never copied: the producer writes straight into one half of the (b, L, 2C)
+    buffer the up-stage reads as its concatenated input."""
+    n = len(net.downs)
+    chans = [net.downs[s][0].conv1[0].out_channels for s in range(n)]
+    lens = [horizon >> s for s in range(n)]
+    if lens[-1] < 1:
+        raise Unsupported("horizon too short for the number of stages")
+    # cat buffer of up-stage u holds [x | skip h[n-1-u]] at resolution n-1-u
+    cats = [View(p.buf(p.rows, lens[n - 1 - u], 2 * chans[n - 1 - u]), lens[n - 1 - u], 2 * chans[n - 1 - u])
+            for u in range(n - 1)]
+
+    def skip_slot(s):     # where h[s] lives
+        if s == 0 or n == 1:
+            return p.act(lens[s], chans[s])
+        u = n - 1 - s
+        return cats[u].channels(chans[s], chans[s])
+
+    for s in range(n):
+        stage = net.downs[s]
+        mid = _lower_resblock(p, stage[0], x, p.act(lens[s], chans[s]), k, film_of(stage[0]))
+        h = _lower_resblock(p, stage[1], mid, skip_slot(s), k, film_of(stage[1]))
+        down = stage[stage_len - 1]
+        if isinstance(down, nn.Identity):
+            x = h
+        else:
+            x = p.conv(h, p.conv_w(down.conv), p.act(lens[s + 1], chans[s]), taps=3, stride=2, pad=1,
+                       bias=_const_vec(p.packed(lambda d=down: d.conv.bias)))
+
+    mids = [net.mid_block1, net.mid_block2] if hasattr(net, "mid_block1") else list(net.mids)
+    x = _lower_resblock(p, mids[0], x, p.act(lens[-1], chans[-1]), k, film_of(mids[0]))
+    dst = cats[0].channels(0, chans[-1]) if n > 1 else p.act(lens[-1], chans[-1])
+    x = _lower_resblock(p, mids[1], x, dst, k, film_of(mids[1]))
+
+    for u in range(n - 1):
+        stage = net.ups[u]
+        s = n - 1 - u                          # resolution index of this up stage
+        c_out = stage[0].conv1[0].out_channels
+        y = _lower_resblock(p, stage[0], cats[u], p.act(lens[s], c_out), k, film_of(stage[0]))
+        y = _lower_resblock(p, stage[1], y, p.act(lens[s], c_out), k, film_of(stage[1]))
+        up = stage[stage_len - 1]
+        if isinstance(up, nn.Identity):
+            raise Unsupported("up stage without Upsample1d")
+        dst = cats[u + 1].channels(0, c_out) if u + 1 < n - 1 else p.act(lens[s - 1], c_out)
+        x = p.conv(y, p.convT_w(up.conv), dst, taps=3, stride=1, pad=1, phases=2, L_out=lens[s],
+                   bias=_const_vec(p.packed(lambda m=up: m.conv.bias)))
+
+    fc = net.final_conv
+    y = _lower_conv_block(p, fc, x, p.act(horizon, fc[0].out_channels), final_k)
+    last = fc[3]
+    return p.conv(y, p.packed(lambda: last.weight[:, :, 0].t()), p.act(horizon, last.out_channels),
+                  bias=_const_vec(p.packed(lambda: last.bias)))
+
+
+def _all_resblocks(net):
+    blocks = []
+    for stage in net.downs:
+        blocks += [stage[0], stage[1]]
+    blocks += [net.mid_block1, net.mid_block2] if hasattr(net, "mid_block1") else list(net.mids)
+    for stage in net.ups:
+        blocks += [stage[0], stage[1]]
+    return blocks
+
+
+def lower_janner(p: Program, net: JannerUNet1d, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
+    if any(not isinstance(s[2], nn.Identity) for s in list(net.downs) + list(net.ups)) or \
+            not isinstance(net.mid_attn, nn.Identity):
+        raise Unsupported("JannerUNet1d(attention=True)")
+    if horizon & (horizon - 1):
+        raise Unsupported("horizon must be 2^n")
+    blocks = _all_resblocks(net)
+    widths = [b.emb_mlp[1].out_features for b in blocks]
+    offs = [sum(widths[:i]) for i in range(len(widths))]
+    total = sum(widths)
+    k = blocks[0].conv1[0].kernel_size[0]
+
+    if not has_cond:
+        # time conditioning is batch-constant: one row per iteration, evaluated by the model's own modules
+        table = p.buf(p.n_iters, total)
+
+        def fill(ctx):
+            e = net.map_noise(ctx.t_all)
+            e = net.map_emb(e + torch.zeros_like(e))
+            table.copy_(torch.cat([b.emb_mlp(e) for b in blocks], dim=1))
+        p.per_call.append(fill)
+        film = {id(b): dict(shift=_vec(step=table, col=o)) for b, o in zip(blocks, offs)}
+    else:
+        # emb = map_emb(map_noise(t) + cond_b): per trajectory AND per iteration -> tiny GEMMs in the loop.
+        md, e_dim = net.map_emb[2].out_features, net.map_emb[0].in_features
+        t_rows = p.buf(p.n_iters, net.map_emb[0].out_features)       # W0 map_noise(t) + b0, per iteration
+        c_rows = p.buf(p.rows, net.map_emb[0].out_features)          # W0 cond_b, per trajectory
+        dummy_in, dummy_w = p.buf(p.rows, 1), p.buf(1, net.map_emb[0].out_features)
+
+        def fill(ctx):
+            t_rows.copy_(net.map_emb[0](net.map_noise(ctx.t_all)))
+            c_rows.copy_(F.linear(ctx.cond_rows, net.map_emb[0].weight))
+        p.per_call.append(fill)
+        h1 = View(p.buf(p.rows, 1, net.map_emb[0].out_features), 1, net.map_emb[0].out_features)
+        p.conv(View(dummy_in, 1, 1), dummy_w, h1, bias=_vec(step=t_rows, sample=c_rows), act=cabi.ACT_MISH)
+        emb_m = View(p.buf(p.rows, 1, md), 1, md)                      # Mish(map_emb(.)): every consumer starts with Mish
+        p.conv(h1, p.linear_w(net.map_emb[2].weight), emb_m, bias=_const_vec(p.packed(lambda: net.map_emb[2].bias)),
+               act=cabi.ACT_MISH)
+        tb = View(p.buf(p.rows, 1, total), 1, total)
+        p.conv(emb_m, p.packed(lambda: torch.cat([b.emb_mlp[1].weight for b in blocks], 0).t()), tb,
+               bias=_const_vec(p.packed(lambda: torch.cat([b.emb_mlp[1].bias for b in blocks], 0))))
+        film = {id(b): dict(shift=_vec(sample=tb.t.view(p.rows, total), col=o)) for b, o in zip(blocks, offs)}
+
+    x = View(x.t, x.L, x.C, x.offset, x.bstride, x.lstride)
+    # first conv reads x_t; under two-branch CFG both halves of the doubled batch read the same rows
+    first = blocks[0]
+    pred = _unet_body_with_mod(p, net, x, horizon, k, lambda b: film[id(b)], 4, 5, in_batch_mod, first)
+    return pred
+
+
+def _unet_body_with_mod(p, net, x, horizon, k, film_of, stage_len, final_k, in_batch_mod, first_block):
+    """``_unet_body`` with ``in_batch_mod`` applied to the operators that read x_t directly (the first block's
+    conv1 and its shortcut)."""
+    n_before = len(p.ops)
+    pred = _unet_body(p, net, x, horizon, k, film_of, stage_len, final_k)
+    if in_batch_mod:
+        x_ptr = x.ptr
+        for op in p.ops[n_before:]:
+            c = op.u.conv
+            if op.kind == cabi.OP_CONV and c.in_ == x_ptr:
+                c.in_batch_mod = in_batch_mod
+            if op.kind == cabi.OP_CONV and (c.res_in == x_ptr or c.res == x_ptr):
+                c.res_batch_mod = in_batch_mod
+    return pred
+
+
+def lower_chi(p: Program, net: ChiUNet1d, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
+    if not net.obs_as_global_cond:
+        raise Unsupported("ChiUNet1d(obs_as_global_cond=False)")
+    if not has_cond:
+        raise Unsupported("ChiUNet1d needs a condition")       # the reference raises too (chiunet.py:149)
+    if horizon & (horizon - 1):
+        raise Unsupported("horizon must be 2^n")
+    blocks = _all_resblocks(net)
+    widths = [b.cond_encoder[1].out_features for b in blocks]
+    offs = [sum(widths[:i]) for i in range(len(widths))]
+    total = sum(widths)
+    e_dim = net.emb_dim
+    k = blocks[0].conv1[0].kernel_size[0]
+    step_tab, samp_tab = p.buf(p.n_iters, total), p.buf(p.rows, total)
+
+    def fill(ctx):
+        # cond_encoder(cat[time, obs]) = W_t Mish(time) + b  (per iteration)  +  W_o Mish(obs)  (per trajectory)
+        te = F.mish(net.map_emb(net.map_noise(ctx.t_all)))
+        oe = F.mish(net.global_cond_encoder(torch.flatten(ctx.cond_rows, 1)))
+        step_tab.copy_(torch.cat([F.linear(te, b.cond_encoder[1].weight[:, :e_dim], b.cond_encoder[1].bias)
+                                  for b in blocks], 1))
+        samp_tab.copy_(torch.cat([F.linear(oe, b.cond_encoder[1].weight[:, e_dim:]) for b in blocks], 1))
+    p.per_call.append(fill)
+
+    def film_of(b):
+        o = offs[[id(z) for z in blocks].index(id(b))]
+        if b.cond_predict_scale:
+            return dict(scale=_vec(step_tab, samp_tab, o), shift=_vec(step_tab, samp_tab, o + b.out_dim))
+        return dict(shift=_vec(step_tab, samp_tab, o))
+    return _unet_body_with_mod(p, net, x, horizon, k, film_of, 3, k, in_batch_mod, blocks[0])
+
+
+# =============================================================================== DQLMlp
+def lower_dql(p: Program, net: DQLMlp, x: View, has_cond: bool, in_batch_mod: int) -> View:
+    act_dim = x.C
+    lin1 = net.mid_layer[0]
+    e_dim = net.time_mlp[2].out_features
+    hidden = lin1.out_features
+    step_tab, samp_tab = p.buf(p.n_iters, hidden), p.buf(p.rows, hidden)
+
+    def fill(ctx):
+        # Linear over cat[x, time_mlp(map_noise(t)), obs] = W_x x + (W_t temb + b) + W_o obs
+        temb = net.time_mlp(net.map_noise(ctx.t_all))
+        step_tab.copy_(F.linear(temb, lin1.weight[:, act_dim:act_dim + e_dim], lin1.bias))
+        if has_cond:
+            samp_tab.copy_(F.linear(ctx.cond_rows, lin1.weight[:, act_dim + e_dim:]))
+        else:
+            samp_tab.zero_()
+    p.per_call.append(fill)
+    h = View(p.buf(p.rows, 1, hidden), 1, hidden)
+    p.conv(x, p.linear_w(lin1.weight, slice(0, act_dim)), h, bias=_vec(step_tab, samp_tab), act=cabi.ACT_MISH,
+           in_batch_mod=in_batch_mod)
+    for idx in (2, 4):
+        lin = net.mid_layer[idx]
+        h2 = View(p.buf(p.rows, 1, lin.out_features), 1, lin.out_features)
+        p.conv(h, p.linear_w(lin.weight), h2, bias=_const_vec(p.packed(lambda m=lin: m.bias)), act=cabi.ACT_MISH)
+        h = h2
+    out = View(p.buf(p.rows, 1, act_dim), 1, act_dim)
+    fl = net.final_layer
+    return p.conv(h, p.linear_w(fl.weight), out, bias=_const_vec(p.packed(lambda: fl.bias)))
+
+
+# =============================================================================== DiT1d
+def lower_dit(p: Program, net: DiT1d, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
+    d = net.d_model
+    depth = len(net.blocks)
+    heads = net.blocks[0].attn.num_heads
+    if net.blocks[0].attn.dropout != 0.0 and net.training:
+        raise Unsupported("attention dropout in train mode")
+    R, L = p.rows, horizon
+
+    # ---- conditioning: emb = Mish(W2 Mish(W0 (map_noise(t) + cond_b) + b0) + b2);  every consumer applies SiLU first
+    w0 = net.map_emb[0]
+    t_rows, c_rows = p.buf(p.n_iters, d), p.buf(R, d)
+    pos = p.buf(L, d)
+    dummy_in, dummy_w = p.buf(R, 1), p.buf(1, d)
+
+    def fill(ctx):
+        t_rows.copy_(w0(net.map_noise(ctx.t_all)))
+        if has_cond:
+            c_rows.copy_(F.linear(ctx.cond_rows, w0.weight))
+        else:
+            c_rows.zero_()
+        pos.copy_(net.pos_emb(torch.arange(L, device=pos.device)))      # int64 positions: degenerate table, by design
+    p.per_call.append(fill)
+    h1 = View(p.buf(R, 1, d), 1, d)
+    p.conv(View(dummy_in, 1, 1), dummy_w, h1, bias=_vec(step=t_rows, sample=c_rows), act=cabi.ACT_MISH)
+    emb_s = View(p.buf(R, 1, d), 1, d)
+    p.conv(h1, p.linear_w(net.map_emb[2].weight), emb_s, bias=_const_vec(p.packed(lambda: net.map_emb[2].bias)),
+           act=cabi.ACT_MISH_SILU)
+    mods = [blk.adaLN_modulation[1] for blk in net.blocks] + [net.final_layer.adaLN_modulation[1]]
+    total = sum(m.out_features for m in mods)
+    mod = View(p.buf(R, 1, total), 1, total)
+    p.conv(emb_s, p.packed(lambda: torch.cat([m.weight for m in mods], 0).t()), mod,
+           bias=_const_vec(p.packed(lambda: torch.cat([m.bias for m in mods], 0))))
+    mod2d = mod.t.view(R, total)
+
+    # ---- tokens
+    X, Y, ATT = p.act(L, d), p.act(L, d), p.act(L, d)
+    QKV, HID = p.act(L, 3 * d), p.act(L, 4 * d)
+    p.conv(x, p.linear_w(net.x_proj.weight), X, bias=_const_vec(p.packed(lambda: net.x_proj.bias)),
+           res=View(pos, L, d, bstride=0), in_batch_mod=in_batch_mod)
+    for i, blk in enumerate(net.blocks):
+        o = 6 * d * i       # chunk order: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+        p.lnmod(X, Y, mod2d, o, o + d, blk.norm1.eps)
+        at = blk.attn
+        p.conv(Y, p.linear_w(at.in_proj_weight), QKV, bias=_const_vec(p.packed(lambda a=at: a.in_proj_bias)))
+        p.attn(QKV, ATT, heads)
+        # reference quirk (dit.py:33-34): the residual wraps the MODULATED tokens Y, not the block input
+        p.conv(ATT, p.linear_w(at.out_proj.weight), X, bias=_const_vec(p.packed(lambda a=at: a.out_proj.bias)),
+               scale=_vec(sample=mod2d, col=o + 2 * d), res=Y)
+        p.lnmod(X, Y, mod2d, o + 3 * d, o + 4 * d, blk.norm2.eps)
+        p.conv(Y, p.linear_w(blk.mlp[0].weight), HID, bias=_const_vec(p.packed(lambda b=blk: b.mlp[0].bias)),
+               act=cabi.ACT_GELU_TANH)
+        p.conv(HID, p.linear_w(blk.mlp[3].weight), X, bias=_const_vec(p.packed(lambda b=blk: b.mlp[3].bias)),
+               scale=_vec(sample=mod2d, col=o + 5 * d), res=X)
+    o = 6 * d * depth
+    fl = net.final_layer
+    p.lnmod(X, Y, mod2d, o, o + d, fl.norm_final.eps)
+    out = p.act(L, net.in_dim)
+    return p.conv(Y, p.linear_w(fl.linear.weight), out, bias=_const_vec(p.packed(lambda: fl.linear.bias)))
+
+
+def lower_denoiser(p: Program, net: nn.Module, x: View, x_shape, has_cond: bool, in_batch_mod: int) -> View:
+    """Dispatch on the backbone type (reference instances are recognised structurally by class name)."""
+    name = type(net).__name__
+    if name == "JannerUNet1d" and len(x_shape) == 2:
+        return lower_janner(p, net, x, x_shape[0], has_cond, in_batch_mod)
+    if name == "ChiUNet1d" and len(x_shape) == 2:
+        return lower_chi(p, net, x, x_shape[0], has_cond, in_batch_mod)
+    if name == "DiT1d" and len(x_shape) == 2:
+        return lower_dit(p, net, x, x_shape[0], has_cond, in_batch_mod)
+    if name == "DQLMlp" and len(x_shape) == 1:
+        return lower_dql(p, net, x, has_cond, in_batch_mod)
+    raise Unsupported(f"backbone {name} with x_shape {tuple(x_shape)}")

@@ -1,6 +1,346 @@
-def try_sample(*a, **k):
+"""Host runtime of the CUDA sampling engine: plan cache, per-call table fill, graph replay.
+
+``try_sample`` is called by ``{Discrete,Continuous}DiffusionSDE.sample`` after the prologue (initial
+noise, mask, nn_condition) and replaces the whole Python reverse loop (diffusionsde.py:525-594) by
+
+    tables  <- per-iteration solver coefficients + time-conditioning rows      (host, tiny)
+    noise   <- the loop's torch.randn_like draws, taken up front IN THE SAME ORDER (so a seeded run consumes
+               the generator exactly like the reference loop would)
+    x_t     <- one device buffer, updated in place by the last operator of every iteration
+    replay  <- cds_plan_run: one CUDA graph per iteration, indexed by a device-side counter
+
+It returns ``None`` when the request is outside what the kernels cover (custom backbone, attention UNet,
+odd shapes ...) and the caller continues on the PyTorch path; a missing/unsound extension raises.
+
+Environment switches (no flag system, pipelines stay unchanged):
+  CDS_BACKEND = auto | torch | cuda    (torch: never use the engine; cuda: raise instead of falling back)
+  CDS_MATH    = fp32 | bf16            (operand precision of the conv/linear GEMMs)
+  CDS_GRAPH   = 1 | 0                  (0: launch kernels directly, for profilers)
+"""
+import os
+from typing import Optional
+
+import torch
+
+from . import cabi
+from .lower import Program, Unsupported, View, lower_denoiser
+from ..diffusion import solvers as S
+
+STATS = {"engine_calls": 0, "fallbacks": 0, "last_fallback_reason": None, "launches": 0}
+
+
+def _backend():
+    return os.environ.get("CDS_BACKEND", "auto")
+
+
+def _math_mode():
+    return cabi.MATH_BF16_TC if os.environ.get("CDS_MATH", "fp32") == "bf16" else cabi.MATH_FP32
+
+
+def _weights_version(module: torch.nn.Module):
+    acc = 0
+    for p in module.parameters():
+        acc = (acc * 1000003 + p._version * 31 + p.data_ptr()) & 0xFFFFFFFFFFFF
+    return acc
+
+
+def _device_ok(device: torch.device) -> bool:
+    return device.type == "cuda"
+
+
+def _make_handle(device: torch.device, ops, n_iters: int):
+    """Hand the operator program to libcds (tests substitute a numpy interpreter to check the lowering on CPU)."""
+    cabi.load()                                   # raises loudly if the extension is not built
+    handle = cabi.Plan(device.index if device.index is not None else torch.cuda.current_device())
+    handle.append(ops)
+    handle.finalize(n_iters)
+    return handle
+
+
+class _Ctx:
+    """What the per-call table fillers see."""
+
+    def __init__(self, t_all, cond_rows):
+        self.t_all, self.cond_rows = t_all, cond_rows
+
+
+class SamplerPlan:
+    """Everything resident on the device for one (model, batch, x_shape, option set)."""
+
+    def __init__(self, device, net, batch, x_shape, n_iters, n_slots, *, cfg_mode, predict_noise, has_mask,
+                 has_min, has_max, keep_history, math, consistency=False):
+        self.device, self.net, self.batch, self.x_shape = device, net, batch, tuple(x_shape)
+        row = 1
+        for s in x_shape:
+            row *= s
+        self.row, self.n_iters = row, n_iters
+        rows = batch * (2 if cfg_mode == 2 else 1)
+        self.cfg_mode = cfg_mode
+        p = Program(device, rows, n_iters, math)
+        self.program = p
+        self.x = p.buf(batch, *x_shape)
+        self.prior = p.buf(batch, *x_shape) if has_mask else None
+        self.mask = p.buf(row) if has_mask else None
+        self.x_min = p.buf(row) if has_min else None
+        self.x_max = p.buf(row) if has_max else None
+        self.coef = p.buf(n_iters, cabi.ROW_FLOATS)
+        self.noise = p.buf(max(n_slots, 1), batch, row) if n_slots > 0 else None
+        self.xhat_prev = p.buf(batch, row) if keep_history else None
+
+        L = x_shape[0] if len(x_shape) == 2 else 1
+        Cn = x_shape[-1]
+        xin = self.x
+        if consistency:
+            self.xin = p.buf(batch, *x_shape)
+            op = cabi.Op()
+            op.kind = cabi.OP_PREP
+            q = op.u.prep
+            q.batch, q.row, q.x, q.xin, q.coef = batch, row, self.x.data_ptr(), self.xin.data_ptr(), self.coef.data_ptr()
+            q.noise = self.noise.data_ptr() if self.noise is not None else None
+            p.ops.append(op)
+            xin = self.xin
+        xview = View(xin, L, Cn)
+        pred = lower_denoiser(p, net, xview, x_shape, cfg_mode != 0, batch if cfg_mode == 2 else 0)
+
+        op = cabi.Op()
+        op.kind = cabi.OP_UPDATE
+        u = op.u.update
+        u.batch, u.row, u.x = batch, row, self.x.data_ptr()
+        u.pred = pred.ptr
+        if cfg_mode == 2:
+            u.pred_uncond = pred.ptr + 4 * batch * row
+        u.noise = self.noise.data_ptr() if self.noise is not None else None
+        u.prior = self.prior.data_ptr() if has_mask else None
+        u.mask = self.mask.data_ptr() if has_mask else None
+        u.x_min = self.x_min.data_ptr() if has_min else None
+        u.x_max = self.x_max.data_ptr() if has_max else None
+        u.xhat_prev = self.xhat_prev.data_ptr() if keep_history else None
+        u.coef = self.coef.data_ptr()
+        u.predict_noise = 1 if predict_noise else 0
+        u.final_clip = 1 if consistency else 0
+        self._update_op = op
+        p.ops.append(op)
+
+        self.handle: Optional[cabi.Plan] = None
+        self.version = _weights_version(net)
+
+    def build(self, w_cfg: float):
+        u = self._update_op.u.update
+        u.w_cfg, u.w_uncond = float(w_cfg), float(1 - w_cfg)
+        self.w_cfg = w_cfg
+        self.handle = _make_handle(self.device, self.program.ops, self.n_iters)
+
+    def refresh_weights(self):
+        v = _weights_version(self.net)
+        if v != self.version:
+            for fn in self.program.packers:
+                fn()
+            self.version = v
+
+    def run(self, t_all, cond_rows, use_graph=True):
+        with torch.no_grad():
+            ctx = _Ctx(t_all, cond_rows)
+            for fn in self.program.per_call:
+                fn(ctx)
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
+        self.handle.run(0, self.n_iters, stream, use_graph)
+        STATS["launches"] = self.handle.launches_per_iter() * self.n_iters + 1
+
+
+def _row(t, x_shape, device):
+    return torch.broadcast_to(t.to(device=device, dtype=torch.float32), (1, *x_shape)).reshape(-1)
+
+
+def _device_of(agent):
+    return torch.device(agent.device)
+
+
+def _fallback(reason):
+    STATS["fallbacks"] += 1
+    STATS["last_fallback_reason"] = reason
+    if _backend() == "cuda":
+        raise RuntimeError(f"CDS_BACKEND=cuda but the engine cannot serve this call: {reason}")
     return None
 
 
-def try_sample_consistency(*a, **k):
-    return None
+def _cfg_mode(w_cfg, cond_emb):
+    if w_cfg == 0.0 or cond_emb is None:
+        return 0 if (w_cfg == 0.0 or w_cfg == 1.0) else None     # two-branch CFG without a condition is an error upstream
+    return 1 if w_cfg == 1.0 else 2
+
+
+def _get_plan(agent, key, factory):
+    plan = agent._engine_plans.get(key)
+    if plan is None:
+        plan = factory()
+        agent._engine_plans[key] = plan
+    else:
+        plan.refresh_weights()
+    return plan
+
+
+def _cond_rows(cfg_mode, cond_emb):
+    if cfg_mode == 0:
+        return None
+    c = cond_emb.to(torch.float32)
+    return torch.cat([c, torch.zeros_like(c)], 0) if cfg_mode == 2 else c
+
+
+def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_values, alphas, sigmas, hs, stds,
+               cond_emb, w_cfg, n_samples):
+    if _backend() == "torch":
+        return None
+    device = _device_of(agent)
+    if not _device_ok(device) or xt.dtype != torch.float32:
+        return None
+    net = model["diffusion"]
+    cfg_mode = _cfg_mode(w_cfg, cond_emb)
+    if cfg_mode is None:
+        return _fallback("two-branch CFG without condition")
+    batch, x_shape = xt.shape[0], tuple(xt.shape[1:])
+    if n_samples != batch:
+        return _fallback("n_samples != prior.shape[0]")
+
+    # ---- per-iteration scalars (host, reference op order) ------------------------------------------------
+    alphas_c, sigmas_c, hs_c, stds_c = (z.detach().float().cpu() for z in (alphas, sigmas, hs, stds))
+    t_cpu = step_values.detach().cpu()
+    table = S.coeff_table(solver, order, sample_steps, alphas_c, sigmas_c, hs_c, stds_c, t_cpu.double())
+    n_slots = 0
+    for n in range(len(order)):
+        if table[n, S.R_NOISE] > 0:
+            n_slots += 1
+            table[n, S.R_NOISE] = float(n_slots)       # 1 + slot index
+    keep_history = S.solver_keeps_history(solver)
+    has_mask = isinstance(agent.fix_mask, torch.Tensor)
+    has_min, has_max = agent.x_min is not None, agent.x_max is not None
+    math = _math_mode()
+    key = ("sde", id(net), batch, x_shape, len(order), n_slots > 0, cfg_mode, bool(agent.predict_noise), has_mask,
+           has_min, has_max, keep_history, math, float(w_cfg) if cfg_mode == 2 else 0.0)
+
+    def factory():
+        plan = SamplerPlan(device, net, batch, x_shape, len(order), n_slots, cfg_mode=cfg_mode,
+                           predict_noise=agent.predict_noise, has_mask=has_mask, has_min=has_min, has_max=has_max,
+                           keep_history=keep_history, math=math)
+        plan.build(w_cfg)
+        return plan
+
+    try:
+        plan = _get_plan(agent, key, factory)
+    except Unsupported as e:
+        return _fallback(str(e))
+    except cabi.CdsError as e:
+        if e.code == -3:
+            return _fallback(str(e))
+        raise
+    if plan.noise is not None and plan.noise.shape[0] < n_slots:
+        return _fallback("noise tape smaller than needed")
+
+    # ---- fill the resident buffers ----------------------------------------------------------------------
+    with torch.no_grad():
+        plan.x.copy_(xt)
+        plan.coef.copy_(table, non_blocking=True)
+        if has_mask:
+            plan.prior.copy_(prior)
+            plan.mask.copy_(_row(agent.fix_mask, x_shape, device))
+        if has_min:
+            plan.x_min.copy_(_row(agent.x_min, x_shape, device))
+        if has_max:
+            plan.x_max.copy_(_row(agent.x_max, x_shape, device))
+        for k in range(n_slots):          # same calls, same order, same shapes as the reference loop's draws
+            plan.noise[k].copy_(torch.randn_like(xt).reshape(batch, -1))
+        idx = torch.as_tensor(order, dtype=torch.long)
+        t_all = t_cpu[idx].to(device)      # int64 (discrete) or float32 (continuous), one entry per iteration
+    plan.run(t_all, _cond_rows(cfg_mode, cond_emb), use_graph=os.environ.get("CDS_GRAPH", "1") != "0")
+    STATS["engine_calls"] += 1
+    return plan.x.clone()
+
+
+def try_sample_consistency(agent, *, model, xt, prior, sigmas, order, cond_emb, n_samples):
+    """ContinuousConsistencyModel.sample on the engine: iteration 0 evaluates f at sigma_max, the following
+    iterations re-noise to sigma_i and evaluate f again (consistency_model.py:401-426)."""
+    if _backend() == "torch":
+        return None
+    device = _device_of(agent)
+    if not _device_ok(device) or xt.dtype != torch.float32:
+        return None
+    net = model["diffusion"]
+    batch, x_shape = xt.shape[0], tuple(xt.shape[1:])
+    if n_samples != batch:
+        return _fallback("n_samples != prior.shape[0]")
+    cfg_mode = 0 if cond_emb is None else 1
+    sig = sigmas.detach().float().cpu()
+    levels = [sig[-1]] + [sig[i] for i in order]
+    n_iters = len(levels)
+    sd, smin = agent.sigma_data, agent.sigma_min
+    table = torch.zeros((n_iters, S.ROW), dtype=torch.float32)
+    for n, s in enumerate(levels):                     # 0-d fp32 tensors, reference op order (:241-251, :423)
+        table[n, S.R_K0] = float(sd ** 2 / (sd ** 2 + (s - smin) ** 2))                      # c_skip
+        table[n, S.R_K1] = float((s - smin) * sd / (sd ** 2 + s ** 2).sqrt())               # c_out
+        table[n, S.R_K3] = float(1 / (sd ** 2 + s ** 2).sqrt())                              # c_in
+        table[n, S.R_KIND] = float(S.UPD_CM)
+        if n > 0:
+            table[n, S.R_K2] = float((s ** 2 - smin ** 2).sqrt())                            # re-noise scale
+            table[n, S.R_NOISE] = float(n)
+        table[n, S.R_T] = float(0.25 * s.log())                                               # c_noise
+    n_slots = n_iters - 1
+    has_mask = isinstance(agent.fix_mask, torch.Tensor)
+    has_min, has_max = agent.x_min is not None, agent.x_max is not None
+    math = _math_mode()
+    key = ("cm", id(net), batch, x_shape, n_iters, cfg_mode, has_mask, has_min, has_max, math)
+
+    def factory():
+        plan = SamplerPlan(device, net, batch, x_shape, n_iters, n_slots, cfg_mode=cfg_mode, predict_noise=False,
+                           has_mask=has_mask, has_min=has_min, has_max=has_max, keep_history=False, math=math,
+                           consistency=True)
+        plan.build(1.0)
+        return plan
+
+    try:
+        plan = _get_plan(agent, key, factory)
+    except Unsupported as e:
+        return _fallback(str(e))
+    except cabi.CdsError as e:
+        if e.code == -3:
+            return _fallback(str(e))
+        raise
+    with torch.no_grad():
+        plan.x.copy_(xt)
+        plan.coef.copy_(table, non_blocking=True)
+        if has_mask:
+            plan.prior.copy_(prior)
+            plan.mask.copy_(_row(agent.fix_mask, x_shape, device))
+        if has_min:
+            plan.x_min.copy_(_row(agent.x_min, x_shape, device))
+        if has_max:
+            plan.x_max.copy_(_row(agent.x_max, x_shape, device))
+        for k in range(n_slots):
+            plan.noise[k].copy_(torch.randn_like(xt).reshape(batch, -1))
+        t_all = table[:, S.R_T].to(device)             # the network sees c_noise = ln(sigma)/4 as its "time"
+    plan.run(t_all, _cond_rows(cfg_mode, cond_emb), use_graph=os.environ.get("CDS_GRAPH", "1") != "0")
+    STATS["engine_calls"] += 1
+    return plan.x.clone()
+
+
+def engine_forward(net, x, t, cond_emb=None, math=None, use_graph=False):
+    """Run ONLY the lowered denoiser once (no solver update): ``net(x, t.expand(b), cond_emb)`` on the engine.
+
+    ``t`` is a 1-element tensor (int64 or float32): inside ``sample()`` the time is batch-constant.  Used by the
+    parity tests and by profiling scripts; raises ``Unsupported`` if the backbone cannot be lowered."""
+    device = x.device
+    batch, x_shape = x.shape[0], tuple(x.shape[1:])
+    p = Program(device, batch, 1, _math_mode() if math is None else math)
+    xin = p.buf(batch, *x_shape)
+    xin.copy_(x)
+    L = x_shape[0] if len(x_shape) == 2 else 1
+    pred = lower_denoiser(p, net, View(xin, L, x_shape[-1]), x_shape, cond_emb is not None, 0)
+    handle = _make_handle(device, p.ops, 1)
+    with torch.no_grad():
+        ctx = _Ctx(t.reshape(1).to(device), None if cond_emb is None else cond_emb.to(torch.float32))
+        for fn in p.per_call:
+            fn(ctx)
+    handle.run(0, 1, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0, use_graph)
+    out = pred.t.clone().reshape(batch, *x_shape)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+    handle.close()
+    return out

@@ -1,0 +1,176 @@
+/* cds.h -- C ABI of the B200 diffusion-sampling engine (libcds.so).
+ *
+ * The reference (CleanDiffuser) has no FFI of its own: its hot path is the Python loop
+ * DiscreteDiffusionSDE.sample / ContinuousDiffusionSDE.sample (cleandiffuser/diffusion/diffusionsde.py:401-606,
+ * :743-952) calling model["diffusion"](x_t, t, cond) -> ATen kernels once per op.  This header is the
+ * boundary a maintainer would bind instead (ctypes stub in INTEGRATION.md): the per-iteration work of that
+ * loop is described ONCE as a short program of fused operators, and the engine replays the program for
+ * all reverse iterations from a CUDA graph with x_t resident on the device and no host round trip.
+ *
+ *   operator            replaces (reference file:line)
+ *   ------------------  ------------------------------------------------------------------------------
+ *   CDS_OP_CONV         nn.Conv1d / ConvTranspose1d / Linear (+bias) followed by GroupNorm1d + Mish, the
+ *                       time/FiLM conditioning and the residual add of a ResidualBlock / ChiResidualBlock
+ *                       (nn_diffusion/jannerunet.py:21-36,52-69, chiunet.py:13-45, utils/building_blocks.py:60-76),
+ *                       the Linear(+Mish/SiLU/GELU) layers of DQLMlp and DiT1d (dqlmlp.py:22-29, dit.py:25-29,43-45)
+ *   CDS_OP_LNMOD        LayerNorm(no affine) + adaLN modulate (dit.py:10-11,19,21,33,35,49)
+ *   CDS_OP_ATTN         nn.MultiheadAttention core softmax(QK^T/sqrt(hd))V per (trajectory, head) (dit.py:20,34)
+ *   CDS_OP_PREP         consistency-model re-noise + c_in pre-scale (consistency_model.py:257,423)
+ *   CDS_OP_UPDATE       CFG combine, clip_prediction, eps<->x0 conversion, the 8 solver updates, fix_mask
+ *                       (diffusionsde.py:202,208-223,539-592) and the CM skip/out combine (consistency_model.py:257-262)
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative cds_status otherwise; cds_last_error() gives the
+ *    message (thread local).  No C++ exception or Python object crosses this ABI.
+ *  - all pointers inside operator descriptors are DEVICE pointers owned by the caller (weights are the
+ *    caller's parameter storage or caller-allocated packed copies; activations live in a caller-allocated
+ *    workspace).  The library never allocates device memory on the hot path and never frees caller memory.
+ *  - activations are fp32, "channels last": element (b, l, c) of a (batch, L, C) tensor sits at
+ *    base + b*bstride + l*lstride + c (strides in floats), which is also the reference's public (b, horizon, dim)
+ *    layout, so x_t needs no permute on entry or exit.
+ *  - "per-iteration" operands are indexed by a device-resident iteration counter, so one captured graph
+ *    serves every reverse iteration:  vec(b, c) = step[iter*step_stride + c] + sample[b*sample_stride + c]
+ *    (either part may be NULL = 0).
+ *  - a plan is not thread safe; distinct plans may be used concurrently.  All work is enqueued on the
+ *    caller's stream (e.g. torch.cuda.current_stream()) and is asynchronous.
+ */
+#ifndef CDS_H_
+#define CDS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDS_ABI_VERSION 1
+
+typedef enum cds_status {
+  CDS_OK = 0,
+  CDS_ERR_INVALID = -1,      /* bad argument / unsupported shape (message says which) */
+  CDS_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+  CDS_ERR_UNSUPPORTED = -3,  /* valid request the kernels cannot serve; caller should fall back */
+  CDS_ERR_STATE = -4         /* call order violated (e.g. run before finalize) */
+} cds_status;
+
+typedef enum cds_op_kind { CDS_OP_CONV = 0, CDS_OP_UPDATE = 1, CDS_OP_LNMOD = 2, CDS_OP_ATTN = 3, CDS_OP_PREP = 4 } cds_op_kind;
+typedef enum cds_act { CDS_ACT_NONE = 0, CDS_ACT_MISH = 1, CDS_ACT_SILU = 2, CDS_ACT_GELU_TANH = 3,
+                       CDS_ACT_MISH_SILU = 4 /* silu(mish(x)): DiT's map_emb tail feeding every adaLN (dit.py:26,43,71) */ } cds_act;
+/* math mode of CDS_OP_CONV: fp32 CUDA-core FMA (bit-faithful to the fp32 oracle up to summation order), or
+ * tcgen05 tensor cores with bf16 operands / fp32 TMEM accumulation */
+typedef enum cds_math { CDS_MATH_FP32 = 0, CDS_MATH_BF16_TC = 1 } cds_math;
+/* update shapes; must match cleandiffuser_b200/diffusion/solvers.py */
+typedef enum cds_update_kind { CDS_UPD_DDPM = 0, CDS_UPD_DDIM = 1, CDS_UPD_EPS = 2, CDS_UPD_X = 3, CDS_UPD_X2M = 4, CDS_UPD_CM = 5 } cds_update_kind;
+
+/* per-iteration coefficient row (floats), one row per reverse iteration */
+enum { CDS_ROW_ALPHA = 0, CDS_ROW_SIGMA = 1, CDS_ROW_K0 = 2, CDS_ROW_K1 = 3, CDS_ROW_K2 = 4, CDS_ROW_K3 = 5,
+       CDS_ROW_K4 = 6, CDS_ROW_KIND = 7, CDS_ROW_NOISE = 8 /* 1 + noise slot, 0 = no draw */, CDS_ROW_T = 9,
+       CDS_ROW_FLOATS = 12 };
+
+/* vec(b, c) = step[iter*step_stride + c] + sample[b*sample_stride + c] */
+typedef struct cds_vec {
+  const float* step;   int64_t step_stride;
+  const float* sample; int64_t sample_stride;
+} cds_vec;
+
+/* Fused 1-D convolution / linear layer as an implicit GEMM over rows (b, l_out):
+ *   acc(b,l,n)  = sum_{tap,ci} in(b, l*stride + tap - pad, ci) * w[tap][ci][n]          (zero outside [0, L_in))
+ *   y = acc + bias(b,n)
+ *   if groups > 0:  y = GroupNorm(y; stats over L_out x (C_out/groups) per (b, group)) * gamma + beta
+ *   y = act(y)
+ *   y = y * scale(b,n) + shift(b,n)                 (each optional)
+ *   y += res(b,l,n)                                  (identity shortcut, optional)
+ *   y += sum_ci res_in(b,l,ci) * res_w[ci][n] + res_bias[n]   (1x1-conv shortcut, optional)
+ *   out(b, l*phases + n / C_out, n % C_out) = y      (phases = 2 writes a stride-2 transposed conv's two
+ *                                                     output phases; N = C_out*phases columns in w)           */
+typedef struct cds_conv_op {
+  int32_t batch, L_in, L_out, C_in, C_out, taps, stride, pad, phases;
+  int32_t in_batch_mod;            /* >0: read in() at batch index b % in_batch_mod (CFG branches share x_t) */
+  const float* in;  int64_t in_bstride;  int32_t in_lstride;
+  const void*  w;                  /* fp32 [taps*C_in][C_out*phases]  (CDS_MATH_FP32)  */
+  cds_vec bias;
+  int32_t groups; const float* gn_gamma; const float* gn_beta; float gn_eps;
+  int32_t act;
+  cds_vec scale, shift;
+  const float* res; int64_t res_bstride; int32_t res_lstride; int32_t res_batch_mod;
+  const float* res_in; int64_t res_in_bstride; int32_t res_in_lstride; int32_t res_C;
+  const void* res_w; const float* res_bias;
+  float* out; int64_t out_bstride; int32_t out_lstride;
+  int32_t math;                    /* cds_math */
+} cds_conv_op;
+
+/* out(b,l,:) = LayerNorm(in(b,l,:), eps, no affine) * (1 + scale(b,:)) + shift(b,:) */
+typedef struct cds_lnmod_op {
+  int32_t batch, L, C; float eps;
+  const float* in; float* out;                  /* dense (batch, L, C) */
+  const float* shift; const float* scale; int64_t mod_bstride;   /* per-trajectory vectors */
+} cds_lnmod_op;
+
+/* qkv dense (batch, L, 3*C) with [q | k | v] column blocks, heads split C evenly; out dense (batch, L, C) */
+typedef struct cds_attn_op {
+  int32_t batch, L, C, heads;
+  const float* qkv; float* out;
+} cds_attn_op;
+
+/* consistency model: if row.NOISE: x += K2 * noise[slot];  xin = K3 * x */
+typedef struct cds_prep_op {
+  int32_t batch, row;
+  float* x; float* xin; const float* noise; const float* coef;
+} cds_prep_op;
+
+/* One reverse-process update on x (batch, row) in place; `coef` is the [n_iters][CDS_ROW_FLOATS] table.
+ *   p = w_cfg*pred + w_uncond*pred_uncond       (if pred_uncond; w_uncond = 1-w_cfg)
+ *   p = clip(p)  (eps-prediction: to [(x-alpha*x_max)/sigma, (x-alpha*x_min)/sigma]; x0-prediction: [x_min,x_max])
+ *   x <- solver update of kind row.KIND with noise slot row.NOISE  ;  x = x*(1-mask) + prior*mask            */
+typedef struct cds_update_op {
+  int32_t batch, row;
+  float* x;
+  const float* pred; const float* pred_uncond; float w_cfg; float w_uncond;  /* w and (1-w), both rounded from double by the host */
+  const float* noise;            /* [n_slots][batch][row] pre-drawn N(0,1) */
+  const float* prior; const float* mask;      /* mask: `row` floats or NULL */
+  const float* x_min; const float* x_max;     /* `row` floats or NULL */
+  float* xhat_prev;              /* (batch,row) history for the 2M solvers or NULL */
+  const float* coef;
+  int32_t predict_noise;
+  int32_t final_clip;            /* CM only: clip the combined prediction to [x_min, x_max] */
+} cds_update_op;
+
+typedef struct cds_op {
+  int32_t kind;                  /* cds_op_kind */
+  int32_t reserved;
+  union { cds_conv_op conv; cds_update_op update; cds_lnmod_op lnmod; cds_attn_op attn; cds_prep_op prep; } u;
+} cds_op;
+
+typedef struct cds_plan cds_plan;
+
+int         cds_version(void);
+/* sizeof(cds_op) as compiled into the library -- bindings assert their struct mirror against it */
+int         cds_op_size(void);
+const char* cds_last_error(void);
+/* number of SMs etc. of `device`, -1 on error; used by the host to size workspaces */
+int         cds_device_sm_count(int device);
+
+/* A plan = the per-iteration operator program for one (model, shape, option set) on one device. */
+int cds_plan_create(int device, cds_plan** out);
+int cds_plan_destroy(cds_plan* plan);
+/* Append operators (copied).  Pointers inside must stay valid until the plan is destroyed or rebuilt. */
+int cds_plan_append(cds_plan* plan, const cds_op* ops, int32_t n_ops);
+/* Validate shapes, choose kernels, allocate the 4-byte device iteration counter. n_iters = rows in coef tables. */
+int cds_plan_finalize(cds_plan* plan, int32_t n_iters);
+/* Enqueue iterations [first, first+count) on `stream` (a cudaStream_t).  The first call captures the
+ * program into a CUDA graph; later calls replay it.  use_graph = 0 launches kernels directly (debug/ncu). */
+int cds_plan_run(cds_plan* plan, int32_t first, int32_t count, void* stream, int32_t use_graph);
+/* Run iteration `iter` once with direct launches, bracketing every operator with CUDA events on `stream`;
+ * ms_per_op[i] receives the device time of operator i (n_ops entries).  Synchronises `stream`.  For bench.py's
+ * live per-kernel roofline; note that it advances x_t like a normal iteration. */
+int cds_plan_profile(cds_plan* plan, int32_t iter, void* stream, float* ms_per_op, int32_t n_ops);
+/* Number of kernel launches one iteration of the program performs (for bench.py's gpu_launches). */
+int cds_plan_launches_per_iter(const cds_plan* plan);
+
+/* Stand-alone operator launch (parity tests of single kernels): runs `op` once with iteration index `iter`. */
+int cds_run_op(int device, const cds_op* op, int32_t iter, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDS_H_ */

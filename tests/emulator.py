@@ -1,0 +1,202 @@
+"""TEST INFRASTRUCTURE: a numpy interpreter of the libcds operator program (include/cds.h semantics).
+
+It lets the CPU test-suite execute the *lowered* program (``engine/lower.py`` output, with CPU tensors behind
+the raw pointers) and compare it with the reference goldens, so that lowering bugs (wrong strides, offsets,
+table columns, phase packing ...) are caught here without a GPU; the kernels themselves are then checked
+against the same goldens on the B200.  Never imported by the product.
+"""
+import ctypes
+
+import numpy as np
+
+from cleandiffuser_b200.engine import cabi
+
+
+def _arr(ptr, shape, strides):
+    """float32 view of raw memory; strides in floats."""
+    if not ptr:
+        return None
+    extent = 1 + sum((s - 1) * abs(st) for s, st in zip(shape, strides))
+    flat = np.ctypeslib.as_array((ctypes.c_float * extent).from_address(ptr))
+    return np.lib.stride_tricks.as_strided(flat, shape=shape, strides=[4 * s for s in strides])
+
+
+def _vec(v, it, rows, n):
+    out = np.zeros((rows, n), dtype=np.float32)
+    present = False
+    if v.step:
+        out += _arr(v.step + 4 * it * v.step_stride, (n,), (1,))[None]
+        present = True
+    if v.sample:
+        out += _arr(v.sample, (rows, n), (v.sample_stride, 1))
+        present = True
+    return out if present else None
+
+
+def _mish(x):
+    sp = np.where(x > 20, x, np.log1p(np.exp(np.minimum(x, 20))))
+    return x * np.tanh(sp)
+
+
+def _act(kind, x):
+    if kind == cabi.ACT_MISH:
+        return _mish(x)
+    if kind == cabi.ACT_SILU:
+        return x / (1 + np.exp(-x))
+    if kind == cabi.ACT_GELU_TANH:
+        return 0.5 * x * (1 + np.tanh(0.7978845608028654 * (x + 0.044715 * x ** 3)))
+    if kind == cabi.ACT_MISH_SILU:
+        m = _mish(x)
+        return m / (1 + np.exp(-m))
+    return x
+
+
+def run_conv(c, it):
+    B, N = c.batch, c.C_out * c.phases
+    bmod = c.in_batch_mod if c.in_batch_mod > 0 else B
+    xin = _arr(c.in_, (bmod, c.L_in, c.C_in), (c.in_bstride, c.in_lstride, 1))
+    xin = xin[np.arange(B) % bmod]
+    w = _arr(c.w, (c.taps, c.C_in, N), (c.C_in * N, N, 1))
+    acc = np.zeros((B, c.L_out, N), dtype=np.float64)
+    for tap in range(c.taps):
+        for l in range(c.L_out):
+            pos = l * c.stride + tap - c.pad
+            if 0 <= pos < c.L_in:
+                acc[:, l, :] += xin[:, pos, :].astype(np.float64) @ w[tap].astype(np.float64)
+    y = acc.astype(np.float32)
+    chan = np.arange(N) % c.C_out
+    bias = _vec(c.bias, it, B, c.C_out)
+    if bias is not None:
+        y = y + bias[:, None, chan]
+    if c.groups > 0:
+        assert c.phases == 1
+        g = y.reshape(B, c.L_out, c.groups, c.C_out // c.groups).astype(np.float64)
+        mean = g.mean(axis=(1, 3), keepdims=True)
+        var = g.var(axis=(1, 3), keepdims=True)
+        g = (g - mean) / np.sqrt(var + c.gn_eps)
+        y = g.reshape(B, c.L_out, c.C_out).astype(np.float32)
+        y = y * _arr(c.gn_gamma, (c.C_out,), (1,)) + _arr(c.gn_beta, (c.C_out,), (1,))
+    y = _act(c.act, y.astype(np.float32)).astype(np.float32)
+    scale, shift = _vec(c.scale, it, B, c.C_out), _vec(c.shift, it, B, c.C_out)
+    if scale is not None:
+        y = y * scale[:, None, chan]
+    if shift is not None:
+        y = y + shift[:, None, chan]
+    rmod = c.res_batch_mod if c.res_batch_mod > 0 else B
+    if c.res:
+        assert c.phases == 1
+        r = _arr(c.res, (rmod if c.res_bstride else 1, c.L_out, c.C_out), (c.res_bstride, c.res_lstride, 1))
+        y = y + r[(np.arange(B) % rmod) if c.res_bstride else np.zeros(B, dtype=int)]
+    if c.res_w:
+        rin = _arr(c.res_in, (rmod, c.L_out, c.res_C), (c.res_in_bstride, c.res_in_lstride, 1))[np.arange(B) % rmod]
+        rw = _arr(c.res_w, (c.res_C, N), (N, 1))
+        y = y + (rin.astype(np.float64) @ rw.astype(np.float64)).astype(np.float32)
+        if c.res_bias:
+            y = y + _arr(c.res_bias, (c.C_out,), (1,))[chan]
+    out = _arr(c.out, (B, c.L_out * c.phases, c.C_out), (c.out_bstride, c.out_lstride, 1))
+    out[...] = y.reshape(B, c.L_out, c.phases, c.C_out).reshape(B, c.L_out * c.phases, c.C_out)
+
+
+def run_lnmod(m):
+    x = _arr(m.in_, (m.batch, m.L, m.C), (m.L * m.C, m.C, 1)).astype(np.float64)
+    mu, var = x.mean(-1, keepdims=True), x.var(-1, keepdims=True)
+    n = (x - mu) / np.sqrt(var + m.eps)
+    sh = _arr(m.shift, (m.batch, m.C), (m.mod_bstride, 1))[:, None]
+    sc = _arr(m.scale, (m.batch, m.C), (m.mod_bstride, 1))[:, None]
+    _arr(m.out, (m.batch, m.L, m.C), (m.L * m.C, m.C, 1))[...] = (n * (1 + sc) + sh).astype(np.float32)
+
+
+def run_attn(a):
+    hd = a.C // a.heads
+    qkv = _arr(a.qkv, (a.batch, a.L, 3, a.heads, hd), (a.L * 3 * a.C, 3 * a.C, a.C, hd, 1)).astype(np.float64)
+    q, k, v = (qkv[:, :, i].transpose(0, 2, 1, 3) for i in range(3))        # (b, h, L, hd)
+    s = q @ k.transpose(0, 1, 3, 2) / np.sqrt(hd)
+    s = np.exp(s - s.max(-1, keepdims=True))
+    s /= s.sum(-1, keepdims=True)
+    o = (s @ v).transpose(0, 2, 1, 3).reshape(a.batch, a.L, a.C)
+    _arr(a.out, (a.batch, a.L, a.C), (a.L * a.C, a.C, 1))[...] = o.astype(np.float32)
+
+
+def _row(coef, it):
+    return _arr(coef + 4 * it * cabi.ROW_FLOATS, (cabi.ROW_FLOATS,), (1,))
+
+
+def run_prep(p, it):
+    row = _row(p.coef, it)
+    n = p.batch * p.row
+    x = _arr(p.x, (n,), (1,))
+    slot = int(row[8]) - 1
+    if slot >= 0:
+        x[...] = x + row[4] * _arr(p.noise + 4 * slot * n, (n,), (1,))
+    _arr(p.xin, (n,), (1,))[...] = row[5] * x
+
+
+def run_update(u, it):
+    f = np.float32
+    row = _row(u.coef, it)
+    alpha, sigma, k0, k1, k2, k3, k4 = (f(row[i]) for i in range(7))
+    kind, slot = int(row[7]), int(row[8]) - 1
+    n = u.batch * u.row
+    x = _arr(u.x, (u.batch, u.row), (u.row, 1))
+    pr = _arr(u.pred, (u.batch, u.row), (u.row, 1)).copy()
+    if u.pred_uncond:
+        pr = f(u.w_cfg) * pr + f(u.w_uncond) * _arr(u.pred_uncond, (u.batch, u.row), (u.row, 1))
+    xmin = _arr(u.x_min, (u.row,), (1,)) if u.x_min else None
+    xmax = _arr(u.x_max, (u.row,), (1,)) if u.x_max else None
+    z = _arr(u.noise + 4 * slot * n, (u.batch, u.row), (u.row, 1)) if slot >= 0 else None
+    if kind == 5:
+        out = k0 * x + k1 * pr
+        if u.final_clip:
+            if xmin is not None:
+                out = np.maximum(out, xmin)
+            if xmax is not None:
+                out = np.minimum(out, xmax)
+    else:
+        if u.predict_noise:
+            if xmax is not None:
+                pr = np.maximum(pr, (x - alpha * xmax) / sigma)
+            if xmin is not None:
+                pr = np.minimum(pr, (x - alpha * xmin) / sigma)
+            eps, xhat = pr, (x - sigma * pr) / alpha
+        else:
+            if xmin is not None:
+                pr = np.maximum(pr, xmin)
+            if xmax is not None:
+                pr = np.minimum(pr, xmax)
+            xhat, eps = pr, (x - alpha * pr) / sigma
+        if kind == 0:
+            out = k0 * (x - sigma * eps) + k1 * eps
+            if z is not None:
+                out = out + k2 * z
+        elif kind == 1:
+            out = k0 * ((x - sigma * eps) / alpha) + k1 * eps
+        else:
+            hist = _arr(u.xhat_prev, (u.batch, u.row), (u.row, 1)) if u.xhat_prev else None
+            target = eps if kind == 2 else (k3 * xhat - k4 * hist if kind == 4 else xhat)
+            out = k0 * x - k1 * target
+            if z is not None:
+                out = out + k2 * z
+            if hist is not None:
+                hist[...] = xhat
+    if u.mask:
+        m = _arr(u.mask, (u.row,), (1,))
+        out = out * (f(1) - m) + _arr(u.prior, (u.batch, u.row), (u.row, 1)) * m
+    x[...] = out.astype(np.float32)
+
+
+def run_program(ops, n_iters, first=0):
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        for it in range(first, first + n_iters):
+            for op in ops:
+                if op.kind == cabi.OP_CONV:
+                    run_conv(op.u.conv, it)
+                elif op.kind == cabi.OP_UPDATE:
+                    run_update(op.u.update, it)
+                elif op.kind == cabi.OP_LNMOD:
+                    run_lnmod(op.u.lnmod)
+                elif op.kind == cabi.OP_ATTN:
+                    run_attn(op.u.attn)
+                elif op.kind == cabi.OP_PREP:
+                    run_prep(op.u.prep, it)
+                else:
+                    raise ValueError(op.kind)

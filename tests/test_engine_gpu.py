@@ -1,0 +1,148 @@
+"""Parity of the CUDA engine (through the C ABI) against the golden vectors of the reference and the
+CPU oracle.  Everything here needs a B200: run with ``-m gpu``."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import oracle.sampler as osamp
+from common import oracle_cond_emb, oracle_net, product_net, tape_of
+from test_host_golden import build_agent
+from cleandiffuser_b200.diffusion import ContinuousConsistencyModel, DiscreteDiffusionSDE
+from cleandiffuser_b200.engine import cabi, runtime
+from cleandiffuser_b200.nn_condition import IdentityCondition
+from cleandiffuser_b200.nn_diffusion import JannerUNet1d
+from cleandiffuser_b200.testing import NoiseTape, load_synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# fp32 CUDA-core path: same arithmetic as the fp32 oracle up to summation order / libm rounding
+NET_ATOL = 2e-4
+SAMPLER_ATOL, SAMPLER_RTOL = 1e-3, 1e-3
+
+
+@pytest.fixture(autouse=True)
+def _force_engine(monkeypatch):
+    monkeypatch.setenv("CDS_BACKEND", "cuda")      # a fallback to PyTorch is a test failure, not a pass
+    monkeypatch.setenv("CDS_MATH", "fp32")
+
+
+def test_library_loaded_from_tree():
+    lib = cabi.load()
+    assert os.path.samefile(cabi.lib_path(), os.path.join(os.path.dirname(cabi.__file__), "..", "csrc", "libcds.so"))
+    assert lib.cds_version() == cabi.ABI_VERSION
+    assert lib.cds_device_sm_count(0) > 0
+
+
+@pytest.mark.parametrize("name", list(cases.NETS))
+def test_denoiser_forward_matches_reference(golden, name):
+    case = cases.NETS[name]
+    net, sd = product_net(case)
+    net = net.to(DEV)
+    x, t, cond = cases.net_inputs(case)
+    cond_emb = None if cond is None else cond.to(DEV)
+    want = golden["nets"][name + "/y"]
+    for i in range(cases.NET_BATCH):                       # inside sample() t is batch-constant: one run per t
+        y = runtime.engine_forward(net, x.to(DEV), t[i:i + 1], cond_emb)
+        np.testing.assert_allclose(y[i].cpu().numpy(), want[i], rtol=0, atol=NET_ATOL, err_msg=f"{name} row {i}")
+
+
+@pytest.mark.parametrize("name", list(cases.sampler_cases()))
+def test_sampler_matches_reference(golden, name):
+    spec = cases.sampler_cases()[name]
+    agent, inp, kw = build_agent(spec, device=DEV)
+    for k in ("condition_cfg", "warm_start_reference"):
+        if kw.get(k) is not None:
+            kw[k] = kw[k].to(DEV)
+    before = runtime.STATS["engine_calls"]
+    tape = NoiseTape(tape_of(golden["samplers"], name))
+    with tape.active(), torch.no_grad():
+        x0, log = agent.sample(inp["prior"].to(DEV), **kw)
+    assert runtime.STATS["engine_calls"] == before + 1, runtime.STATS
+    assert tape.pos == len(tape.draws)
+    assert x0.device.type == "cuda" and log["sample_history"] is None
+    np.testing.assert_allclose(x0.cpu().numpy(), golden["samplers"][name + "/x0"], rtol=SAMPLER_RTOL, atol=SAMPLER_ATOL)
+
+
+@pytest.mark.parametrize("steps", [1, 3])
+def test_consistency_matches_reference(golden, steps):
+    g = golden["consistency"]
+    net, _ = product_net(cases.NETS["chi_cm_fourier"])
+    cm = ContinuousConsistencyModel(net, IdentityCondition(dropout=0.0), x_max=torch.ones(1, 8, 3),
+                                    x_min=-torch.ones(1, 8, 3), device=DEV)
+    tape = NoiseTape(tape_of(g, f"cm{steps}"))
+    before = runtime.STATS["engine_calls"]
+    with tape.active(), torch.no_grad():
+        x0, _ = cm.sample(torch.zeros(4, 8, 3, device=DEV), n_samples=4, sample_steps=steps,
+                          condition_cfg=torch.as_tensor(g[f"cm{steps}/cond"]).to(DEV), w_cfg=1.0)
+    assert runtime.STATS["engine_calls"] == before + 1
+    np.testing.assert_allclose(x0.cpu().numpy(), g[f"cm{steps}/x0"], rtol=SAMPLER_RTOL, atol=SAMPLER_ATOL)
+
+
+def _cfg2_agent(T):
+    net = load_synth(JannerUNet1d(14, model_dim=32, emb_dim=32, kernel_size=5, dim_mult=[1, 2, 2, 2]), seed=0)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    mask = torch.zeros(32, 14)
+    mask[0, :11] = 1.
+    return DiscreteDiffusionSDE(net, None, fix_mask=mask, predict_noise=False, diffusion_steps=T, device=DEV), sd, mask
+
+
+def test_cfg2_full_batch_properties_and_oracle():
+    """BASELINE config 2 shapes (B=4096, H=32, d=14; 10 DDPM steps to keep the oracle leg short):
+    size-independent properties at full batch + oracle comparison on a slice."""
+    T, B = 10, 4096
+    agent, sd, mask = _cfg2_agent(T)
+    g = torch.Generator().manual_seed(1)
+    prior = torch.zeros(B, 32, 14)
+    prior[:, 0, :11] = torch.randn(B, 11, generator=g)
+    tape = NoiseTape()
+    with tape.active(), torch.no_grad():
+        x_full, _ = agent.sample(prior.to(DEV), solver="ddpm", n_samples=B, sample_steps=T, temperature=0.5)
+    x_full = x_full.cpu()
+    assert torch.isfinite(x_full).all()
+    # (a) the fixed portion is re-imposed exactly
+    assert torch.equal(x_full[:, 0, :11], prior[:, 0, :11])
+    # (b) trajectories are independent: a 96-row sub-batch with the same noise gives the same bits
+    sub = slice(1000, 1096)
+    tape_sub = NoiseTape([z[sub] for z in tape.draws])
+    with tape_sub.active(), torch.no_grad():
+        x_sub, _ = agent.sample(prior[sub].to(DEV), solver="ddpm", n_samples=96, sample_steps=T, temperature=0.5)
+    assert torch.equal(x_sub.cpu(), x_full[sub])
+    # (c) oracle on 16 trajectories
+    pick = slice(2040, 2056)
+    fn = oracle_net(cases.NETS["janner_cfg2"], sd)
+    with torch.no_grad():
+        x_ref = osamp.sample_discrete(fn, prior[pick], osamp.Tape([z[pick].numpy() for z in tape.draws]), T=T, steps=T,
+                                      solver="ddpm", temperature=0.5, fix_mask=mask[None], predict_noise=False)
+    np.testing.assert_allclose(x_full[pick].numpy(), x_ref.numpy(), rtol=SAMPLER_RTOL, atol=SAMPLER_ATOL)
+
+
+def test_weights_refresh_after_training_step():
+    """Training mutates parameters behind the plan's back; the packed copies must follow."""
+    spec = cases.sampler_cases()["disc_dx_ddpm_eps"]
+    agent, inp, kw = build_agent(spec, device=DEV)
+    kw["condition_cfg"] = kw["condition_cfg"].to(DEV)
+    kw["use_ema"] = False
+    agent.model.eval()
+
+    def run(backend):
+        os.environ["CDS_BACKEND"] = backend
+        torch.manual_seed(7)
+        with torch.no_grad():
+            return agent.sample(inp["prior"].to(DEV), **kw)[0]
+
+    a0 = run("cuda")
+    with torch.no_grad():
+        for p in agent.model["diffusion"].parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    a1, t1 = run("cuda"), run("torch")
+    assert (a1 - a0).abs().max() > 1e-4
+    np.testing.assert_allclose(a1.cpu().numpy(), t1.cpu().numpy(), rtol=SAMPLER_RTOL, atol=SAMPLER_ATOL)
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()

@@ -1,0 +1,76 @@
+"""Execute the lowered operator programs with the numpy interpreter (tests/emulator.py) on CPU tensors and
+compare with the reference goldens: pins ``engine/lower.py`` + ``engine/runtime.py`` (strides, table columns,
+phase packing, CFG row doubling, noise slots, coefficient rows) without needing a GPU."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import emulator
+from common import product_net, tape_of
+from test_host_golden import build_agent
+from cleandiffuser_b200.diffusion import ContinuousConsistencyModel
+from cleandiffuser_b200.engine import runtime
+from cleandiffuser_b200.nn_condition import IdentityCondition
+from cleandiffuser_b200.testing import NoiseTape
+
+
+class EmuHandle:
+    def __init__(self, ops, n_iters):
+        self.ops, self.n_iters = list(ops), n_iters
+
+    def run(self, first, count, stream, use_graph=True):
+        emulator.run_program(self.ops, count, first)
+
+    def launches_per_iter(self):
+        return len(self.ops) + 1
+
+    def close(self):
+        pass
+
+
+@pytest.fixture(autouse=True)
+def _emulate(monkeypatch):
+    monkeypatch.setattr(runtime, "_device_ok", lambda device: True)
+    monkeypatch.setattr(runtime, "_make_handle", lambda device, ops, n: EmuHandle(ops, n))
+    monkeypatch.setenv("CDS_BACKEND", "cuda")       # any fallback to the PyTorch loop is a failure here
+    monkeypatch.setenv("CDS_MATH", "fp32")
+
+
+@pytest.mark.parametrize("name", list(cases.NETS))
+def test_lowered_denoiser(golden, name):
+    case = cases.NETS[name]
+    net, _ = product_net(case)
+    x, t, cond = cases.net_inputs(case)
+    want = golden["nets"][name + "/y"]
+    for i in range(cases.NET_BATCH):
+        y = runtime.engine_forward(net, x, t[i:i + 1], cond)
+        np.testing.assert_allclose(y[i].numpy(), want[i], rtol=0, atol=2e-5, err_msg=f"{name} row {i}")
+
+
+@pytest.mark.parametrize("name", list(cases.sampler_cases()))
+def test_lowered_sampler(golden, name):
+    spec = cases.sampler_cases()[name]
+    agent, inp, kw = build_agent(spec)
+    before = runtime.STATS["engine_calls"]
+    tape = NoiseTape(tape_of(golden["samplers"], name))
+    with tape.active(), torch.no_grad():
+        x0, _ = agent.sample(inp["prior"], **kw)
+    assert runtime.STATS["engine_calls"] == before + 1
+    assert tape.pos == len(tape.draws)
+    np.testing.assert_allclose(x0.numpy(), golden["samplers"][name + "/x0"], rtol=1e-4, atol=3e-4)
+
+
+@pytest.mark.parametrize("steps", [1, 3])
+def test_lowered_consistency(golden, steps):
+    g = golden["consistency"]
+    net, _ = product_net(cases.NETS["chi_cm_fourier"])
+    cm = ContinuousConsistencyModel(net, IdentityCondition(dropout=0.0), x_max=torch.ones(1, 8, 3),
+                                    x_min=-torch.ones(1, 8, 3), device="cpu")
+    tape = NoiseTape(tape_of(g, f"cm{steps}"))
+    before = runtime.STATS["engine_calls"]
+    with tape.active(), torch.no_grad():
+        x0, _ = cm.sample(torch.zeros(4, 8, 3), n_samples=4, sample_steps=steps,
+                          condition_cfg=torch.as_tensor(g[f"cm{steps}/cond"]), w_cfg=1.0)
+    assert runtime.STATS["engine_calls"] == before + 1
+    np.testing.assert_allclose(x0.numpy(), g[f"cm{steps}/x0"], rtol=1e-4, atol=3e-4)
