@@ -10,6 +10,7 @@
 #include "cds.h"
 #include "attention.cuh"
 #include "conv_simt.cuh"
+#include "conv_tc.cuh"
 #include "elementwise.cuh"
 
 namespace {
@@ -35,6 +36,8 @@ int fail(int code, const char* fmt, ...) {
 struct Step {            // one validated operator + its kernel choice
   cds_op op;
   int conv_bn = 0;
+  bool tc = false;       // tensor-core conv: tensor maps + launch geometry prepared at append time
+  cds::ConvTcLaunch tcl;
 };
 
 int elementwise_grid(int64_t total, int sm_count) {
@@ -56,7 +59,15 @@ int validate(const cds_op& op, Step* out) {
       if (c.groups > 0 && (!c.gn_gamma || !c.gn_beta)) return fail(CDS_ERR_INVALID, "conv: GroupNorm without affine");
       if (c.res_w && (!c.res_in || c.res_C <= 0)) return fail(CDS_ERR_INVALID, "conv: shortcut conv without input");
       if (c.res_w && (c.stride != 1 || c.phases != 1)) return fail(CDS_ERR_INVALID, "conv: shortcut conv needs stride 1");
-      if (c.math != CDS_MATH_FP32) return fail(CDS_ERR_UNSUPPORTED, "conv: math mode %d not built", c.math);
+      if (c.math == CDS_MATH_BF16_TC) {
+        if (!cds::conv_tc_eligible(c))
+          return fail(CDS_ERR_INVALID, "conv: op is not eligible for the tensor-core kernel (ask cds_conv_tc_supported)");
+        if (!cds::conv_tc_prepare(c, &out->tcl))
+          return fail(CDS_ERR_CUDA, "conv: cuTensorMapEncodeTiled failed (C_in=%d L=%d C_out=%d)", c.C_in, c.L_in, c.C_out);
+        out->tc = true;
+        return CDS_OK;
+      }
+      if (c.math != CDS_MATH_FP32) return fail(CDS_ERR_UNSUPPORTED, "conv: math mode %d unknown", c.math);
       out->conv_bn = cds::conv_simt_pick_bn(c);
       if (out->conv_bn == 0)
         return fail(CDS_ERR_UNSUPPORTED, "conv: GroupNorm tile does not fit (L_out=%d C_out=%d groups=%d)", c.L_out,
@@ -97,7 +108,8 @@ int validate(const cds_op& op, Step* out) {
 int launch(const Step& s, const int* iter_ptr, int sm_count, cudaStream_t st) {
   switch (s.op.kind) {
     case CDS_OP_CONV:
-      CDS_CUDA(cds::conv_simt_launch(s.op.u.conv, s.conv_bn, iter_ptr, st));
+      if (s.tc) CDS_CUDA(cds::conv_tc_launch(s.tcl, iter_ptr, st));
+      else CDS_CUDA(cds::conv_simt_launch(s.op.u.conv, s.conv_bn, iter_ptr, st));
       return CDS_OK;
     case CDS_OP_UPDATE: {
       const cds_update_op& u = s.op.u.update;
@@ -133,6 +145,14 @@ int preload_kernels() {
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<32>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<64>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<128>));
+  CDS_CUDA((cds::conv_tc_preload_t<64, 32, false>()));  CDS_CUDA((cds::conv_tc_preload_t<64, 32, true>()));
+  CDS_CUDA((cds::conv_tc_preload_t<64, 64, false>()));  CDS_CUDA((cds::conv_tc_preload_t<64, 64, true>()));
+  CDS_CUDA((cds::conv_tc_preload_t<64, 128, false>())); CDS_CUDA((cds::conv_tc_preload_t<64, 128, true>()));
+  CDS_CUDA((cds::conv_tc_preload_t<64, 256, false>())); CDS_CUDA((cds::conv_tc_preload_t<64, 256, true>()));
+  CDS_CUDA((cds::conv_tc_preload_t<32, 32, false>()));  CDS_CUDA((cds::conv_tc_preload_t<32, 32, true>()));
+  CDS_CUDA((cds::conv_tc_preload_t<32, 64, false>()));  CDS_CUDA((cds::conv_tc_preload_t<32, 64, true>()));
+  CDS_CUDA((cds::conv_tc_preload_t<32, 128, false>())); CDS_CUDA((cds::conv_tc_preload_t<32, 128, true>()));
+  CDS_CUDA((cds::conv_tc_preload_t<32, 256, false>())); CDS_CUDA((cds::conv_tc_preload_t<32, 256, true>()));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<16>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<32>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<64>));
@@ -163,6 +183,13 @@ extern "C" {
 int cds_version(void) { return CDS_ABI_VERSION; }
 int cds_op_size(void) { return (int)sizeof(cds_op); }
 const char* cds_last_error(void) { return g_err.c_str(); }
+
+int cds_conv_tc_supported(const cds_conv_op* op) {
+  if (!op) return 0;
+  cds_conv_op c = *op;
+  c.math = CDS_MATH_BF16_TC;
+  return cds::conv_tc_eligible(c) ? 1 : 0;
+}
 
 int cds_device_sm_count(int device) {
   int n = 0;

@@ -15,6 +15,8 @@
 // Algorithmic HBM bytes per launch: 4*(batch*L_in*C_in + batch*L_out*C_out*phases) (+ shortcut input, +weights
 // once per CTA column through L2).  The tcgen05 path (conv_tc.cuh) replaces the main loop; the epilogue is shared.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace cds {
@@ -24,8 +26,17 @@ constexpr int kBK = 16;       // depth per smem stage
 constexpr int kThreads = 256; // 16 x 16 thread grid, each thread an 8 x (BN/16) register tile
 constexpr int kAPad = 4;
 
+__device__ __forceinline__ float ld_act(const void* base, int64_t idx, int dtype) {
+  return dtype == CDS_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx])
+                           : __ldg(reinterpret_cast<const float*>(base) + idx);
+}
+__device__ __forceinline__ void st_act(void* base, int64_t idx, int dtype, float v) {
+  if (dtype == CDS_BF16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(base)[idx] = v;
+}
+
 struct ConvSrc {              // one im2col source (main conv, or the 1x1 shortcut)
-  const float* in; int64_t bstride; int lstride; int bmod;
+  const void* in; int dtype; int64_t bstride; int lstride; int bmod;
   int C, taps, stride, pad, L_in;
   const float* w;             // [taps*C][N]
 };
@@ -73,7 +84,7 @@ __device__ __forceinline__ void gemm_mainloop(const ConvSrc& s, float (&acc)[8][
     for (int j = 0; j < 8; ++j) {
       int pos = a_pos0[j] + tap;
       bool ok = kv && pos >= 0 && pos < s.L_in;
-      a_reg[j] = ok ? __ldg(s.in + a_base[j] + (int64_t)pos * s.lstride + ci) : 0.f;
+      a_reg[j] = ok ? ld_act(s.in, a_base[j] + (int64_t)pos * s.lstride + ci, s.dtype) : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < kBLoads; ++j) {
@@ -144,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_f32_kernel(const cds_conv_
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  ConvSrc main_src{p.in, p.in_bstride, p.in_lstride, p.in_batch_mod, p.C_in, p.taps, p.stride, p.pad, p.L_in,
+  ConvSrc main_src{p.in, p.in_dtype, p.in_bstride, p.in_lstride, p.in_batch_mod, p.C_in, p.taps, p.stride, p.pad, p.L_in,
                    reinterpret_cast<const float*>(p.w)};
   gemm_mainloop<BN>(main_src, acc, As, Bs, st_b, st_l, n0, N_total);
 
@@ -211,10 +222,10 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_f32_kernel(const cds_conv_
     if (shift.present()) v += shift.at(b, c);
     if (p.res) {
       int rb = p.res_batch_mod > 0 ? b % p.res_batch_mod : b;
-      v += __ldg(p.res + (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + c);
+      v += ld_act(p.res, (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + c, p.res_dtype);
     }
     if (second_gemm) Cs[m * (BN + 1) + n] = v;
-    else p.out[(int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + c] = v;
+    else st_act(p.out, (int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + c, p.out_dtype, v);
   }
   if (!second_gemm) return;
   __syncthreads();
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_f32_kernel(const cds_conv_
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  ConvSrc res_src{p.res_in, p.res_in_bstride, p.res_in_lstride, p.res_batch_mod, p.res_C, 1, 1, 0, p.L_out,
+  ConvSrc res_src{p.res_in, p.res_in_dtype, p.res_in_bstride, p.res_in_lstride, p.res_batch_mod, p.res_C, 1, 1, 0, p.L_out,
                   reinterpret_cast<const float*>(p.res_w)};
   gemm_mainloop<BN>(res_src, acc, As, Bs, st_b, st_l, n0, N_total);
 #pragma unroll
@@ -244,7 +255,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_f32_kernel(const cds_conv_
     if (r >= rows || ng >= N_total) continue;
     int b = r / p.L_out, l = r - b * p.L_out;
     int phase = ng / p.C_out, c = ng - phase * p.C_out;
-    p.out[(int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + c] = Cs[m * (BN + 1) + n];
+    st_act(p.out, (int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + c, p.out_dtype,
+           Cs[m * (BN + 1) + n]);
   }
 }
 

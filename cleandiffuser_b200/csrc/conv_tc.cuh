@@ -1,0 +1,424 @@
+// CDS_OP_CONV, tensor-core path (CDS_MATH_BF16_TC): implicit-GEMM 1-D convolution on tcgen05 with the UNet block
+// post-processing fused into the TMEM epilogue.
+//
+//   D[128 rows x N] (fp32, TMEM) = sum over (tap, 64- or 32-channel chunk) of  A_tap[128 x KC] * W_tap[N x KC]^T
+//
+// * rows = 128/L whole trajectories x L positions.  The im2col never exists: the A tile of tap j is ONE TMA box
+//   {KC channels, L positions, T trajectories} of the channels-last bf16 activation whose position coordinate starts at
+//   j - pad; positions outside [0, L) are zero-filled by the TMA unit (out-of-bound fill), which is exactly the conv's
+//   zero padding, and trajectories never bleed into each other because they are a separate tensor dimension.
+// * W_tap is a TMA box {KC, N} of the bf16 weight packed [tap][C_out][C_in]; both operands land in shared memory in the
+//   K-major SWIZZLE_128B (KC=64) / SWIZZLE_64B (KC=32) layout that tcgen05.mma consumes directly.
+// * warp roles: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warp 2 TMEM allocator,
+//   warps 4..11 epilogue.  smem ring of kStages, mbarrier full/empty pairs, one tcgen05.commit per stage.
+// * an optional second accumulator (TMEM columns N..2N) receives the 1x1 shortcut conv of a ResidualBlock.
+// * epilogue: thread = one output row (TMEM lane); GroupNorm statistics = in-thread sum over the group's columns +
+//   warp-shuffle reduction over the L lanes of the trajectory; then GN-affine, Mish, FiLM, residual, bf16/fp32 store.
+//
+// Algorithmic HBM bytes per launch: 2*(batch*L*C_in + batch*L*C_out) (+ shortcut input), weights once through L2.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace cds {
+
+constexpr int kTcThreads = 384;   // 12 warps: producer, mma, tmem-alloc, spare, 8 epilogue
+constexpr int kTcStages = 4;
+
+struct ConvTcParams {
+  CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
+  int batch, L, log2L, C_out, taps, pad;
+  int kchunks, kchunks2;          // channel chunks of the main conv / of the shortcut conv
+  int in_batch_mod;
+  cds_vec bias, scale, shift;
+  int groups; const float* gn_gamma; const float* gn_beta; float gn_eps;
+  int act;
+  const void* res; int64_t res_bstride; int res_lstride; int res_batch_mod; int res_dtype;
+  const float* res_bias;
+  void* out; int64_t out_bstride; int out_lstride; int out_dtype;
+};
+
+__device__ __forceinline__ float fast_mish(float x) {
+  // x * tanh(softplus(x)) with tanh(log(1+e)) = n/(n+2), n = e*(e+2), e = exp(x)
+  float e = __expf(fminf(x, 20.f));
+  float n = e * (e + 2.f);
+  return x > 20.f ? x : x * __fdividef(n, n + 2.f);
+}
+__device__ __forceinline__ float tc_act(int act, float x) {
+  switch (act) {
+    case CDS_ACT_MISH: return fast_mish(x);
+    case CDS_ACT_SILU: return x * __fdividef(1.f, 1.f + __expf(-x));
+    case CDS_ACT_GELU_TANH: return act_gelu_tanh(x);
+    case CDS_ACT_MISH_SILU: { float m = fast_mish(x); return m * __fdividef(1.f, 1.f + __expf(-m)); }
+    default: return x;
+  }
+}
+
+template <int KC, int N, bool HAS_RES>
+struct ConvTcCfg {
+  static constexpr int kRowBytes = KC * 2;
+  static constexpr int kABytes = 128 * kRowBytes;
+  static constexpr int kBBytes = N * kRowBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kTcStages * kStageBytes + 1024;
+  static constexpr uint32_t kTmemCols = (N * (HAS_RES ? 2 : 1)) < 32 ? 32 : (N * (HAS_RES ? 2 : 1));
+};
+
+template <int KC, int N, bool HAS_RES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ iter_ptr) {
+  using Cfg = ConvTcCfg<KC, N, HAS_RES>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kTcStages];
+  __shared__ __align__(8) uint64_t empty_bar[kTcStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_holder;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // operand ring, 1024-byte aligned (swizzle atoms)
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+
+  const int T = 128 >> p.log2L;                       // trajectories per tile
+  const int b0 = blockIdx.x * T;
+  const int n_kb_main = p.taps * p.kchunks;
+  const int n_kb = n_kb_main + (HAS_RES ? p.kchunks2 : 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    ptx::mbar_init(&tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.tm_a);
+    ptx::prefetch_tensormap(&p.tm_b);
+    if (HAS_RES) { ptx::prefetch_tensormap(&p.tm_a2); ptx::prefetch_tensormap(&p.tm_b2); }
+  }
+  if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (ptx::elect_one()) {
+      const int a_b0 = p.in_batch_mod > 0 ? b0 % p.in_batch_mod : b0;
+      const int r_b0 = p.res_batch_mod > 0 ? b0 % p.res_batch_mod : b0;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (kb / kTcStages) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem_al + s * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        ptx::mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        if (!HAS_RES || kb < n_kb_main) {
+          const int tap = kb / p.kchunks, ck = kb - tap * p.kchunks;
+          ptx::tma_load_3d(sa, &p.tm_a, &full_bar[s], ck * KC, tap - p.pad, a_b0);
+          ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KC, tap * p.C_out);
+        } else {
+          const int ck = kb - n_kb_main;
+          ptx::tma_load_3d(sa, &p.tm_a2, &full_bar[s], ck * KC, 0, r_b0);
+          ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], ck * KC, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, N);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (kb / kTcStages) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint64_t da = ptx::make_kmajor_desc<Cfg::kRowBytes>(sa);
+        const uint64_t db = ptx::make_kmajor_desc<Cfg::kRowBytes>(sa + Cfg::kABytes);
+        const bool second = HAS_RES && kb >= n_kb_main;
+        const uint32_t d_addr = tmem_base + (second ? (uint32_t)N : 0u);
+        const bool first_of_acc = second ? (kb == n_kb_main) : (kb == 0);
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k) {
+          // advancing 16 bf16 (32 B) along K inside the swizzle span = +2 in the (addr >> 4) field
+          ptx::umma_bf16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (first_of_acc && k == 0) ? 0u : 1u);
+        }
+        ptx::umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
+      }
+      ptx::umma_commit(&tmem_full_bar);           // accumulators complete
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue =====================================
+    const int iter = iter_ptr ? *iter_ptr : 0;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may touch
+    const int half = (warp - 4) >> 2;               // which half of the N columns
+    constexpr int NH = N / 2;                       // columns per thread
+    constexpr int CPG = N / 8;                      // GroupNorm group width (groups == 8)
+    constexpr int NCHUNK = NH / 16;
+    const int m = 32 * q + lane;
+    const int64_t row = (int64_t)blockIdx.x * 128 + m;
+    const bool valid = row < (int64_t)p.batch * p.L;
+    const int b = (int)(row >> p.log2L), l = (int)(row & (p.L - 1));
+    const int col0 = half * NH;
+    const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)col0;
+    const VecRef bias = resolve(p.bias, iter), scale = resolve(p.scale, iter), shift = resolve(p.shift, iter);
+    const bool has_bias = bias.present(), has_scale = scale.present(), has_shift = shift.present();
+
+    ptx::mbar_wait(&tmem_full_bar, 0);
+    ptx::tc_fence_after_sync();
+
+    float mean[4], rstd[4];
+    if (p.groups > 0) {
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        float v[16];
+        ptx::tmem_ld_32x32b_x16(t_row + ch * 16, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = ch * 16 + j;                // column inside this thread's half
+          float x = v[j] + (has_bias ? bias.at(b, col0 + c) : 0.f);
+          x = valid ? x : 0.f;
+          s1[c / CPG] += x;
+          s2[c / CPG] = fmaf(x, x, s2[c / CPG]);
+        }
+      }
+      // reduce over the L lanes (positions) of this trajectory
+      for (int off = p.L >> 1; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          s1[g] += __shfl_xor_sync(0xffffffffu, s1[g], off);
+          s2[g] += __shfl_xor_sync(0xffffffffu, s2[g], off);
+        }
+      }
+      const float inv_cnt = 1.f / (float)(p.L * CPG);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        mean[g] = s1[g] * inv_cnt;
+        float var = fmaxf(s2[g] * inv_cnt - mean[g] * mean[g], 0.f);
+        rstd[g] = rsqrtf(var + p.gn_eps);
+      }
+    }
+
+    const int rb = p.res_batch_mod > 0 ? b % p.res_batch_mod : b;
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      float v[16];
+      ptx::tmem_ld_32x32b_x16(t_row + ch * 16, v);
+      float r2[16];
+      if (HAS_RES) ptx::tmem_ld_32x32b_x16(t_row + N + ch * 16, r2);
+      if (valid) {
+        const int cbase = col0 + ch * 16;
+        float resv[16];
+        if (p.res) {
+          const int64_t ro = (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + cbase;
+          if (p.res_dtype == 1) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + ro);
+            uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
+              resv[2 * j] = f0.x; resv[2 * j + 1] = f0.y; resv[8 + 2 * j] = f1.x; resv[8 + 2 * j + 1] = f1.y;
+            }
+          } else {
+            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + ro);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 f = __ldg(rp + j);
+              resv[4 * j] = f.x; resv[4 * j + 1] = f.y; resv[4 * j + 2] = f.z; resv[4 * j + 3] = f.w;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = cbase + j;
+          float x = v[j] + (has_bias ? bias.at(b, c) : 0.f);
+          if (p.groups > 0) {
+            const int g = (ch * 16 + j) / CPG;
+            x = (x - mean[g]) * rstd[g];
+            x = fmaf(x, __ldg(p.gn_gamma + c), __ldg(p.gn_beta + c));
+          }
+          x = tc_act(p.act, x);
+          if (has_scale) x *= scale.at(b, c);
+          if (has_shift) x += shift.at(b, c);
+          if (p.res) x += resv[j];
+          if (HAS_RES) x += r2[j] + (p.res_bias ? __ldg(p.res_bias + c) : 0.f);
+          v[j] = x;
+        }
+        const int64_t oo = (int64_t)b * p.out_bstride + (int64_t)l * p.out_lstride + cbase;
+        if (p.out_dtype == 1) {
+          uint4 u0, u1;
+          __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&u0);
+          __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&u1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+          }
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + oo);
+          op[0] = u0; op[1] = u1;
+        } else {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oo);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+    ptx::tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor, dims innermost-first; strides in elements for dims 1.. (dim 0 is contiguous)
+inline bool encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                            const uint32_t* box, int kc) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], es[3];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_el[i - 1] * 2;
+  CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+inline int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
+
+// channel-chunk width: 64 (SWIZZLE_128B) when every K extent is a multiple of 64, else 32 (SWIZZLE_64B)
+inline int conv_tc_pick_kc(const cds_conv_op& c) {
+  bool k64 = (c.C_in % 64 == 0) && (!c.res_w || c.res_C % 64 == 0);
+  return k64 ? 64 : 32;
+}
+
+// can the tensor-core kernel serve this op?  (otherwise the fp32 CUDA-core kernel runs it, any dtype)
+inline bool conv_tc_eligible(const cds_conv_op& c) {
+  if (c.math != CDS_MATH_BF16_TC || c.in_dtype != 1) return false;
+  if (c.stride != 1 || c.phases != 1 || c.L_in != c.L_out) return false;
+  int L = c.L_out;
+  if (L > 32 || (L & (L - 1)) != 0) return false;
+  int N = c.C_out;
+  if (N != 32 && N != 64 && N != 128 && N != 256) return false;
+  if (c.C_in % 32 != 0) return false;
+  if (c.groups != 0 && c.groups != 8) return false;
+  int T = 128 / L;
+  if (c.in_batch_mod > 0 && c.in_batch_mod % T != 0) return false;
+  if (c.res_batch_mod > 0 && c.res_batch_mod % T != 0) return false;
+  if (c.res_w && (c.res_in_dtype != 1 || c.res_C % 32 != 0)) return false;
+  if ((c.in_lstride % 8) || (c.in_bstride % 8) || ((uintptr_t)c.in % 16)) return false;
+  if (c.out_dtype == 1 ? ((c.out_lstride % 8) || ((uintptr_t)c.out % 16)) : ((c.out_lstride % 4) || ((uintptr_t)c.out % 16)))
+    return false;
+  if (c.res && (c.res_dtype == 1 ? (c.res_lstride % 8) : (c.res_lstride % 4))) return false;
+  return true;
+}
+
+struct ConvTcLaunch {
+  ConvTcParams prm;
+  int kc = 0, n = 0;
+  bool has_res = false;
+  dim3 grid;
+};
+
+inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
+  ConvTcLaunch& L = *out;
+  memset(&L.prm, 0, sizeof(L.prm));
+  const int kc = conv_tc_pick_kc(c);
+  L.kc = kc; L.n = c.C_out; L.has_res = c.res_w != nullptr;
+  ConvTcParams& p = L.prm;
+  const int Lp = c.L_out, T = 128 / Lp;
+  const uint64_t in_b = c.in_batch_mod > 0 ? (uint64_t)c.in_batch_mod : (uint64_t)c.batch;
+  {
+    uint64_t dims[3] = {(uint64_t)c.C_in, (uint64_t)c.L_in, in_b};
+    uint64_t str[2] = {(uint64_t)c.in_lstride, (uint64_t)c.in_bstride};
+    uint32_t box[3] = {(uint32_t)kc, (uint32_t)Lp, (uint32_t)T};
+    if (!encode_bf16_map(&p.tm_a, c.in, 3, dims, str, box, kc)) return false;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)c.C_in, (uint64_t)c.taps * c.C_out};
+    uint64_t str[1] = {(uint64_t)c.C_in};
+    uint32_t box[2] = {(uint32_t)kc, (uint32_t)c.C_out};
+    if (!encode_bf16_map(&p.tm_b, c.w, 2, dims, str, box, kc)) return false;
+  }
+  if (L.has_res) {
+    const uint64_t r_b = c.res_batch_mod > 0 ? (uint64_t)c.res_batch_mod : (uint64_t)c.batch;
+    uint64_t dims[3] = {(uint64_t)c.res_C, (uint64_t)Lp, r_b};
+    uint64_t str[2] = {(uint64_t)c.res_in_lstride, (uint64_t)c.res_in_bstride};
+    uint32_t box[3] = {(uint32_t)kc, (uint32_t)Lp, (uint32_t)T};
+    if (!encode_bf16_map(&p.tm_a2, c.res_in, 3, dims, str, box, kc)) return false;
+    uint64_t d2[2] = {(uint64_t)c.res_C, (uint64_t)c.C_out};
+    uint64_t s2[1] = {(uint64_t)c.res_C};
+    uint32_t b2[2] = {(uint32_t)kc, (uint32_t)c.C_out};
+    if (!encode_bf16_map(&p.tm_b2, c.res_w, 2, d2, s2, b2, kc)) return false;
+  }
+  p.batch = c.batch; p.L = Lp; p.log2L = ilog2(Lp); p.C_out = c.C_out; p.taps = c.taps; p.pad = c.pad;
+  p.kchunks = c.C_in / kc; p.kchunks2 = L.has_res ? c.res_C / kc : 0;
+  p.in_batch_mod = c.in_batch_mod;
+  p.bias = c.bias; p.scale = c.scale; p.shift = c.shift;
+  p.groups = c.groups; p.gn_gamma = c.gn_gamma; p.gn_beta = c.gn_beta; p.gn_eps = c.gn_eps; p.act = c.act;
+  p.res = c.res; p.res_bstride = c.res_bstride; p.res_lstride = c.res_lstride; p.res_batch_mod = c.res_batch_mod;
+  p.res_dtype = c.res_dtype; p.res_bias = c.res_bias;
+  p.out = c.out; p.out_bstride = c.out_bstride; p.out_lstride = c.out_lstride; p.out_dtype = c.out_dtype;
+  int64_t rows = (int64_t)c.batch * Lp;
+  L.grid = dim3((unsigned)((rows + 127) / 128));
+  return true;
+}
+
+template <int KC, int N, bool HAS_RES>
+inline cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStream_t st) {
+  using Cfg = ConvTcCfg<KC, N, HAS_RES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  conv_tc_kernel<KC, N, HAS_RES><<<L.grid, kTcThreads, Cfg::kSmemBytes, st>>>(L.prm, iter_ptr);
+  return cudaGetLastError();
+}
+
+inline cudaError_t conv_tc_launch(const ConvTcLaunch& L, const int* iter_ptr, cudaStream_t st) {
+#define CDS_TC_CASE(KC_, N_)                                                                     \
+  if (L.kc == KC_ && L.n == N_)                                                                  \
+    return L.has_res ? conv_tc_launch_t<KC_, N_, true>(L, iter_ptr, st) : conv_tc_launch_t<KC_, N_, false>(L, iter_ptr, st);
+  CDS_TC_CASE(64, 32) CDS_TC_CASE(64, 64) CDS_TC_CASE(64, 128) CDS_TC_CASE(64, 256)
+  CDS_TC_CASE(32, 32) CDS_TC_CASE(32, 64) CDS_TC_CASE(32, 128) CDS_TC_CASE(32, 256)
+#undef CDS_TC_CASE
+  return cudaErrorInvalidValue;
+}
+
+template <int KC, int N, bool HAS_RES>
+inline cudaError_t conv_tc_preload_t() {
+  cudaFuncAttributes a;
+  return cudaFuncGetAttributes(&a, conv_tc_kernel<KC, N, HAS_RES>);
+}
+
+}  // namespace cds

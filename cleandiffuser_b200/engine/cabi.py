@@ -14,6 +14,7 @@ ABI_VERSION = 1
 OP_CONV, OP_UPDATE, OP_LNMOD, OP_ATTN, OP_PREP = range(5)
 ACT_NONE, ACT_MISH, ACT_SILU, ACT_GELU_TANH, ACT_MISH_SILU = range(5)
 MATH_FP32, MATH_BF16_TC = 0, 1
+F32, BF16 = 0, 1
 ROW_FLOATS = 12
 
 _f32p = C.c_void_p   # device pointers are passed as integers
@@ -39,6 +40,7 @@ class ConvOp(C.Structure):
         ("res_w", C.c_void_p), ("res_bias", _f32p),
         ("out", _f32p), ("out_bstride", C.c_int64), ("out_lstride", C.c_int32),
         ("math", C.c_int32),
+        ("in_dtype", C.c_int32), ("out_dtype", C.c_int32), ("res_dtype", C.c_int32), ("res_in_dtype", C.c_int32),
     ]
 
 
@@ -83,7 +85,7 @@ class CdsError(RuntimeError):
 _lib = None
 
 # every symbol include/cds.h declares (tests check that the built library exports all of them)
-EXPORTS = ["cds_version", "cds_op_size", "cds_last_error", "cds_device_sm_count", "cds_plan_create", "cds_plan_destroy",
+EXPORTS = ["cds_version", "cds_op_size", "cds_conv_tc_supported", "cds_last_error", "cds_device_sm_count", "cds_plan_create", "cds_plan_destroy",
            "cds_plan_append", "cds_plan_finalize", "cds_plan_run", "cds_plan_profile", "cds_plan_launches_per_iter",
            "cds_run_op"]
 
@@ -106,6 +108,7 @@ def load():
     lib.cds_version.restype = C.c_int
     lib.cds_last_error.restype = C.c_char_p
     lib.cds_device_sm_count.argtypes = [C.c_int]
+    lib.cds_conv_tc_supported.argtypes = [C.POINTER(ConvOp)]
     lib.cds_plan_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.cds_plan_destroy.argtypes = [C.c_void_p]
     lib.cds_plan_append.argtypes = [C.c_void_p, C.POINTER(Op), C.c_int32]

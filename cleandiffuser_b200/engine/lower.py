@@ -37,10 +37,11 @@ class Unsupported(Exception):
 
 
 class View:
-    """A channels-last activation: element (b, l, c) at base + b*bstride + l*lstride + c (floats)."""
+    """A channels-last activation: element (b, l, c) at base + b*bstride + l*lstride + c (elements of its dtype)."""
 
     def __init__(self, tensor: torch.Tensor, L: int, Cn: int, offset: int = 0, bstride: Optional[int] = None,
                  lstride: Optional[int] = None):
+        assert tensor.dtype in (torch.float32, torch.bfloat16)
         # module dims may be numpy ints (np.cumprod(dim_mult)); ctypes wants python ints
         self.t, self.L, self.C, self.offset = tensor, int(L), int(Cn), int(offset)
         self.lstride = self.C if lstride is None else int(lstride)
@@ -48,7 +49,11 @@ class View:
 
     @property
     def ptr(self):
-        return self.t.data_ptr() + 4 * self.offset
+        return self.t.data_ptr() + self.t.element_size() * self.offset
+
+    @property
+    def dtype(self):
+        return cabi.BF16 if self.t.dtype == torch.bfloat16 else cabi.F32
 
     def channels(self, start: int, count: int) -> "View":
         return View(self.t, self.L, count, self.offset + int(start), self.bstride, self.lstride)
@@ -72,6 +77,45 @@ def _const_vec(t: Optional[torch.Tensor]) -> cabi.Vec:
     return v
 
 
+class WSpec:
+    """Where a GEMM weight comes from; packed lazily in the layout of the kernel that ends up running the op.
+
+    kn() -> fp32 [K = taps*C_in, N = C_out*phases]   (CUDA-core kernel: K rows, N contiguous)
+    nk() -> [taps, C_out, C_in]                      (tensor-core kernel: K contiguous; cast to bf16), or None"""
+
+    def __init__(self, kn: Callable[[], torch.Tensor], nk: Optional[Callable[[], torch.Tensor]] = None):
+        self.kn, self.nk = kn, nk
+
+
+def w_conv(conv: nn.Conv1d) -> WSpec:                        # [Cout, Cin, k]
+    return WSpec(lambda: conv.weight.permute(2, 1, 0).reshape(-1, conv.weight.shape[0]),
+                 lambda: conv.weight.permute(2, 0, 1))
+
+
+def w_linear(weight: torch.Tensor, cols: Optional[slice] = None) -> WSpec:    # [out, in]
+    pick = (lambda: weight) if cols is None else (lambda: weight[:, cols])
+    return WSpec(lambda: pick().t(), lambda: pick()[None])
+
+
+def w_rows(make_out_in: Callable[[], torch.Tensor]) -> WSpec:                 # callable -> [out, in]
+    return WSpec(lambda: make_out_in().t(), lambda: make_out_in()[None])
+
+
+def w_convT(conv: nn.ConvTranspose1d) -> WSpec:
+    """ConvTranspose1d(k=4, s=2, p=1) as a 3-tap conv with two output phases:
+    out[2m]   = x[m-1] W[..,3] + x[m] W[..,1]        out[2m+1] = x[m] W[..,2] + x[m+1] W[..,0]"""
+    def make():
+        w = conv.weight                                      # [Cin, Cout, 4]
+        cin, cout, _ = w.shape
+        p = torch.zeros(3, cin, 2 * cout, device=w.device, dtype=w.dtype)
+        p[0, :, :cout] = w[:, :, 3]
+        p[1, :, :cout] = w[:, :, 1]
+        p[1, :, cout:] = w[:, :, 2]
+        p[2, :, cout:] = w[:, :, 0]
+        return p.reshape(3 * cin, 2 * cout)
+    return WSpec(make, None)
+
+
 class Program:
     def __init__(self, device: torch.device, rows: int, n_iters: int, math: int = cabi.MATH_FP32):
         self.device, self.rows, self.n_iters, self.math = device, rows, n_iters, math
@@ -81,18 +125,23 @@ class Program:
         self.per_call: List[Callable[[object], None]] = []
 
     # ---- memory ---------------------------------------------------------------------------
-    def buf(self, *shape) -> torch.Tensor:
-        t = torch.zeros(tuple(int(s) for s in shape), device=self.device, dtype=torch.float32)
+    def buf(self, *shape, dtype=torch.float32) -> torch.Tensor:
+        t = torch.zeros(tuple(int(s) for s in shape), device=self.device, dtype=dtype)
         self.keep.append(t)
         return t
 
-    def act(self, L: int, Cn: int) -> View:
-        return View(self.buf(self.rows, L, Cn), L, Cn)
+    @property
+    def act_dtype(self):
+        """Intermediate activations: bf16 when the program runs on the tensor-core kernels, else fp32."""
+        return torch.bfloat16 if self.math == cabi.MATH_BF16_TC else torch.float32
 
-    def packed(self, make: Callable[[], torch.Tensor]) -> torch.Tensor:
+    def act(self, L: int, Cn: int, dtype=None) -> View:
+        return View(self.buf(self.rows, L, Cn, dtype=self.act_dtype if dtype is None else dtype), L, Cn)
+
+    def packed(self, make: Callable[[], torch.Tensor], dtype=torch.float32) -> torch.Tensor:
         """Persistent packed copy of parameters; ``make`` is re-evaluated into it when weights change."""
         with torch.no_grad():
-            t = make().detach().to(device=self.device, dtype=torch.float32).contiguous().clone()
+            t = make().detach().to(device=self.device, dtype=dtype).contiguous().clone()
         self.keep.append(t)
 
         def refresh():
@@ -101,32 +150,12 @@ class Program:
         self.packers.append(refresh)
         return t
 
-    # ---- weight layouts ---------------------------------------------------------------------
-    def conv_w(self, conv: nn.Conv1d) -> torch.Tensor:            # [Cout, Cin, k] -> [k*Cin, Cout]
-        return self.packed(lambda: conv.weight.permute(2, 1, 0).reshape(-1, conv.weight.shape[0]))
-
-    def linear_w(self, lin_weight: torch.Tensor, cols: Optional[slice] = None) -> torch.Tensor:   # [out, in] -> [in, out]
-        return self.packed(lambda: (lin_weight if cols is None else lin_weight[:, cols]).t())
-
-    def convT_w(self, conv: nn.ConvTranspose1d) -> torch.Tensor:
-        """ConvTranspose1d(k=4, s=2, p=1) as a 3-tap conv with two output phases:
-        out[2m]   = x[m-1] W[..,3] + x[m] W[..,1]        out[2m+1] = x[m] W[..,2] + x[m+1] W[..,0]"""
-        def make():
-            w = conv.weight                                  # [Cin, Cout, 4]
-            cin, cout, _ = w.shape
-            p = torch.zeros(3, cin, 2 * cout, device=w.device, dtype=w.dtype)
-            p[0, :, :cout] = w[:, :, 3]
-            p[1, :, :cout] = w[:, :, 1]
-            p[1, :, cout:] = w[:, :, 2]
-            p[2, :, cout:] = w[:, :, 0]
-            return p.reshape(3 * cin, 2 * cout)
-        return self.packed(make)
-
     # ---- operator emitters --------------------------------------------------------------------
-    def conv(self, x: View, w: torch.Tensor, out: View, *, taps=1, stride=1, pad=0, phases=1, L_out=None,
+    def conv(self, x: View, w: WSpec, out: View, *, taps=1, stride=1, pad=0, phases=1, L_out=None,
              bias: Optional[cabi.Vec] = None, gn: Optional[GroupNorm1d] = None, act=cabi.ACT_NONE,
              scale: Optional[cabi.Vec] = None, shift: Optional[cabi.Vec] = None, res: Optional[View] = None,
              res_conv=None, in_batch_mod=0, res_batch_mod=0, rows=None):
+        """Emit one CDS_OP_CONV.  ``res_conv`` = (View, WSpec of the 1x1 weight, bias tensor maker)."""
         op = cabi.Op()
         op.kind = cabi.OP_CONV
         c = op.u.conv
@@ -135,9 +164,7 @@ class Program:
         c.C_in, c.C_out = x.C, out.C
         c.taps, c.stride, c.pad, c.phases = int(taps), int(stride), int(pad), int(phases)
         c.in_batch_mod = int(in_batch_mod)
-        c.in_, c.in_bstride, c.in_lstride = x.ptr, x.bstride, x.lstride
-        c.w = w.data_ptr()
-        assert w.shape == (taps * x.C, out.C * phases), (w.shape, taps, x.C, out.C, phases)
+        c.in_, c.in_bstride, c.in_lstride, c.in_dtype = x.ptr, x.bstride, x.lstride, x.dtype
         if bias is not None:
             c.bias = bias
         if gn is not None:
@@ -149,14 +176,30 @@ class Program:
         if shift is not None:
             c.shift = shift
         if res is not None:
-            c.res, c.res_bstride, c.res_lstride = res.ptr, res.bstride, res.lstride
+            c.res, c.res_bstride, c.res_lstride, c.res_dtype = res.ptr, res.bstride, res.lstride, res.dtype
         c.res_batch_mod = int(res_batch_mod)
         if res_conv is not None:
-            rx, rw, rb = res_conv
+            rx = res_conv[0]
             c.res_in, c.res_in_bstride, c.res_in_lstride, c.res_C = rx.ptr, rx.bstride, rx.lstride, rx.C
-            c.res_w, c.res_bias = rw.data_ptr(), rb.data_ptr()
-        c.out, c.out_bstride, c.out_lstride = out.ptr, out.bstride, out.lstride
-        c.math = self.math
+            c.res_in_dtype = rx.dtype
+            c.res_w = 1          # placeholder so that eligibility sees a shortcut conv; real pointer set below
+        c.out, c.out_bstride, c.out_lstride, c.out_dtype = out.ptr, out.bstride, out.lstride, out.dtype
+
+        # kernel family: tensor cores when the program asks for them AND this op qualifies, else CUDA cores
+        use_tc = False
+        if self.math == cabi.MATH_BF16_TC and w.nk is not None and (res_conv is None or res_conv[1].nk is not None):
+            use_tc = bool(cabi.load().cds_conv_tc_supported(C.byref(c)))
+        c.math = cabi.MATH_BF16_TC if use_tc else cabi.MATH_FP32
+        if use_tc:
+            wt = self.packed(lambda: w.nk().reshape(taps * out.C, x.C), torch.bfloat16)
+        else:
+            wt = self.packed(w.kn)
+            assert wt.shape == (taps * x.C, out.C * phases), (wt.shape, taps, x.C, out.C, phases)
+        c.w = wt.data_ptr()
+        if res_conv is not None:
+            rw = res_conv[1]
+            rwt = self.packed(lambda: rw.nk().reshape(out.C, rx.C), torch.bfloat16) if use_tc else self.packed(rw.kn)
+            c.res_w, c.res_bias = rwt.data_ptr(), self.packed(res_conv[2]).data_ptr()
         self.ops.append(op)
         return out
 
@@ -185,7 +228,7 @@ def _lower_conv_block(p: Program, seq: nn.Sequential, x: View, out: View, k: int
     conv, gn = seq[0], seq[1]
     if not isinstance(gn, GroupNorm1d):
         raise Unsupported("norm_type other than groupnorm")
-    return p.conv(x, p.conv_w(conv), out, taps=k, pad=k // 2, bias=_const_vec(p.packed(lambda: conv.bias)),
+    return p.conv(x, w_conv(conv), out, taps=k, pad=k // 2, bias=_const_vec(p.packed(lambda: conv.bias)),
                   gn=gn, act=cabi.ACT_MISH, **kw)
 
 
@@ -195,7 +238,7 @@ def _lower_resblock(p: Program, blk, x: View, out: View, k: int, cond: dict):
     _lower_conv_block(p, blk.conv1, x, h, k, **cond)
     if isinstance(blk.residual_conv, nn.Conv1d):
         rc = blk.residual_conv
-        shortcut = dict(res_conv=(x, p.packed(lambda: rc.weight[:, :, 0].t()), p.packed(lambda: rc.bias)))
+        shortcut = dict(res_conv=(x, w_rows(lambda: rc.weight[:, :, 0]), lambda: rc.bias))
     else:
         shortcut = dict(res=x)
     return _lower_conv_block(p, blk.conv2, h, out, k, **shortcut)
@@ -211,8 +254,8 @@ def _unet_body(p: Program, net, x: View, horizon: int, k: int, film_of: Callable
     if lens[-1] < 1:
         raise Unsupported("horizon too short for the number of stages")
     # cat buffer of up-stage u holds [x | skip h[n-1-u]] at resolution n-1-u
-    cats = [View(p.buf(p.rows, lens[n - 1 - u], 2 * chans[n - 1 - u]), lens[n - 1 - u], 2 * chans[n - 1 - u])
-            for u in range(n - 1)]
+    cats = [View(p.buf(p.rows, lens[n - 1 - u], 2 * chans[n - 1 - u], dtype=p.act_dtype), lens[n - 1 - u],
+                 2 * chans[n - 1 - u]) for u in range(n - 1)]
 
     def skip_slot(s):     # where h[s] lives
         if s == 0 or n == 1:
@@ -228,7 +271,7 @@ def _unet_body(p: Program, net, x: View, horizon: int, k: int, film_of: Callable
         if isinstance(down, nn.Identity):
             x = h
         else:
-            x = p.conv(h, p.conv_w(down.conv), p.act(lens[s + 1], chans[s]), taps=3, stride=2, pad=1,
+            x = p.conv(h, w_conv(down.conv), p.act(lens[s + 1], chans[s]), taps=3, stride=2, pad=1,
                        bias=_const_vec(p.packed(lambda d=down: d.conv.bias)))
 
     mids = [net.mid_block1, net.mid_block2] if hasattr(net, "mid_block1") else list(net.mids)
@@ -246,13 +289,13 @@ def _unet_body(p: Program, net, x: View, horizon: int, k: int, film_of: Callable
         if isinstance(up, nn.Identity):
             raise Unsupported("up stage without Upsample1d")
         dst = cats[u + 1].channels(0, c_out) if u + 1 < n - 1 else p.act(lens[s - 1], c_out)
-        x = p.conv(y, p.convT_w(up.conv), dst, taps=3, stride=1, pad=1, phases=2, L_out=lens[s],
+        x = p.conv(y, w_convT(up.conv), dst, taps=3, stride=1, pad=1, phases=2, L_out=lens[s],
                    bias=_const_vec(p.packed(lambda m=up: m.conv.bias)))
 
     fc = net.final_conv
     y = _lower_conv_block(p, fc, x, p.act(horizon, fc[0].out_channels), final_k)
     last = fc[3]
-    return p.conv(y, p.packed(lambda: last.weight[:, :, 0].t()), p.act(horizon, last.out_channels),
+    return p.conv(y, w_rows(lambda: last.weight[:, :, 0]), p.act(horizon, last.out_channels, dtype=torch.float32),
                   bias=_const_vec(p.packed(lambda: last.bias)))
 
 
@@ -300,12 +343,12 @@ def lower_janner(p: Program, net: JannerUNet1d, x: View, horizon: int, has_cond:
             c_rows.copy_(F.linear(ctx.cond_rows, net.map_emb[0].weight))
         p.per_call.append(fill)
         h1 = View(p.buf(p.rows, 1, net.map_emb[0].out_features), 1, net.map_emb[0].out_features)
-        p.conv(View(dummy_in, 1, 1), dummy_w, h1, bias=_vec(step=t_rows, sample=c_rows), act=cabi.ACT_MISH)
+        p.conv(View(dummy_in, 1, 1), WSpec(lambda: dummy_w), h1, bias=_vec(step=t_rows, sample=c_rows), act=cabi.ACT_MISH)
         emb_m = View(p.buf(p.rows, 1, md), 1, md)                      # Mish(map_emb(.)): every consumer starts with Mish
-        p.conv(h1, p.linear_w(net.map_emb[2].weight), emb_m, bias=_const_vec(p.packed(lambda: net.map_emb[2].bias)),
+        p.conv(h1, w_linear(net.map_emb[2].weight), emb_m, bias=_const_vec(p.packed(lambda: net.map_emb[2].bias)),
                act=cabi.ACT_MISH)
         tb = View(p.buf(p.rows, 1, total), 1, total)
-        p.conv(emb_m, p.packed(lambda: torch.cat([b.emb_mlp[1].weight for b in blocks], 0).t()), tb,
+        p.conv(emb_m, w_rows(lambda: torch.cat([b.emb_mlp[1].weight for b in blocks], 0)), tb,
                bias=_const_vec(p.packed(lambda: torch.cat([b.emb_mlp[1].bias for b in blocks], 0))))
         film = {id(b): dict(shift=_vec(sample=tb.t.view(p.rows, total), col=o)) for b, o in zip(blocks, offs)}
 
@@ -382,16 +425,16 @@ def lower_dql(p: Program, net: DQLMlp, x: View, has_cond: bool, in_batch_mod: in
             samp_tab.zero_()
     p.per_call.append(fill)
     h = View(p.buf(p.rows, 1, hidden), 1, hidden)
-    p.conv(x, p.linear_w(lin1.weight, slice(0, act_dim)), h, bias=_vec(step_tab, samp_tab), act=cabi.ACT_MISH,
+    p.conv(x, w_linear(lin1.weight, slice(0, act_dim)), h, bias=_vec(step_tab, samp_tab), act=cabi.ACT_MISH,
            in_batch_mod=in_batch_mod)
     for idx in (2, 4):
         lin = net.mid_layer[idx]
         h2 = View(p.buf(p.rows, 1, lin.out_features), 1, lin.out_features)
-        p.conv(h, p.linear_w(lin.weight), h2, bias=_const_vec(p.packed(lambda m=lin: m.bias)), act=cabi.ACT_MISH)
+        p.conv(h, w_linear(lin.weight), h2, bias=_const_vec(p.packed(lambda m=lin: m.bias)), act=cabi.ACT_MISH)
         h = h2
     out = View(p.buf(p.rows, 1, act_dim), 1, act_dim)
     fl = net.final_layer
-    return p.conv(h, p.linear_w(fl.weight), out, bias=_const_vec(p.packed(lambda: fl.bias)))
+    return p.conv(h, w_linear(fl.weight), out, bias=_const_vec(p.packed(lambda: fl.bias)))
 
 
 # =============================================================================== DiT1d
@@ -418,41 +461,42 @@ def lower_dit(p: Program, net: DiT1d, x: View, horizon: int, has_cond: bool, in_
         pos.copy_(net.pos_emb(torch.arange(L, device=pos.device)))      # int64 positions: degenerate table, by design
     p.per_call.append(fill)
     h1 = View(p.buf(R, 1, d), 1, d)
-    p.conv(View(dummy_in, 1, 1), dummy_w, h1, bias=_vec(step=t_rows, sample=c_rows), act=cabi.ACT_MISH)
+    p.conv(View(dummy_in, 1, 1), WSpec(lambda: dummy_w), h1, bias=_vec(step=t_rows, sample=c_rows), act=cabi.ACT_MISH)
     emb_s = View(p.buf(R, 1, d), 1, d)
-    p.conv(h1, p.linear_w(net.map_emb[2].weight), emb_s, bias=_const_vec(p.packed(lambda: net.map_emb[2].bias)),
+    p.conv(h1, w_linear(net.map_emb[2].weight), emb_s, bias=_const_vec(p.packed(lambda: net.map_emb[2].bias)),
            act=cabi.ACT_MISH_SILU)
     mods = [blk.adaLN_modulation[1] for blk in net.blocks] + [net.final_layer.adaLN_modulation[1]]
     total = sum(m.out_features for m in mods)
     mod = View(p.buf(R, 1, total), 1, total)
-    p.conv(emb_s, p.packed(lambda: torch.cat([m.weight for m in mods], 0).t()), mod,
+    p.conv(emb_s, w_rows(lambda: torch.cat([m.weight for m in mods], 0)), mod,
            bias=_const_vec(p.packed(lambda: torch.cat([m.bias for m in mods], 0))))
     mod2d = mod.t.view(R, total)
 
     # ---- tokens
-    X, Y, ATT = p.act(L, d), p.act(L, d), p.act(L, d)
-    QKV, HID = p.act(L, 3 * d), p.act(L, 4 * d)
-    p.conv(x, p.linear_w(net.x_proj.weight), X, bias=_const_vec(p.packed(lambda: net.x_proj.bias)),
+    f32 = torch.float32          # the LayerNorm / attention operators are fp32: keep the token stream fp32 for now
+    X, Y, ATT = p.act(L, d, f32), p.act(L, d, f32), p.act(L, d, f32)
+    QKV, HID = p.act(L, 3 * d, f32), p.act(L, 4 * d, f32)
+    p.conv(x, w_linear(net.x_proj.weight), X, bias=_const_vec(p.packed(lambda: net.x_proj.bias)),
            res=View(pos, L, d, bstride=0), in_batch_mod=in_batch_mod)
     for i, blk in enumerate(net.blocks):
         o = 6 * d * i       # chunk order: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
         p.lnmod(X, Y, mod2d, o, o + d, blk.norm1.eps)
         at = blk.attn
-        p.conv(Y, p.linear_w(at.in_proj_weight), QKV, bias=_const_vec(p.packed(lambda a=at: a.in_proj_bias)))
+        p.conv(Y, w_linear(at.in_proj_weight), QKV, bias=_const_vec(p.packed(lambda a=at: a.in_proj_bias)))
         p.attn(QKV, ATT, heads)
         # reference quirk (dit.py:33-34): the residual wraps the MODULATED tokens Y, not the block input
-        p.conv(ATT, p.linear_w(at.out_proj.weight), X, bias=_const_vec(p.packed(lambda a=at: a.out_proj.bias)),
+        p.conv(ATT, w_linear(at.out_proj.weight), X, bias=_const_vec(p.packed(lambda a=at: a.out_proj.bias)),
                scale=_vec(sample=mod2d, col=o + 2 * d), res=Y)
         p.lnmod(X, Y, mod2d, o + 3 * d, o + 4 * d, blk.norm2.eps)
-        p.conv(Y, p.linear_w(blk.mlp[0].weight), HID, bias=_const_vec(p.packed(lambda b=blk: b.mlp[0].bias)),
+        p.conv(Y, w_linear(blk.mlp[0].weight), HID, bias=_const_vec(p.packed(lambda b=blk: b.mlp[0].bias)),
                act=cabi.ACT_GELU_TANH)
-        p.conv(HID, p.linear_w(blk.mlp[3].weight), X, bias=_const_vec(p.packed(lambda b=blk: b.mlp[3].bias)),
+        p.conv(HID, w_linear(blk.mlp[3].weight), X, bias=_const_vec(p.packed(lambda b=blk: b.mlp[3].bias)),
                scale=_vec(sample=mod2d, col=o + 5 * d), res=X)
     o = 6 * d * depth
     fl = net.final_layer
     p.lnmod(X, Y, mod2d, o, o + d, fl.norm_final.eps)
-    out = p.act(L, net.in_dim)
-    return p.conv(Y, p.linear_w(fl.linear.weight), out, bias=_const_vec(p.packed(lambda: fl.linear.bias)))
+    out = p.act(L, net.in_dim, f32)
+    return p.conv(Y, w_linear(fl.linear.weight), out, bias=_const_vec(p.packed(lambda: fl.linear.bias)))
 
 
 def lower_denoiser(p: Program, net: nn.Module, x: View, x_shape, has_cond: bool, in_batch_mod: int) -> View:

@@ -25,9 +25,10 @@
  *  - all pointers inside operator descriptors are DEVICE pointers owned by the caller (weights are the
  *    caller's parameter storage or caller-allocated packed copies; activations live in a caller-allocated
  *    workspace).  The library never allocates device memory on the hot path and never frees caller memory.
- *  - activations are fp32, "channels last": element (b, l, c) of a (batch, L, C) tensor sits at
- *    base + b*bstride + l*lstride + c (strides in floats), which is also the reference's public (b, horizon, dim)
- *    layout, so x_t needs no permute on entry or exit.
+ *  - activations are "channels last": element (b, l, c) of a (batch, L, C) tensor sits at
+ *    base + b*bstride + l*lstride + c (strides in elements), which is also the reference's public (b, horizon, dim)
+ *    layout, so x_t needs no permute on entry or exit.  x_t, predictions and all tables are fp32; intermediate
+ *    activations are fp32 (CDS_MATH_FP32 programs) or bf16 (CDS_MATH_BF16_TC programs).
  *  - "per-iteration" operands are indexed by a device-resident iteration counter, so one captured graph
  *    serves every reverse iteration:  vec(b, c) = step[iter*step_stride + c] + sample[b*sample_stride + c]
  *    (either part may be NULL = 0).
@@ -59,6 +60,7 @@ typedef enum cds_act { CDS_ACT_NONE = 0, CDS_ACT_MISH = 1, CDS_ACT_SILU = 2, CDS
 /* math mode of CDS_OP_CONV: fp32 CUDA-core FMA (bit-faithful to the fp32 oracle up to summation order), or
  * tcgen05 tensor cores with bf16 operands / fp32 TMEM accumulation */
 typedef enum cds_math { CDS_MATH_FP32 = 0, CDS_MATH_BF16_TC = 1 } cds_math;
+typedef enum cds_dtype { CDS_F32 = 0, CDS_BF16 = 1 } cds_dtype;
 /* update shapes; must match cleandiffuser_b200/diffusion/solvers.py */
 typedef enum cds_update_kind { CDS_UPD_DDPM = 0, CDS_UPD_DDIM = 1, CDS_UPD_EPS = 2, CDS_UPD_X = 3, CDS_UPD_X2M = 4, CDS_UPD_CM = 5 } cds_update_kind;
 
@@ -86,17 +88,19 @@ typedef struct cds_vec {
 typedef struct cds_conv_op {
   int32_t batch, L_in, L_out, C_in, C_out, taps, stride, pad, phases;
   int32_t in_batch_mod;            /* >0: read in() at batch index b % in_batch_mod (CFG branches share x_t) */
-  const float* in;  int64_t in_bstride;  int32_t in_lstride;
-  const void*  w;                  /* fp32 [taps*C_in][C_out*phases]  (CDS_MATH_FP32)  */
+  const void* in;   int64_t in_bstride;  int32_t in_lstride;   /* strides in ELEMENTS of the tensor's dtype */
+  const void*  w;                  /* CDS_MATH_FP32: fp32 [taps*C_in][C_out*phases] (K rows, N contiguous)
+                                      CDS_MATH_BF16_TC: bf16 [taps][C_out][C_in]     (K contiguous, TMA/UMMA K-major) */
   cds_vec bias;
   int32_t groups; const float* gn_gamma; const float* gn_beta; float gn_eps;
   int32_t act;
   cds_vec scale, shift;
-  const float* res; int64_t res_bstride; int32_t res_lstride; int32_t res_batch_mod;
-  const float* res_in; int64_t res_in_bstride; int32_t res_in_lstride; int32_t res_C;
-  const void* res_w; const float* res_bias;
-  float* out; int64_t out_bstride; int32_t out_lstride;
-  int32_t math;                    /* cds_math */
+  const void* res; int64_t res_bstride; int32_t res_lstride; int32_t res_batch_mod;
+  const void* res_in; int64_t res_in_bstride; int32_t res_in_lstride; int32_t res_C;
+  const void* res_w; const float* res_bias;   /* res_w: fp32 [res_C][C_out] or bf16 [C_out][res_C], as `w` */
+  void* out; int64_t out_bstride; int32_t out_lstride;
+  int32_t math;                    /* cds_math: which kernel family / weight layout */
+  int32_t in_dtype, out_dtype, res_dtype, res_in_dtype;   /* cds_dtype of the activation tensors */
 } cds_conv_op;
 
 /* out(b,l,:) = LayerNorm(in(b,l,:), eps, no affine) * (1 + scale(b,:)) + shift(b,:) */
@@ -149,6 +153,11 @@ int         cds_op_size(void);
 const char* cds_last_error(void);
 /* number of SMs etc. of `device`, -1 on error; used by the host to size workspaces */
 int         cds_device_sm_count(int device);
+
+/* 1 if the tensor-core (CDS_MATH_BF16_TC) kernel can run `op` as described (dtypes, strides, shapes; `w` may still be
+ * NULL), else 0: the host lowering asks before choosing the weight layout; ops that are not eligible run on the
+ * CUDA-core kernel with math = CDS_MATH_FP32 (which accepts fp32 or bf16 activations).  Pure host logic. */
+int cds_conv_tc_supported(const cds_conv_op* op);
 
 /* A plan = the per-iteration operator program for one (model, shape, option set) on one device. */
 int cds_plan_create(int device, cds_plan** out);

@@ -21,6 +21,33 @@ def _arr(ptr, shape, strides):
     return np.lib.stride_tricks.as_strided(flat, shape=shape, strides=[4 * s for s in strides])
 
 
+def _bf16_to_f32(u16):
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
+def _f32_to_bf16(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+
+
+def _load(ptr, shape, strides, dtype):
+    """float32 COPY of an fp32 / bf16 activation view (strides in elements)."""
+    if dtype == cabi.F32:
+        return np.array(_arr(ptr, shape, strides))
+    extent = 1 + sum((s - 1) * abs(st) for s, st in zip(shape, strides))
+    flat = np.ctypeslib.as_array((ctypes.c_uint16 * extent).from_address(ptr))
+    return _bf16_to_f32(np.lib.stride_tricks.as_strided(flat, shape=shape, strides=[2 * s for s in strides]))
+
+
+def _store(ptr, shape, strides, dtype, values):
+    if dtype == cabi.F32:
+        _arr(ptr, shape, strides)[...] = values
+        return
+    extent = 1 + sum((s - 1) * abs(st) for s, st in zip(shape, strides))
+    flat = np.ctypeslib.as_array((ctypes.c_uint16 * extent).from_address(ptr))
+    np.lib.stride_tricks.as_strided(flat, shape=shape, strides=[2 * s for s in strides])[...] = _f32_to_bf16(values)
+
+
 def _vec(v, it, rows, n):
     out = np.zeros((rows, n), dtype=np.float32)
     present = False
@@ -54,9 +81,14 @@ def _act(kind, x):
 def run_conv(c, it):
     B, N = c.batch, c.C_out * c.phases
     bmod = c.in_batch_mod if c.in_batch_mod > 0 else B
-    xin = _arr(c.in_, (bmod, c.L_in, c.C_in), (c.in_bstride, c.in_lstride, 1))
+    xin = _load(c.in_, (bmod, c.L_in, c.C_in), (c.in_bstride, c.in_lstride, 1), c.in_dtype)
     xin = xin[np.arange(B) % bmod]
-    w = _arr(c.w, (c.taps, c.C_in, N), (c.C_in * N, N, 1))
+    tc = c.math == cabi.MATH_BF16_TC
+    if tc:      # bf16 [taps][C_out][C_in]
+        assert c.phases == 1 and c.in_dtype == cabi.BF16
+        w = _load(c.w, (c.taps, c.C_out, c.C_in), (c.C_out * c.C_in, c.C_in, 1), cabi.BF16).transpose(0, 2, 1)
+    else:
+        w = _arr(c.w, (c.taps, c.C_in, N), (c.C_in * N, N, 1))
     acc = np.zeros((B, c.L_out, N), dtype=np.float64)
     for tap in range(c.taps):
         for l in range(c.L_out):
@@ -85,16 +117,17 @@ def run_conv(c, it):
     rmod = c.res_batch_mod if c.res_batch_mod > 0 else B
     if c.res:
         assert c.phases == 1
-        r = _arr(c.res, (rmod if c.res_bstride else 1, c.L_out, c.C_out), (c.res_bstride, c.res_lstride, 1))
+        r = _load(c.res, (rmod if c.res_bstride else 1, c.L_out, c.C_out), (c.res_bstride, c.res_lstride, 1), c.res_dtype)
         y = y + r[(np.arange(B) % rmod) if c.res_bstride else np.zeros(B, dtype=int)]
     if c.res_w:
-        rin = _arr(c.res_in, (rmod, c.L_out, c.res_C), (c.res_in_bstride, c.res_in_lstride, 1))[np.arange(B) % rmod]
-        rw = _arr(c.res_w, (c.res_C, N), (N, 1))
+        rin = _load(c.res_in, (rmod, c.L_out, c.res_C), (c.res_in_bstride, c.res_in_lstride, 1),
+                    c.res_in_dtype)[np.arange(B) % rmod]
+        rw = _load(c.res_w, (c.C_out, c.res_C), (c.res_C, 1), cabi.BF16).T if tc else _arr(c.res_w, (c.res_C, N), (N, 1))
         y = y + (rin.astype(np.float64) @ rw.astype(np.float64)).astype(np.float32)
         if c.res_bias:
             y = y + _arr(c.res_bias, (c.C_out,), (1,))[chan]
-    out = _arr(c.out, (B, c.L_out * c.phases, c.C_out), (c.out_bstride, c.out_lstride, 1))
-    out[...] = y.reshape(B, c.L_out, c.phases, c.C_out).reshape(B, c.L_out * c.phases, c.C_out)
+    _store(c.out, (B, c.L_out * c.phases, c.C_out), (c.out_bstride, c.out_lstride, 1), c.out_dtype,
+           y.reshape(B, c.L_out, c.phases, c.C_out).reshape(B, c.L_out * c.phases, c.C_out))
 
 
 def run_lnmod(m):

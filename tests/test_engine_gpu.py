@@ -146,3 +146,52 @@ def test_weights_refresh_after_training_step():
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# tensor-core programs (CDS_MATH=bf16): bf16 operands / activations, fp32 TMEM accumulation and fp32 GN/Mish epilogue.
+# Stated tolerance vs the fp32 reference (measured by emulation: ~8e-3 relative per forward, no
+# compounding over the reverse steps): max-abs 2e-1, mean-abs 2e-2 on O(1) outputs.
+BF16_NETS = ["janner_cfg2", "janner_kitchen_cond", "chi_small", "chi_cm_fourier"]
+
+
+@pytest.mark.parametrize("name", BF16_NETS)
+def test_denoiser_forward_bf16_tensor_cores(golden, name, monkeypatch):
+    monkeypatch.setenv("CDS_MATH", "bf16")
+    case = cases.NETS[name]
+    net, _ = product_net(case)
+    net = net.to(DEV)
+    x, t, cond = cases.net_inputs(case)
+    cond_emb = None if cond is None else cond.to(DEV)
+    want = golden["nets"][name + "/y"]
+    for i in range(cases.NET_BATCH):
+        y = runtime.engine_forward(net, x.to(DEV), t[i:i + 1], cond_emb)
+        err = np.abs(y[i].cpu().numpy() - want[i])
+        assert err.max() < 0.08 and err.mean() < 0.015, (name, i, float(err.max()), float(err.mean()))
+
+
+def test_cfg2_bf16_tensor_cores_full_batch(monkeypatch):
+    monkeypatch.setenv("CDS_MATH", "bf16")
+    T, B = 10, 4096
+    agent, sd, mask = _cfg2_agent(T)
+    g = torch.Generator().manual_seed(1)
+    prior = torch.zeros(B, 32, 14)
+    prior[:, 0, :11] = torch.randn(B, 11, generator=g)
+    tape = NoiseTape()
+    with tape.active(), torch.no_grad():
+        x_full, _ = agent.sample(prior.to(DEV), solver="ddpm", n_samples=B, sample_steps=T, temperature=0.5)
+    x_full = x_full.cpu()
+    assert torch.isfinite(x_full).all()
+    assert torch.equal(x_full[:, 0, :11], prior[:, 0, :11])
+    sub = slice(1024, 1024 + 128)
+    tape_sub = NoiseTape([z[sub] for z in tape.draws])
+    with tape_sub.active(), torch.no_grad():
+        x_sub, _ = agent.sample(prior[sub].to(DEV), solver="ddpm", n_samples=128, sample_steps=T, temperature=0.5)
+    assert torch.equal(x_sub.cpu(), x_full[sub])
+    pick = slice(2040, 2056)
+    fn = oracle_net(cases.NETS["janner_cfg2"], sd)
+    with torch.no_grad():
+        x_ref = osamp.sample_discrete(fn, prior[pick], osamp.Tape([z[pick].numpy() for z in tape.draws]), T=T, steps=T,
+                                      solver="ddpm", temperature=0.5, fix_mask=mask[None], predict_noise=False)
+    err = (x_full[pick] - x_ref).abs()
+    assert err.max() < 0.2 and err.mean() < 0.02, (float(err.max()), float(err.mean()))

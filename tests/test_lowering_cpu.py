@@ -74,3 +74,37 @@ def test_lowered_consistency(golden, steps):
                           condition_cfg=torch.as_tensor(g[f"cm{steps}/cond"]), w_cfg=1.0)
     assert runtime.STATS["engine_calls"] == before + 1
     np.testing.assert_allclose(x0.numpy(), g[f"cm{steps}/x0"], rtol=1e-4, atol=3e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bf16 tensor-core programs: same lowering, bf16 activations/weights in the interpreter.  Tolerances are the
+# SURVEY 8(c) bf16 figures (single forward ~8e-3 relative); this pins the bf16 *lowering* (dtypes, [tap][Cout][Cin]
+# weight packing, which ops go to which kernel family), the kernels themselves are checked on the GPU.
+BF16_NETS = ["janner_cfg2", "janner_kitchen_cond", "chi_small", "chi_cm_fourier"]
+
+
+@pytest.mark.parametrize("name", BF16_NETS)
+def test_lowered_denoiser_bf16(golden, name, monkeypatch):
+    monkeypatch.setenv("CDS_MATH", "bf16")
+    case = cases.NETS[name]
+    net, _ = product_net(case)
+    x, t, cond = cases.net_inputs(case)
+    want = golden["nets"][name + "/y"]
+    for i in range(cases.NET_BATCH):
+        y = runtime.engine_forward(net, x, t[i:i + 1], cond)
+        err = np.abs(y[i].numpy() - want[i])
+        assert err.max() < 0.08 and err.mean() < 0.015, (name, i, err.max(), err.mean())
+
+
+def test_bf16_program_uses_tensor_core_ops(monkeypatch):
+    monkeypatch.setenv("CDS_MATH", "bf16")
+    from cleandiffuser_b200.engine import cabi
+    from cleandiffuser_b200.engine.lower import Program, View, lower_denoiser
+    net, _ = product_net(cases.NETS["janner_cfg2"])
+    p = Program(torch.device("cpu"), 8, 1, cabi.MATH_BF16_TC)
+    xin = p.buf(8, 32, 14)
+    lower_denoiser(p, net, View(xin, 32, 14), (32, 14), False, 0)
+    kinds = [op.u.conv.math for op in p.ops if op.kind == cabi.OP_CONV]
+    # everything except the first block (conv1 reads the 14-channel x_t, conv2 carries the 14-channel shortcut), the
+    # 3 down / 3 up resampling convs and the final 1x1 (C_out=14) runs on tcgen05
+    assert kinds.count(cabi.MATH_BF16_TC) == len(kinds) - 2 - 6 - 1, kinds
