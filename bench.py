@@ -113,17 +113,37 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def cpu_reference_arm(steps, warmup, sample_batch=256):
     """The reference's algorithm on the host cores: oracle port of JannerUNet1d + DiscreteDiffusionSDE.sample
-    (PyTorch CPU primitives, exactly what the reference executes on CPU), on a bounded sample of the workload."""
+    (PyTorch CPU primitives, exactly what the reference executes on CPU), on a bounded sample of the workload.
+    Thread count: the fastest of {all cores, 64, 32, 16} on a 3-forward probe (small convs stop scaling, and can get
+    slower, long before 128 threads); the count used is reported as ``cores``."""
     import oracle.nets as onets
     import oracle.sampler as osamp
-    torch.set_num_threads(os.cpu_count() or 1)
     _, net, mask = build_agent("cpu")
     sd = {k: v.clone() for k, v in net.state_dict().items()}
     fn = lambda x, t, c=None: onets.janner_unet(sd, x, t, c, emb_dim=32, kernel_size=5, n_stages=4)  # noqa: E731
     prior = make_prior(sample_batch)
     g = torch.Generator().manual_seed(2)
+    ncpu = os.cpu_count() or 1
+    best = (None, 1)
+    for nt in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
+        torch.set_num_threads(nt)
+        xp, tp = torch.randn(sample_batch, H, D), torch.full((sample_batch,), 7)
+        with torch.no_grad():
+            fn(xp, tp)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn(xp, tp)
+            dt = time.perf_counter() - t0
+        log(f"cpu probe: {nt} threads -> {dt / 3 * 1e3:.1f} ms / forward (B={sample_batch})")
+        if best[0] is None or dt < best[0]:
+            best = (dt, nt)
+    torch.set_num_threads(best[1])
 
     def one():
         tape = lambda like: torch.randn(like.shape, generator=g)  # noqa: E731
@@ -226,13 +246,18 @@ def main():
         return float(ms.item())
 
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
+        log("warm-up")
+        for i in range(max(args.warmup, 3)):
             step_resident()
+            torch.cuda.synchronize()
+            log(f"warm-up step {i} done")
         with ClockSampler(local_rank) as clk:
             ms = timed(step_resident, args.steps)
+        log(f"timed: {ms / args.steps:.1f} ms/step")
         launches = runtime.STATS["launches"] * args.steps
         step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+        log(f"e2e: {ms_e2e / args.steps:.1f} ms/step")
 
     value = world * B * args.steps / (ms / 1e3)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
@@ -262,6 +287,14 @@ def main():
                                            + (c.L_out * c.res_C if c.res_w else 0) + (c.L_out * c.C_out if c.res else 0))
             conv_flops += 2.0 * c.batch * c.L_out * c.C_out * c.phases * (c.taps * c.C_in + (c.res_C if c.res_w else 0))
         iter_ms = sum(per_op)
+        for i, (op, t_ms) in enumerate(zip(ops, per_op)):
+            if op.kind == 0:
+                c = op.u.conv
+                log(f"op {i:2d} conv {'tc ' if c.math == 1 else 'f32'} L {c.L_in:3d}->{c.L_out * c.phases:3d} C {c.C_in:4d}->{c.C_out:4d} "
+                    f"k{c.taps} s{c.stride} gn{c.groups} res{'W' if c.res_w else ('I' if c.res else '-')}: {t_ms * 1e3:8.1f} us")
+            else:
+                log(f"op {i:2d} kind {op.kind}: {t_ms * 1e3:8.1f} us")
+        log(f"iteration total {iter_ms * 1e3:.1f} us (direct launches, event-bracketed)")
         achieved = conv_bytes / (conv_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "conv_gemm (fused Conv1d+GN+Mish+FiLM+residual), all launches of one iteration",
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

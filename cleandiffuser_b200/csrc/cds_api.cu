@@ -100,6 +100,12 @@ int validate(const cds_op& op, Step* out) {
       if (p.batch <= 0 || p.row <= 0 || !p.x || !p.xin || !p.coef) return fail(CDS_ERR_INVALID, "prep: bad arguments");
       return CDS_OK;
     }
+    case CDS_OP_CAST: {
+      const cds_cast_op& k = op.u.cast;
+      if (k.batch <= 0 || k.L <= 0 || k.C_in <= 0 || k.C_out < k.C_in || (k.C_out & 1) || !k.in || !k.out)
+        return fail(CDS_ERR_INVALID, "cast: bad arguments");
+      return CDS_OK;
+    }
     default:
       return fail(CDS_ERR_INVALID, "unknown operator kind %d", op.kind);
   }
@@ -135,6 +141,12 @@ int launch(const Step& s, const int* iter_ptr, int sm_count, cudaStream_t st) {
     case CDS_OP_ATTN:
       CDS_CUDA(cds::attention_launch(s.op.u.attn, st));
       return CDS_OK;
+    case CDS_OP_CAST: {
+      const cds_cast_op& k = s.op.u.cast;
+      cds::cast_pad_kernel<<<elementwise_grid((int64_t)k.batch * k.L * (k.C_out / 2), sm_count), 256, 0, st>>>(k);
+      CDS_CUDA(cudaGetLastError());
+      return CDS_OK;
+    }
   }
   return fail(CDS_ERR_INVALID, "unknown operator kind");
 }
@@ -145,6 +157,8 @@ int preload_kernels() {
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<32>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<64>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<128>));
+  CDS_CUDA((cds::conv_tc_preload_t<64, 16, false>()));  CDS_CUDA((cds::conv_tc_preload_t<64, 16, true>()));
+  CDS_CUDA((cds::conv_tc_preload_t<32, 16, false>()));  CDS_CUDA((cds::conv_tc_preload_t<32, 16, true>()));
   CDS_CUDA((cds::conv_tc_preload_t<64, 32, false>()));  CDS_CUDA((cds::conv_tc_preload_t<64, 32, true>()));
   CDS_CUDA((cds::conv_tc_preload_t<64, 64, false>()));  CDS_CUDA((cds::conv_tc_preload_t<64, 64, true>()));
   CDS_CUDA((cds::conv_tc_preload_t<64, 128, false>())); CDS_CUDA((cds::conv_tc_preload_t<64, 128, true>()));
@@ -158,6 +172,7 @@ int preload_kernels() {
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<64>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::solver_update_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cm_prep_kernel));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::cast_pad_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::ln_modulate_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::set_iter_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::advance_iter_kernel));

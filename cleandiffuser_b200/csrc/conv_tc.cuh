@@ -30,7 +30,8 @@ constexpr int kTcStages = 4;
 
 struct ConvTcParams {
   CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
-  int batch, L, log2L, C_out, taps, pad;
+  int batch, L, log2L, C_out, taps, pad;   // L = output positions per tile-trajectory; C_out = channels per phase
+  int phases;                     // 2: columns [0,C_out) / [C_out,2C_out) are output positions 2l / 2l+1 (transposed conv)
   int kchunks, kchunks2;          // channel chunks of the main conv / of the shortcut conv
   int in_batch_mod;
   cds_vec bias, scale, shift;
@@ -65,6 +66,7 @@ struct ConvTcCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kTcStages * kStageBytes + 1024;
   static constexpr uint32_t kTmemCols = (N * (HAS_RES ? 2 : 1)) < 32 ? 32 : (N * (HAS_RES ? 2 : 1));
+  static constexpr int kEpiSplit = N >= 32 ? 2 : 1;     // epilogue warps per TMEM lane quarter (column split)
 };
 
 template <int KC, int N, bool HAS_RES>
@@ -118,7 +120,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         if (!HAS_RES || kb < n_kb_main) {
           const int tap = kb / p.kchunks, ck = kb - tap * p.kchunks;
           ptx::tma_load_3d(sa, &p.tm_a, &full_bar[s], ck * KC, tap - p.pad, a_b0);
-          ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KC, tap * p.C_out);
+          ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KC, tap * p.C_out * p.phases);
         } else {
           const int ck = kb - n_kb_main;
           ptx::tma_load_3d(sa, &p.tm_a2, &full_bar[s], ck * KC, 0, r_b0);
@@ -154,24 +156,27 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     // ===================================== epilogue =====================================
     const int iter = iter_ptr ? *iter_ptr : 0;
     const int q = warp & 3;                         // TMEM lane quarter this warp may touch
-    const int half = (warp - 4) >> 2;               // which half of the N columns
-    constexpr int NH = N / 2;                       // columns per thread
-    constexpr int CPG = N / 8;                      // GroupNorm group width (groups == 8)
+    constexpr int EW = Cfg::kEpiSplit;
+    const int half = (warp - 4) >> 2;               // which slice of the N columns this warp handles
+    constexpr int NH = N / EW;                      // columns per thread
+    constexpr int CPG = N >= 32 ? N / 8 : 1;        // GroupNorm group width (groups == 8 and N == C_out)
     constexpr int NCHUNK = NH / 16;
+    const bool active = half < EW;
     const int m = 32 * q + lane;
     const int64_t row = (int64_t)blockIdx.x * 128 + m;
-    const bool valid = row < (int64_t)p.batch * p.L;
+    const bool valid = active && row < (int64_t)p.batch * p.L;
     const int b = (int)(row >> p.log2L), l = (int)(row & (p.L - 1));
     const int col0 = half * NH;
     const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)col0;
     const VecRef bias = resolve(p.bias, iter), scale = resolve(p.scale, iter), shift = resolve(p.shift, iter);
     const bool has_bias = bias.present(), has_scale = scale.present(), has_shift = shift.present();
+    const bool full_cols = (p.C_out * p.phases == N) && (p.C_out % 16 == 0);   // else: ragged N (C_out < 16), scalar stores
 
     ptx::mbar_wait(&tmem_full_bar, 0);
     ptx::tc_fence_after_sync();
 
     float mean[4], rstd[4];
-    if (p.groups > 0) {
+    if constexpr (N >= 32) if (p.groups > 0 && active) {
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ch = 0; ch < NCHUNK; ++ch) {
@@ -206,12 +211,15 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     const int rb = p.res_batch_mod > 0 ? b % p.res_batch_mod : b;
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
+      if (!active) break;                            // warp-uniform
       float v[16];
       ptx::tmem_ld_32x32b_x16(t_row + ch * 16, v);
       float r2[16];
       if (HAS_RES) ptx::tmem_ld_32x32b_x16(t_row + N + ch * 16, r2);
       if (valid) {
-        const int cbase = col0 + ch * 16;
+        const int ncol = col0 + ch * 16;             // first GEMM column of this chunk
+        const int phase = full_cols ? ncol / p.C_out : 0;
+        const int cbase = ncol - phase * p.C_out;    // channel of that column
         float resv[16];
         if (p.res) {
           const int64_t ro = (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + cbase;
@@ -237,8 +245,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int c = cbase + j;
+          if (!full_cols && c >= p.C_out) { v[j] = 0.f; continue; }
           float x = v[j] + (has_bias ? bias.at(b, c) : 0.f);
-          if (p.groups > 0) {
+          if constexpr (N >= 32) if (p.groups > 0) {
             const int g = (ch * 16 + j) / CPG;
             x = (x - mean[g]) * rstd[g];
             x = fmaf(x, __ldg(p.gn_gamma + c), __ldg(p.gn_beta + c));
@@ -250,8 +259,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
           if (HAS_RES) x += r2[j] + (p.res_bias ? __ldg(p.res_bias + c) : 0.f);
           v[j] = x;
         }
-        const int64_t oo = (int64_t)b * p.out_bstride + (int64_t)l * p.out_lstride + cbase;
-        if (p.out_dtype == 1) {
+        const int64_t oo = (int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + cbase;
+        if (!full_cols) {
+          for (int j = 0; j < 16 && cbase + j < p.C_out; ++j) {
+            if (p.out_dtype == 1) reinterpret_cast<__nv_bfloat16*>(p.out)[oo + j] = __float2bfloat16_rn(v[j]);
+            else reinterpret_cast<float*>(p.out)[oo + j] = v[j];
+          }
+        } else if (p.out_dtype == 1) {
           uint4 u0, u1;
           __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&u0);
           __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&u1);
@@ -298,12 +312,12 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 // bf16 tensor, dims innermost-first; strides in elements for dims 1.. (dim 0 is contiguous)
 inline bool encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
-                            const uint32_t* box, int kc) {
+                            const uint32_t* box, int kc, const uint32_t* elem_strides = nullptr) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t bx[3], es[3];
-  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_el[i - 1] * 2;
   CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
@@ -319,24 +333,38 @@ inline int conv_tc_pick_kc(const cds_conv_op& c) {
   return k64 ? 64 : 32;
 }
 
+// GEMM width of the op: C_out*phases, or 16 for a narrow (C_out <= 16) 1x1 head whose missing weight rows the TMA
+// unit zero-fills (out-of-bound rows of the weight tensor); 0 = not a width the kernel is instantiated for
+inline int conv_tc_width(const cds_conv_op& c) {
+  int n = c.C_out * c.phases;
+  if (n == 32 || n == 64 || n == 128 || n == 256) return (c.phases == 1 || c.C_out % 16 == 0) ? n : 0;
+  if (n <= 16 && c.phases == 1 && c.taps == 1 && c.groups == 0 && !c.res_w) return 16;
+  return 0;
+}
+
 // can the tensor-core kernel serve this op?  (otherwise the fp32 CUDA-core kernel runs it, any dtype)
 inline bool conv_tc_eligible(const cds_conv_op& c) {
   if (c.math != CDS_MATH_BF16_TC || c.in_dtype != 1) return false;
-  if (c.stride != 1 || c.phases != 1 || c.L_in != c.L_out) return false;
-  int L = c.L_out;
+  if (c.stride != 1 && c.stride != 2) return false;
+  if (c.phases != 1 && c.phases != 2) return false;
+  int L = c.L_out;                                   // tile rows = 128/L trajectories x L output positions
   if (L > 32 || (L & (L - 1)) != 0) return false;
-  int N = c.C_out;
-  if (N != 32 && N != 64 && N != 128 && N != 256) return false;
+  if (c.stride == 1 ? (c.L_in != L) : (c.L_in != 2 * L || c.phases != 1 || c.res_w || c.res)) return false;
+  if (conv_tc_width(c) == 0) return false;
   if (c.C_in % 32 != 0) return false;
-  if (c.groups != 0 && c.groups != 8) return false;
+  if (c.groups != 0 && (c.groups != 8 || c.phases != 1 || c.C_out < 32)) return false;
+  if (c.phases == 2 && (c.res || c.res_w)) return false;
   int T = 128 / L;
   if (c.in_batch_mod > 0 && c.in_batch_mod % T != 0) return false;
   if (c.res_batch_mod > 0 && c.res_batch_mod % T != 0) return false;
   if (c.res_w && (c.res_in_dtype != 1 || c.res_C % 32 != 0)) return false;
   if ((c.in_lstride % 8) || (c.in_bstride % 8) || ((uintptr_t)c.in % 16)) return false;
-  if (c.out_dtype == 1 ? ((c.out_lstride % 8) || ((uintptr_t)c.out % 16)) : ((c.out_lstride % 4) || ((uintptr_t)c.out % 16)))
+  if (c.C_out % 16 == 0) {                           // vector stores
+    if (c.out_dtype == 1 ? ((c.out_lstride % 8) || ((uintptr_t)c.out % 16)) : ((c.out_lstride % 4) || ((uintptr_t)c.out % 16)))
+      return false;
+  }
+  if (c.res && (c.res_dtype == 1 ? ((c.res_lstride % 8) || ((uintptr_t)c.res % 16)) : ((c.res_lstride % 4) || ((uintptr_t)c.res % 16))))
     return false;
-  if (c.res && (c.res_dtype == 1 ? (c.res_lstride % 8) : (c.res_lstride % 4))) return false;
   return true;
 }
 
@@ -351,20 +379,23 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
   ConvTcLaunch& L = *out;
   memset(&L.prm, 0, sizeof(L.prm));
   const int kc = conv_tc_pick_kc(c);
-  L.kc = kc; L.n = c.C_out; L.has_res = c.res_w != nullptr;
+  L.kc = kc; L.n = conv_tc_width(c); L.has_res = c.res_w != nullptr;
   ConvTcParams& p = L.prm;
   const int Lp = c.L_out, T = 128 / Lp;
   const uint64_t in_b = c.in_batch_mod > 0 ? (uint64_t)c.in_batch_mod : (uint64_t)c.batch;
   {
     uint64_t dims[3] = {(uint64_t)c.C_in, (uint64_t)c.L_in, in_b};
     uint64_t str[2] = {(uint64_t)c.in_lstride, (uint64_t)c.in_bstride};
-    uint32_t box[3] = {(uint32_t)kc, (uint32_t)Lp, (uint32_t)T};
-    if (!encode_bf16_map(&p.tm_a, c.in, 3, dims, str, box, kc)) return false;
+    // stride-2 conv: the box walks the position axis with element stride 2 (box extent = 2*L traversed -> L loaded)
+    uint32_t box[3] = {(uint32_t)kc, (uint32_t)(Lp * c.stride), (uint32_t)T};
+    uint32_t es[3] = {1u, (uint32_t)c.stride, 1u};
+    if (!encode_bf16_map(&p.tm_a, c.in, 3, dims, str, box, kc, es)) return false;
   }
   {
-    uint64_t dims[2] = {(uint64_t)c.C_in, (uint64_t)c.taps * c.C_out};
+    // weight rows beyond taps*C_out*phases (narrow heads padded to N=16) are zero-filled by the TMA unit
+    uint64_t dims[2] = {(uint64_t)c.C_in, (uint64_t)c.taps * c.C_out * c.phases};
     uint64_t str[1] = {(uint64_t)c.C_in};
-    uint32_t box[2] = {(uint32_t)kc, (uint32_t)c.C_out};
+    uint32_t box[2] = {(uint32_t)kc, (uint32_t)L.n};
     if (!encode_bf16_map(&p.tm_b, c.w, 2, dims, str, box, kc)) return false;
   }
   if (L.has_res) {
@@ -379,6 +410,7 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
     if (!encode_bf16_map(&p.tm_b2, c.res_w, 2, d2, s2, b2, kc)) return false;
   }
   p.batch = c.batch; p.L = Lp; p.log2L = ilog2(Lp); p.C_out = c.C_out; p.taps = c.taps; p.pad = c.pad;
+  p.phases = c.phases;
   p.kchunks = c.C_in / kc; p.kchunks2 = L.has_res ? c.res_C / kc : 0;
   p.in_batch_mod = c.in_batch_mod;
   p.bias = c.bias; p.scale = c.scale; p.shift = c.shift;
@@ -409,8 +441,8 @@ inline cudaError_t conv_tc_launch(const ConvTcLaunch& L, const int* iter_ptr, cu
 #define CDS_TC_CASE(KC_, N_)                                                                     \
   if (L.kc == KC_ && L.n == N_)                                                                  \
     return L.has_res ? conv_tc_launch_t<KC_, N_, true>(L, iter_ptr, st) : conv_tc_launch_t<KC_, N_, false>(L, iter_ptr, st);
-  CDS_TC_CASE(64, 32) CDS_TC_CASE(64, 64) CDS_TC_CASE(64, 128) CDS_TC_CASE(64, 256)
-  CDS_TC_CASE(32, 32) CDS_TC_CASE(32, 64) CDS_TC_CASE(32, 128) CDS_TC_CASE(32, 256)
+  CDS_TC_CASE(64, 16) CDS_TC_CASE(64, 32) CDS_TC_CASE(64, 64) CDS_TC_CASE(64, 128) CDS_TC_CASE(64, 256)
+  CDS_TC_CASE(32, 16) CDS_TC_CASE(32, 32) CDS_TC_CASE(32, 64) CDS_TC_CASE(32, 128) CDS_TC_CASE(32, 256)
 #undef CDS_TC_CASE
   return cudaErrorInvalidValue;
 }

@@ -2,6 +2,8 @@
 // pre-scale (CDS_OP_PREP) and LayerNorm+modulate (CDS_OP_LNMOD).  All HBM-bound streaming kernels:
 // algorithmic bytes per element are listed with each kernel.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace cds {
@@ -106,6 +108,21 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const cds_lnmod_op p) 
     const float* sc = p.scale + (int64_t)b * p.mod_bstride;
     float* dst = p.out + r * p.C;
     for (int c = lane; c < p.C; c += 32) dst[c] = fmaf((src[c] - mean) * rstd, 1.f + sc[c], sh[c]);
+  }
+}
+
+// fp32 (rows, C_in) -> bf16 (rows, C_out) zero padded; one thread per output pair.  4*C_in + 2*C_out B / row
+__global__ void __launch_bounds__(256) cast_pad_kernel(const cds_cast_op p) {
+  const int64_t rows = (int64_t)p.batch * p.L;
+  const int pairs = p.C_out >> 1;
+  const int64_t total = rows * pairs;
+  __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(p.out);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / pairs;
+    const int c = (int)(i - r * pairs) * 2;
+    const float a = c < p.C_in ? p.in[r * p.C_in + c] : 0.f;
+    const float b = c + 1 < p.C_in ? p.in[r * p.C_in + c + 1] : 0.f;
+    out[i] = __floats2bfloat162_rn(a, b);
   }
 }
 

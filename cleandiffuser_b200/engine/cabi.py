@@ -11,7 +11,7 @@ import os
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "libcds.so")
 
 ABI_VERSION = 1
-OP_CONV, OP_UPDATE, OP_LNMOD, OP_ATTN, OP_PREP = range(5)
+OP_CONV, OP_UPDATE, OP_LNMOD, OP_ATTN, OP_PREP, OP_CAST = range(6)
 ACT_NONE, ACT_MISH, ACT_SILU, ACT_GELU_TANH, ACT_MISH_SILU = range(5)
 MATH_FP32, MATH_BF16_TC = 0, 1
 F32, BF16 = 0, 1
@@ -59,6 +59,11 @@ class PrepOp(C.Structure):
                 ("coef", _f32p)]
 
 
+class CastOp(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("L", C.c_int32), ("C_in", C.c_int32), ("C_out", C.c_int32),
+                ("in_", _f32p), ("out", C.c_void_p)]
+
+
 class UpdateOp(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("row", C.c_int32), ("x", _f32p),
@@ -69,7 +74,8 @@ class UpdateOp(C.Structure):
 
 
 class _OpUnion(C.Union):
-    _fields_ = [("conv", ConvOp), ("update", UpdateOp), ("lnmod", LnModOp), ("attn", AttnOp), ("prep", PrepOp)]
+    _fields_ = [("conv", ConvOp), ("update", UpdateOp), ("lnmod", LnModOp), ("attn", AttnOp), ("prep", PrepOp),
+                ("cast", CastOp)]
 
 
 class Op(C.Structure):

@@ -87,9 +87,18 @@ class WSpec:
         self.kn, self.nk = kn, nk
 
 
-def w_conv(conv: nn.Conv1d) -> WSpec:                        # [Cout, Cin, k]
-    return WSpec(lambda: conv.weight.permute(2, 1, 0).reshape(-1, conv.weight.shape[0]),
-                 lambda: conv.weight.permute(2, 0, 1))
+def _pad_cin(w: torch.Tensor, cin: Optional[int]) -> torch.Tensor:
+    """Zero-pad dim 1 (input channels) of a [Cout, Cin, ...] weight up to ``cin`` (x_t is fed 32-channel padded)."""
+    if cin is None or cin == w.shape[1]:
+        return w
+    out = torch.zeros((w.shape[0], cin, *w.shape[2:]), device=w.device, dtype=w.dtype)
+    out[:, :w.shape[1]] = w
+    return out
+
+
+def w_conv(conv: nn.Conv1d, cin: Optional[int] = None) -> WSpec:           # [Cout, Cin, k]
+    return WSpec(lambda: _pad_cin(conv.weight, cin).permute(2, 1, 0).reshape(-1, conv.weight.shape[0]),
+                 lambda: _pad_cin(conv.weight, cin).permute(2, 0, 1))
 
 
 def w_linear(weight: torch.Tensor, cols: Optional[slice] = None) -> WSpec:    # [out, in]
@@ -113,7 +122,10 @@ def w_convT(conv: nn.ConvTranspose1d) -> WSpec:
         p[1, :, cout:] = w[:, :, 2]
         p[2, :, cout:] = w[:, :, 0]
         return p.reshape(3 * cin, 2 * cout)
-    return WSpec(make, None)
+
+    def make_nk():                                           # [3][2*Cout][Cin]
+        return make().reshape(3, conv.weight.shape[0], -1).permute(0, 2, 1)
+    return WSpec(make, make_nk)
 
 
 class Program:
@@ -191,7 +203,7 @@ class Program:
             use_tc = bool(cabi.load().cds_conv_tc_supported(C.byref(c)))
         c.math = cabi.MATH_BF16_TC if use_tc else cabi.MATH_FP32
         if use_tc:
-            wt = self.packed(lambda: w.nk().reshape(taps * out.C, x.C), torch.bfloat16)
+            wt = self.packed(lambda: w.nk().reshape(taps * out.C * phases, x.C), torch.bfloat16)
         else:
             wt = self.packed(w.kn)
             assert wt.shape == (taps * x.C, out.C * phases), (wt.shape, taps, x.C, out.C, phases)
@@ -200,6 +212,18 @@ class Program:
             rw = res_conv[1]
             rwt = self.packed(lambda: rw.nk().reshape(out.C, rx.C), torch.bfloat16) if use_tc else self.packed(rw.kn)
             c.res_w, c.res_bias = rwt.data_ptr(), self.packed(res_conv[2]).data_ptr()
+        self.ops.append(op)
+        return out
+
+    def cast_pad(self, x: View, width: int) -> View:
+        """fp32 dense (rows, L, C) -> bf16 dense (rows, L, width) with zero channels appended."""
+        assert x.t.dtype == torch.float32 and x.lstride == x.C and x.bstride == x.L * x.C
+        rows = x.t.shape[0]
+        out = View(self.buf(rows, x.L, width, dtype=torch.bfloat16), x.L, width)
+        op = cabi.Op()
+        op.kind = cabi.OP_CAST
+        k = op.u.cast
+        k.batch, k.L, k.C_in, k.C_out, k.in_, k.out = rows, x.L, x.C, int(width), x.ptr, out.ptr
         self.ops.append(op)
         return out
 
@@ -228,7 +252,7 @@ def _lower_conv_block(p: Program, seq: nn.Sequential, x: View, out: View, k: int
     conv, gn = seq[0], seq[1]
     if not isinstance(gn, GroupNorm1d):
         raise Unsupported("norm_type other than groupnorm")
-    return p.conv(x, w_conv(conv), out, taps=k, pad=k // 2, bias=_const_vec(p.packed(lambda: conv.bias)),
+    return p.conv(x, w_conv(conv, x.C), out, taps=k, pad=k // 2, bias=_const_vec(p.packed(lambda: conv.bias)),
                   gn=gn, act=cabi.ACT_MISH, **kw)
 
 
@@ -238,7 +262,7 @@ def _lower_resblock(p: Program, blk, x: View, out: View, k: int, cond: dict):
     _lower_conv_block(p, blk.conv1, x, h, k, **cond)
     if isinstance(blk.residual_conv, nn.Conv1d):
         rc = blk.residual_conv
-        shortcut = dict(res_conv=(x, w_rows(lambda: rc.weight[:, :, 0]), lambda: rc.bias))
+        shortcut = dict(res_conv=(x, w_rows(lambda: _pad_cin(rc.weight, x.C)[:, :, 0]), lambda: rc.bias))
     else:
         shortcut = dict(res=x)
     return _lower_conv_block(p, blk.conv2, h, out, k, **shortcut)
@@ -502,6 +526,8 @@ def lower_dit(p: Program, net: DiT1d, x: View, horizon: int, has_cond: bool, in_
 def lower_denoiser(p: Program, net: nn.Module, x: View, x_shape, has_cond: bool, in_batch_mod: int) -> View:
     """Dispatch on the backbone type (reference instances are recognised structurally by class name)."""
     name = type(net).__name__
+    if name in ("JannerUNet1d", "ChiUNet1d") and len(x_shape) == 2 and p.math == cabi.MATH_BF16_TC:
+        x = p.cast_pad(x, 32 * ((x.C + 31) // 32))           # TMA/UMMA want K in multiples of 32 bf16
     if name == "JannerUNet1d" and len(x_shape) == 2:
         return lower_janner(p, net, x, x_shape[0], has_cond, in_batch_mod)
     if name == "ChiUNet1d" and len(x_shape) == 2:

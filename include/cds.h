@@ -16,6 +16,7 @@
  *   CDS_OP_LNMOD        LayerNorm(no affine) + adaLN modulate (dit.py:10-11,19,21,33,35,49)
  *   CDS_OP_ATTN         nn.MultiheadAttention core softmax(QK^T/sqrt(hd))V per (trajectory, head) (dit.py:20,34)
  *   CDS_OP_PREP         consistency-model re-noise + c_in pre-scale (consistency_model.py:257,423)
+ *   CDS_OP_CAST         x.permute(0,2,1) entry of the UNets (jannerunet.py:169, chiunet.py:142): layout/dtype hand-over of x_t
  *   CDS_OP_UPDATE       CFG combine, clip_prediction, eps<->x0 conversion, the 8 solver updates, fix_mask
  *                       (diffusionsde.py:202,208-223,539-592) and the CM skip/out combine (consistency_model.py:257-262)
  *
@@ -54,7 +55,8 @@ typedef enum cds_status {
   CDS_ERR_STATE = -4         /* call order violated (e.g. run before finalize) */
 } cds_status;
 
-typedef enum cds_op_kind { CDS_OP_CONV = 0, CDS_OP_UPDATE = 1, CDS_OP_LNMOD = 2, CDS_OP_ATTN = 3, CDS_OP_PREP = 4 } cds_op_kind;
+typedef enum cds_op_kind { CDS_OP_CONV = 0, CDS_OP_UPDATE = 1, CDS_OP_LNMOD = 2, CDS_OP_ATTN = 3, CDS_OP_PREP = 4,
+                           CDS_OP_CAST = 5 } cds_op_kind;
 typedef enum cds_act { CDS_ACT_NONE = 0, CDS_ACT_MISH = 1, CDS_ACT_SILU = 2, CDS_ACT_GELU_TANH = 3,
                        CDS_ACT_MISH_SILU = 4 /* silu(mish(x)): DiT's map_emb tail feeding every adaLN (dit.py:26,43,71) */ } cds_act;
 /* math mode of CDS_OP_CONV: fp32 CUDA-core FMA (bit-faithful to the fp32 oracle up to summation order), or
@@ -116,6 +118,13 @@ typedef struct cds_attn_op {
   const float* qkv; float* out;
 } cds_attn_op;
 
+/* dense fp32 (batch, L, C_in) -> dense bf16 (batch, L, C_out), channels [C_in, C_out) zero: gives x_t the 32-channel
+ * bf16 form the tensor-core conv reads through TMA (the UNets' first conv has C_in = obs+act dims, e.g. 14) */
+typedef struct cds_cast_op {
+  int32_t batch, L, C_in, C_out;
+  const float* in; void* out;
+} cds_cast_op;
+
 /* consistency model: if row.NOISE: x += K2 * noise[slot];  xin = K3 * x */
 typedef struct cds_prep_op {
   int32_t batch, row;
@@ -142,7 +151,7 @@ typedef struct cds_update_op {
 typedef struct cds_op {
   int32_t kind;                  /* cds_op_kind */
   int32_t reserved;
-  union { cds_conv_op conv; cds_update_op update; cds_lnmod_op lnmod; cds_attn_op attn; cds_prep_op prep; } u;
+  union { cds_conv_op conv; cds_update_op update; cds_lnmod_op lnmod; cds_attn_op attn; cds_prep_op prep; cds_cast_op cast; } u;
 } cds_op;
 
 typedef struct cds_plan cds_plan;

@@ -84,9 +84,9 @@ def run_conv(c, it):
     xin = _load(c.in_, (bmod, c.L_in, c.C_in), (c.in_bstride, c.in_lstride, 1), c.in_dtype)
     xin = xin[np.arange(B) % bmod]
     tc = c.math == cabi.MATH_BF16_TC
-    if tc:      # bf16 [taps][C_out][C_in]
-        assert c.phases == 1 and c.in_dtype == cabi.BF16
-        w = _load(c.w, (c.taps, c.C_out, c.C_in), (c.C_out * c.C_in, c.C_in, 1), cabi.BF16).transpose(0, 2, 1)
+    if tc:      # bf16 [taps][C_out*phases][C_in]
+        assert c.in_dtype == cabi.BF16
+        w = _load(c.w, (c.taps, N, c.C_in), (N * c.C_in, c.C_in, 1), cabi.BF16).transpose(0, 2, 1)
     else:
         w = _arr(c.w, (c.taps, c.C_in, N), (c.C_in * N, N, 1))
     acc = np.zeros((B, c.L_out, N), dtype=np.float64)
@@ -148,6 +148,13 @@ def run_attn(a):
     s /= s.sum(-1, keepdims=True)
     o = (s @ v).transpose(0, 2, 1, 3).reshape(a.batch, a.L, a.C)
     _arr(a.out, (a.batch, a.L, a.C), (a.L * a.C, a.C, 1))[...] = o.astype(np.float32)
+
+
+def run_cast(k):
+    x = _arr(k.in_, (k.batch, k.L, k.C_in), (k.L * k.C_in, k.C_in, 1))
+    y = np.zeros((k.batch, k.L, k.C_out), dtype=np.float32)
+    y[..., :k.C_in] = x
+    _store(k.out, (k.batch, k.L, k.C_out), (k.L * k.C_out, k.C_out, 1), cabi.BF16, y)
 
 
 def _row(coef, it):
@@ -231,5 +238,7 @@ def run_program(ops, n_iters, first=0):
                     run_attn(op.u.attn)
                 elif op.kind == cabi.OP_PREP:
                     run_prep(op.u.prep, it)
+                elif op.kind == cabi.OP_CAST:
+                    run_cast(op.u.cast)
                 else:
                     raise ValueError(op.kind)
