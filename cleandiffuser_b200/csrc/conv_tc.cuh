@@ -20,12 +20,16 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
 namespace cds {
 
-constexpr int kTcThreads = 384;   // 12 warps: producer, mma, tmem-alloc, spare, 8 epilogue
+constexpr int kTcThreads = 320;   // warps 0-7 epilogue (TMEM lane quarter = warp % 4, column slice = warp / 4),
+                                  // warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer
+constexpr int kTcEpiThreads = 256;
 constexpr int kTcStages = 4;
 
 struct ConvTcParams {
@@ -67,10 +71,62 @@ struct ConvTcCfg {
   static constexpr int kSmemBytes = kTcStages * kStageBytes + 1024;
   static constexpr uint32_t kTmemCols = (N * (HAS_RES ? 2 : 1)) < 32 ? 32 : (N * (HAS_RES ? 2 : 1));
   static constexpr int kEpiSplit = N >= 32 ? 2 : 1;     // epilogue warps per TMEM lane quarter (column split)
+  static constexpr int kMinBlocks = N <= 64 ? 3 : (N <= 128 ? 2 : 1);
 };
 
+// W consecutive activations (bf16 or fp32) <-> registers, 8/16-byte vector accesses
+template <int W>
+__device__ __forceinline__ void load_row(const void* base, int64_t off, int dtype, float (&r)[W]) {
+  if (dtype == CDS_BF16) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + off;
+    if constexpr (W == 4) {
+      uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+      r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < W / 8; ++k) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + k);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); r[8 * k + 2 * j] = f.x; r[8 * k + 2 * j + 1] = f.y; }
+      }
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+#pragma unroll
+    for (int k = 0; k < W / 4; ++k) { float4 f = __ldg(p + k); r[4 * k] = f.x; r[4 * k + 1] = f.y; r[4 * k + 2] = f.z; r[4 * k + 3] = f.w; }
+  }
+}
+template <int W>
+__device__ __forceinline__ void store_row(void* base, int64_t off, int dtype, const float (&v)[W]) {
+  if (dtype == CDS_BF16) {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + off;
+    if constexpr (W == 4) {
+      uint2 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+      h[0] = __floats2bfloat162_rn(v[0], v[1]); h[1] = __floats2bfloat162_rn(v[2], v[3]);
+      *reinterpret_cast<uint2*>(p) = u;
+    } else {
+#pragma unroll
+      for (int k = 0; k < W / 8; ++k) {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[8 * k + 2 * j], v[8 * k + 2 * j + 1]);
+        reinterpret_cast<uint4*>(p)[k] = u;
+      }
+    }
+  } else {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+#pragma unroll
+    for (int k = 0; k < W / 4; ++k) p[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  }
+}
+
 template <int KC, int N, bool HAS_RES>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, ConvTcCfg<KC, N, HAS_RES>::kMinBlocks)
 conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ iter_ptr) {
   using Cfg = ConvTcCfg<KC, N, HAS_RES>;
   extern __shared__ uint8_t smem_raw[];
@@ -78,6 +134,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   __shared__ __align__(8) uint64_t empty_bar[kTcStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_holder;
+  // per-column constants of the epilogue, staged once per CTA while the main loop runs:
+  // 0 bias  1 GN gamma  2 GN beta  3 FiLM scale  4 FiLM shift  5 shortcut bias   (iteration-indexed "step" parts)
+  __shared__ __align__(16) float s_col[6][N];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // operand ring, 1024-byte aligned (swizzle atoms)
@@ -94,18 +153,18 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     ptx::mbar_init(&tmem_full_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tensormap(&p.tm_a);
     ptx::prefetch_tensormap(&p.tm_b);
     if (HAS_RES) { ptx::prefetch_tensormap(&p.tm_a2); ptx::prefetch_tensormap(&p.tm_b2); }
   }
-  if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
+  if (warp == 9) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_holder;
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ===================================== TMA producer =====================================
     if (ptx::elect_one()) {
       const int a_b0 = p.in_batch_mod > 0 ? b0 % p.in_batch_mod : b0;
@@ -128,7 +187,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ===================================== MMA issuer =====================================
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, N);
@@ -152,142 +211,130 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       }
       ptx::umma_commit(&tmem_full_bar);           // accumulators complete
     }
-  } else if (warp >= 4) {
-    // ===================================== epilogue =====================================
+  } else {
+    // ===================================== epilogue (warps 0..7) =====================================
     const int iter = iter_ptr ? *iter_ptr : 0;
-    const int q = warp & 3;                         // TMEM lane quarter this warp may touch
     constexpr int EW = Cfg::kEpiSplit;
-    const int half = (warp - 4) >> 2;               // which slice of the N columns this warp handles
     constexpr int NH = N / EW;                      // columns per thread
-    constexpr int CPG = N >= 32 ? N / 8 : 1;        // GroupNorm group width (groups == 8 and N == C_out)
-    constexpr int NCHUNK = NH / 16;
-    const bool active = half < EW;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may touch
+    const int half = warp >> 2;                     // which slice of the N columns this warp handles
+    const bool active = half < EW;                  // warp-uniform (N = 16: only warps 0..3 work)
+    const int n_real = p.C_out * p.phases;          // < N only for narrow heads (C_out <= 16)
+
+    // ---- stage the per-column constants (overlaps with the TMA/MMA main loop)
+    {
+      const float* bstep = p.bias.step ? p.bias.step + (int64_t)iter * p.bias.step_stride : nullptr;
+      const float* sstep = p.scale.step ? p.scale.step + (int64_t)iter * p.scale.step_stride : nullptr;
+      const float* hstep = p.shift.step ? p.shift.step + (int64_t)iter * p.shift.step_stride : nullptr;
+      const bool scale_any = p.scale.step || p.scale.sample;
+      for (int n = threadIdx.x; n < N; n += kTcEpiThreads) {
+        const bool real = n < n_real;
+        const int c = real ? n % p.C_out : 0;
+        s_col[0][n] = (real && bstep) ? __ldg(bstep + c) : 0.f;
+        s_col[1][n] = (real && p.groups > 0) ? __ldg(p.gn_gamma + c) : 1.f;
+        s_col[2][n] = (real && p.groups > 0) ? __ldg(p.gn_beta + c) : 0.f;
+        s_col[3][n] = sstep ? (real ? __ldg(sstep + c) : 0.f) : (scale_any ? 0.f : 1.f);
+        s_col[4][n] = (real && hstep) ? __ldg(hstep + c) : 0.f;
+        s_col[5][n] = (real && HAS_RES && p.res_bias) ? __ldg(p.res_bias + c) : 0.f;
+      }
+      ptx::named_bar_sync(1, kTcEpiThreads);
+    }
+
     const int m = 32 * q + lane;
     const int64_t row = (int64_t)blockIdx.x * 128 + m;
     const bool valid = active && row < (int64_t)p.batch * p.L;
     const int b = (int)(row >> p.log2L), l = (int)(row & (p.L - 1));
     const int col0 = half * NH;
-    const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)col0;
-    const VecRef bias = resolve(p.bias, iter), scale = resolve(p.scale, iter), shift = resolve(p.shift, iter);
-    const bool has_bias = bias.present(), has_scale = scale.present(), has_shift = shift.present();
-    const bool full_cols = (p.C_out * p.phases == N) && (p.C_out % 16 == 0);   // else: ragged N (C_out < 16), scalar stores
+    const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16);
+    const float* bias_smp = p.bias.sample ? p.bias.sample + (int64_t)b * p.bias.sample_stride : nullptr;
+    const float* scale_smp = p.scale.sample ? p.scale.sample + (int64_t)b * p.scale.sample_stride : nullptr;
+    const float* shift_smp = p.shift.sample ? p.shift.sample + (int64_t)b * p.shift.sample_stride : nullptr;
+    const int rb = p.res_batch_mod > 0 ? b % p.res_batch_mod : b;
 
     ptx::mbar_wait(&tmem_full_bar, 0);
     ptx::tc_fence_after_sync();
 
-    float mean[4], rstd[4];
-    if constexpr (N >= 32) if (p.groups > 0 && active) {
-      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    // one group of W columns starting at GEMM column n0: TMEM -> registers -> full post-processing -> global
+    auto finish = [&](auto w_tag, int n0, bool gn, float mean, float rstd) {
+      constexpr int W = decltype(w_tag)::value;
+      float v[W], r2[W];
+      ptx::tmem_ld<W>(t_row + (uint32_t)n0, v);
+      if constexpr (HAS_RES) ptx::tmem_ld<W>(t_row + (uint32_t)(N + n0), r2);
+      if (!valid) return;
+      const int phase = n0 / p.C_out >= p.phases ? 0 : n0 / p.C_out;
+      const int c0 = n0 - phase * p.C_out;                       // first channel of the group
+      float resv[W];
+      const bool io_vec = n_real == N;
+      if (p.res && io_vec) load_row<W>(p.res, (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + c0, p.res_dtype, resv);
 #pragma unroll
-      for (int ch = 0; ch < NCHUNK; ++ch) {
-        float v[16];
-        ptx::tmem_ld_32x32b_x16(t_row + ch * 16, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = ch * 16 + j;                // column inside this thread's half
-          float x = v[j] + (has_bias ? bias.at(b, col0 + c) : 0.f);
-          x = valid ? x : 0.f;
-          s1[c / CPG] += x;
-          s2[c / CPG] = fmaf(x, x, s2[c / CPG]);
+      for (int j = 0; j < W; ++j) {
+        const int n = n0 + j, c = c0 + j;
+        float x = v[j] + s_col[0][n];
+        if (bias_smp && c < p.C_out) x += __ldg(bias_smp + c);
+        if (gn) x = fmaf((x - mean) * rstd, s_col[1][n], s_col[2][n]);
+        x = tc_act(p.act, x);
+        float sc = s_col[3][n], sh = s_col[4][n];
+        if (scale_smp && c < p.C_out) sc += __ldg(scale_smp + c);
+        if (shift_smp && c < p.C_out) sh += __ldg(shift_smp + c);
+        x = fmaf(x, sc, sh);
+        if (p.res && io_vec) x += resv[j];
+        if constexpr (HAS_RES) x += r2[j] + s_col[5][n];
+        v[j] = x;
+      }
+      const int64_t oo = (int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + c0;
+      if (io_vec) {
+        store_row<W>(p.out, oo, p.out_dtype, v);
+      } else {
+        for (int j = 0; j < W && c0 + j < p.C_out; ++j) {
+          if (p.out_dtype == CDS_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[oo + j] = __float2bfloat16_rn(v[j]);
+          else reinterpret_cast<float*>(p.out)[oo + j] = v[j];
         }
       }
-      // reduce over the L lanes (positions) of this trajectory
-      for (int off = p.L >> 1; off >= 1; off >>= 1) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          s1[g] += __shfl_xor_sync(0xffffffffu, s1[g], off);
-          s2[g] += __shfl_xor_sync(0xffffffffu, s2[g], off);
-        }
-      }
-      const float inv_cnt = 1.f / (float)(p.L * CPG);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        mean[g] = s1[g] * inv_cnt;
-        float var = fmaxf(s2[g] * inv_cnt - mean[g] * mean[g], 0.f);
-        rstd[g] = rsqrtf(var + p.gn_eps);
-      }
-    }
+    };
 
-    const int rb = p.res_batch_mod > 0 ? b % p.res_batch_mod : b;
+    if (active) {
+      if constexpr (N >= 32) {
+        if (p.groups > 0) {
+          // GroupNorm (8 groups, N == C_out): this thread's slice holds 4 whole groups of CPG columns
+          constexpr int CPG = N / 8;
+          float mean[4], rstd[4];
 #pragma unroll
-    for (int ch = 0; ch < NCHUNK; ++ch) {
-      if (!active) break;                            // warp-uniform
-      float v[16];
-      ptx::tmem_ld_32x32b_x16(t_row + ch * 16, v);
-      float r2[16];
-      if (HAS_RES) ptx::tmem_ld_32x32b_x16(t_row + N + ch * 16, r2);
-      if (valid) {
-        const int ncol = col0 + ch * 16;             // first GEMM column of this chunk
-        const int phase = full_cols ? ncol / p.C_out : 0;
-        const int cbase = ncol - phase * p.C_out;    // channel of that column
-        float resv[16];
-        if (p.res) {
-          const int64_t ro = (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + cbase;
-          if (p.res_dtype == 1) {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + ro);
-            uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
-            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
-            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+          for (int g = 0; g < 4; ++g) {
+            float v[CPG];
+            const int n0 = col0 + g * CPG;
+            ptx::tmem_ld<CPG>(t_row + (uint32_t)n0, v);
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
-              resv[2 * j] = f0.x; resv[2 * j + 1] = f0.y; resv[8 + 2 * j] = f1.x; resv[8 + 2 * j + 1] = f1.y;
+            for (int j = 0; j < CPG; ++j) {
+              float x = v[j] + s_col[0][n0 + j];
+              if (bias_smp) x += __ldg(bias_smp + n0 + j);
+              x = valid ? x : 0.f;
+              s1 += x;
+              s2 = fmaf(x, x, s2);
             }
-          } else {
-            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + ro);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 f = __ldg(rp + j);
-              resv[4 * j] = f.x; resv[4 * j + 1] = f.y; resv[4 * j + 2] = f.z; resv[4 * j + 3] = f.w;
+            for (int off = p.L >> 1; off >= 1; off >>= 1) {       // over the L lanes (positions) of this trajectory
+              s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, off);
             }
+            const float inv_cnt = 1.f / (float)(p.L * CPG);
+            mean[g] = s1 * inv_cnt;
+            rstd[g] = rsqrtf(fmaxf(s2 * inv_cnt - mean[g] * mean[g], 0.f) + p.gn_eps);
           }
-        }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = cbase + j;
-          if (!full_cols && c >= p.C_out) { v[j] = 0.f; continue; }
-          float x = v[j] + (has_bias ? bias.at(b, c) : 0.f);
-          if constexpr (N >= 32) if (p.groups > 0) {
-            const int g = (ch * 16 + j) / CPG;
-            x = (x - mean[g]) * rstd[g];
-            x = fmaf(x, __ldg(p.gn_gamma + c), __ldg(p.gn_beta + c));
-          }
-          x = tc_act(p.act, x);
-          if (has_scale) x *= scale.at(b, c);
-          if (has_shift) x += shift.at(b, c);
-          if (p.res) x += resv[j];
-          if (HAS_RES) x += r2[j] + (p.res_bias ? __ldg(p.res_bias + c) : 0.f);
-          v[j] = x;
-        }
-        const int64_t oo = (int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + cbase;
-        if (!full_cols) {
-          for (int j = 0; j < 16 && cbase + j < p.C_out; ++j) {
-            if (p.out_dtype == 1) reinterpret_cast<__nv_bfloat16*>(p.out)[oo + j] = __float2bfloat16_rn(v[j]);
-            else reinterpret_cast<float*>(p.out)[oo + j] = v[j];
-          }
-        } else if (p.out_dtype == 1) {
-          uint4 u0, u1;
-          __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&u0);
-          __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&u1);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
-          }
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + oo);
-          op[0] = u0; op[1] = u1;
+          for (int g = 0; g < 4; ++g) finish(std::integral_constant<int, CPG>{}, col0 + g * CPG, true, mean[g], rstd[g]);
         } else {
-          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oo);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+#pragma unroll 1
+          for (int ch = 0; ch < NH / 16; ++ch) finish(std::integral_constant<int, 16>{}, col0 + ch * 16, false, 0.f, 1.f);
         }
+      } else {
+        finish(std::integral_constant<int, 16>{}, 0, false, 0.f, 1.f);
       }
     }
     ptx::tc_fence_before_sync();
   }
 
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 9) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
@@ -430,6 +477,10 @@ inline cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, 
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    // several CTAs per SM for the narrow tiles: ask for the maximum shared-memory carve-out
+    e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     attr = true;
   }

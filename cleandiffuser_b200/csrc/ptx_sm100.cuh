@@ -91,18 +91,44 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// ---------------------------------------------------------------- tcgen05: TMEM -> registers (32 lanes x 32b, N columns)
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
+// ---------------------------------------------------------------- tcgen05: TMEM -> registers
+// 32 lanes x 32 bit, W consecutive columns: lane i of the warp receives columns [c, c+W) of TMEM lane (quarter*32 + i).
+#define CDS_R4(o)  "=r"(r[o]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3])
+#define CDS_R8(o)  CDS_R4(o), CDS_R4(o + 4)
+#define CDS_R16(o) CDS_R8(o), CDS_R8(o + 8)
+template <int W>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[W]) {
+  static_assert(W == 4 || W == 8 || W == 16 || W == 32, "unsupported tcgen05.ld width");
+  uint32_t r[W];
+  if constexpr (W == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : CDS_R4(0) : "r"(taddr));
+  } else if constexpr (W == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : CDS_R8(0) : "r"(taddr));
+  } else if constexpr (W == 16) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : CDS_R16(0)
+        : "r"(taddr));
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : CDS_R16(0), CDS_R16(16)
+        : "r"(taddr));
+  }
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < W; ++i) v[i] = __uint_as_float(r[i]);
+}
+#undef CDS_R4
+#undef CDS_R8
+#undef CDS_R16
+
+// named barrier among a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
 // ---------------------------------------------------------------- descriptors
