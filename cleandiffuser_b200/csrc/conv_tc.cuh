@@ -52,13 +52,21 @@ __device__ __forceinline__ float fast_mish(float x) {
   float n = e * (e + 2.f);
   return x > 20.f ? x : x * __fdividef(n, n + 2.f);
 }
+// ACT is a compile-time constant inside the unrolled epilogue loops (a runtime switch there multiplies the code size
+// by the number of activations and thrashes the instruction cache); kActOther keeps the generic runtime switch.
+constexpr int kActOther = -1;
+template <int ACT>
 __device__ __forceinline__ float tc_act(int act, float x) {
-  switch (act) {
-    case CDS_ACT_MISH: return fast_mish(x);
-    case CDS_ACT_SILU: return x * __fdividef(1.f, 1.f + __expf(-x));
-    case CDS_ACT_GELU_TANH: return act_gelu_tanh(x);
-    case CDS_ACT_MISH_SILU: { float m = fast_mish(x); return m * __fdividef(1.f, 1.f + __expf(-m)); }
-    default: return x;
+  if constexpr (ACT == CDS_ACT_NONE) return x;
+  else if constexpr (ACT == CDS_ACT_MISH) return fast_mish(x);
+  else {
+    switch (act) {
+      case CDS_ACT_SILU: return x * __fdividef(1.f, 1.f + __expf(-x));
+      case CDS_ACT_GELU_TANH: { float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);   // tanh(u) = 1 - 2/(e^{2u}+1)
+                                float th = 1.f - __fdividef(2.f, __expf(2.f * u) + 1.f); return 0.5f * x * (1.f + th); }
+      case CDS_ACT_MISH_SILU: { float m = fast_mish(x); return m * __fdividef(1.f, 1.f + __expf(-m)); }
+      default: return x;
+    }
   }
 }
 
@@ -254,9 +262,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     ptx::mbar_wait(&tmem_full_bar, 0);
     ptx::tc_fence_after_sync();
 
-    // one group of W columns starting at GEMM column n0: TMEM -> registers -> full post-processing -> global
-    auto finish = [&](auto w_tag, int n0, bool gn, float mean, float rstd) {
+    // one group of W columns starting at GEMM column n0: TMEM -> registers -> full post-processing -> global.
+    // W, GN, ACT and SMP (any per-trajectory bias/scale/shift vector) are compile-time so the unrolled body is branch-free.
+    auto finish = [&](auto w_tag, auto gn_tag, auto act_tag, auto smp_tag, int n0, float mean, float rstd) {
       constexpr int W = decltype(w_tag)::value;
+      constexpr bool GN = decltype(gn_tag)::value;
+      constexpr int ACT = decltype(act_tag)::value;
+      constexpr bool SMP = decltype(smp_tag)::value;
       float v[W], r2[W];
       ptx::tmem_ld<W>(t_row + (uint32_t)n0, v);
       if constexpr (HAS_RES) ptx::tmem_ld<W>(t_row + (uint32_t)(N + n0), r2);
@@ -265,19 +277,22 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       const int c0 = n0 - phase * p.C_out;                       // first channel of the group
       float resv[W];
       const bool io_vec = n_real == N;
-      if (p.res && io_vec) load_row<W>(p.res, (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + c0, p.res_dtype, resv);
+      const bool add_res = p.res != nullptr && io_vec;
+      if (add_res) load_row<W>(p.res, (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + c0, p.res_dtype, resv);
 #pragma unroll
       for (int j = 0; j < W; ++j) {
         const int n = n0 + j, c = c0 + j;
         float x = v[j] + s_col[0][n];
-        if (bias_smp && c < p.C_out) x += __ldg(bias_smp + c);
-        if (gn) x = fmaf((x - mean) * rstd, s_col[1][n], s_col[2][n]);
-        x = tc_act(p.act, x);
+        if constexpr (SMP) { if (bias_smp && c < p.C_out) x += __ldg(bias_smp + c); }
+        if constexpr (GN) x = fmaf((x - mean) * rstd, s_col[1][n], s_col[2][n]);
+        x = tc_act<ACT>(p.act, x);
         float sc = s_col[3][n], sh = s_col[4][n];
-        if (scale_smp && c < p.C_out) sc += __ldg(scale_smp + c);
-        if (shift_smp && c < p.C_out) sh += __ldg(shift_smp + c);
+        if constexpr (SMP) {
+          if (scale_smp && c < p.C_out) sc += __ldg(scale_smp + c);
+          if (shift_smp && c < p.C_out) sh += __ldg(shift_smp + c);
+        }
         x = fmaf(x, sc, sh);
-        if (p.res && io_vec) x += resv[j];
+        if (add_res) x += resv[j];
         if constexpr (HAS_RES) x += r2[j] + s_col[5][n];
         v[j] = x;
       }
@@ -292,42 +307,70 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       }
     };
 
-    if (active) {
+    // the whole slice of this thread, for one compile-time (ACT, SMP) combination
+    auto run = [&](auto act_tag, auto smp_tag) {
+      constexpr bool SMP = decltype(smp_tag)::value;
+      using F = std::false_type;
+      using Tt = std::true_type;
       if constexpr (N >= 32) {
         if (p.groups > 0) {
-          // GroupNorm (8 groups, N == C_out): this thread's slice holds 4 whole groups of CPG columns
+          // GroupNorm (8 groups, N == C_out): this thread's slice holds 4 whole groups of CPG columns.  Groups and
+          // 16-column sub-chunks are rolled loops (the body stays resident in the instruction cache); statistics and
+          // post-processing of a group both read the accumulator from TMEM, which is cheap.
           constexpr int CPG = N / 8;
-          float mean[4], rstd[4];
-#pragma unroll
+          constexpr int SW = CPG < 16 ? CPG : 16;
+#pragma unroll 1
           for (int g = 0; g < 4; ++g) {
-            float v[CPG];
-            const int n0 = col0 + g * CPG;
-            ptx::tmem_ld<CPG>(t_row + (uint32_t)n0, v);
+            const int g0 = col0 + g * CPG;
             float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int sub = 0; sub < CPG / SW; ++sub) {
+              float v[SW];
+              const int n0 = g0 + sub * SW;
+              ptx::tmem_ld<SW>(t_row + (uint32_t)n0, v);
 #pragma unroll
-            for (int j = 0; j < CPG; ++j) {
-              float x = v[j] + s_col[0][n0 + j];
-              if (bias_smp) x += __ldg(bias_smp + n0 + j);
-              x = valid ? x : 0.f;
-              s1 += x;
-              s2 = fmaf(x, x, s2);
+              for (int j = 0; j < SW; ++j) {
+                float x = v[j] + s_col[0][n0 + j];
+                if constexpr (SMP) { if (bias_smp) x += __ldg(bias_smp + n0 + j); }
+                x = valid ? x : 0.f;
+                s1 += x;
+                s2 = fmaf(x, x, s2);
+              }
             }
             for (int off = p.L >> 1; off >= 1; off >>= 1) {       // over the L lanes (positions) of this trajectory
               s1 += __shfl_xor_sync(0xffffffffu, s1, off);
               s2 += __shfl_xor_sync(0xffffffffu, s2, off);
             }
             const float inv_cnt = 1.f / (float)(p.L * CPG);
-            mean[g] = s1 * inv_cnt;
-            rstd[g] = rsqrtf(fmaxf(s2 * inv_cnt - mean[g] * mean[g], 0.f) + p.gn_eps);
+            const float mean = s1 * inv_cnt;
+            const float rstd = rsqrtf(fmaxf(s2 * inv_cnt - mean * mean, 0.f) + p.gn_eps);
+#pragma unroll 1
+            for (int sub = 0; sub < CPG / SW; ++sub)
+              finish(std::integral_constant<int, SW>{}, Tt{}, act_tag, smp_tag, g0 + sub * SW, mean, rstd);
           }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) finish(std::integral_constant<int, CPG>{}, col0 + g * CPG, true, mean[g], rstd[g]);
         } else {
 #pragma unroll 1
-          for (int ch = 0; ch < NH / 16; ++ch) finish(std::integral_constant<int, 16>{}, col0 + ch * 16, false, 0.f, 1.f);
+          for (int ch = 0; ch < NH / 16; ++ch)
+            finish(std::integral_constant<int, 16>{}, F{}, act_tag, smp_tag, col0 + ch * 16, 0.f, 1.f);
         }
       } else {
-        finish(std::integral_constant<int, 16>{}, 0, false, 0.f, 1.f);
+        finish(std::integral_constant<int, 16>{}, F{}, act_tag, smp_tag, 0, 0.f, 1.f);
+      }
+    };
+
+    if (active) {
+      const bool smp = bias_smp || scale_smp || shift_smp;      // CTA-uniform
+      using A0 = std::integral_constant<int, CDS_ACT_NONE>;
+      using A1 = std::integral_constant<int, CDS_ACT_MISH>;
+      using AX = std::integral_constant<int, kActOther>;
+      if (!smp) {
+        if (p.act == CDS_ACT_MISH) run(A1{}, std::false_type{});
+        else if (p.act == CDS_ACT_NONE) run(A0{}, std::false_type{});
+        else run(AX{}, std::false_type{});
+      } else {
+        if (p.act == CDS_ACT_MISH) run(A1{}, std::true_type{});
+        else if (p.act == CDS_ACT_NONE) run(A0{}, std::true_type{});
+        else run(AX{}, std::true_type{});
       }
     }
     ptx::tc_fence_before_sync();
