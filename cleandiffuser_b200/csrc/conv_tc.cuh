@@ -35,6 +35,7 @@ constexpr int kTcStages = 4;
 struct ConvTcParams {
   CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
   int batch, L, log2L, C_out, taps, pad;   // L = output positions per tile-trajectory; C_out = channels per phase
+  int num_tiles;                  // ceil(batch*L / 128); CTAs are persistent and stride over the tiles
   int phases;                     // 2: columns [0,C_out) / [C_out,2C_out) are output positions 2l / 2l+1 (transposed conv)
   int kchunks, kchunks2;          // channel chunks of the main conv / of the shortcut conv
   int in_batch_mod;
@@ -77,7 +78,9 @@ struct ConvTcCfg {
   static constexpr int kBBytes = N * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kTcStages * kStageBytes + 1024;
-  static constexpr uint32_t kTmemCols = (N * (HAS_RES ? 2 : 1)) < 32 ? 32 : (N * (HAS_RES ? 2 : 1));
+  static constexpr int kColsPerTile = N * (HAS_RES ? 2 : 1);             // main (+ shortcut) accumulator
+  static constexpr int kAccBufs = 2 * kColsPerTile <= 512 ? 2 : 1;       // double-buffered when TMEM allows
+  static constexpr uint32_t kTmemCols = (kAccBufs * kColsPerTile) < 32 ? 32 : (kAccBufs * kColsPerTile);
   static constexpr int kEpiSplit = N >= 32 ? 2 : 1;     // epilogue warps per TMEM lane quarter (column split)
   static constexpr int kMinBlocks = N <= 64 ? 3 : (N <= 128 ? 2 : 1);
 };
@@ -140,7 +143,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kTcStages];
   __shared__ __align__(8) uint64_t empty_bar[kTcStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];    // MMA -> epilogue, per accumulator buffer
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];   // epilogue -> MMA
   __shared__ uint32_t tmem_base_holder;
   // per-column constants of the epilogue, staged once per CTA while the main loop runs:
   // 0 bias  1 GN gamma  2 GN beta  3 FiLM scale  4 FiLM shift  5 shortcut bias   (iteration-indexed "step" parts)
@@ -152,13 +156,12 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   uint8_t* smem_al = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
 
   const int T = 128 >> p.log2L;                       // trajectories per tile
-  const int b0 = blockIdx.x * T;
   const int n_kb_main = p.taps * p.kchunks;
   const int n_kb = n_kb_main + (HAS_RES ? p.kchunks2 : 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    ptx::mbar_init(&tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], kTcEpiThreads / 32); }
     ptx::fence_barrier_init();
   }
   if (warp == 8 && lane == 0) {
@@ -175,11 +178,14 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   if (warp == 8) {
     // ===================================== TMA producer =====================================
     if (ptx::elect_one()) {
+      int ring = 0;                                   // k-blocks issued so far (smem ring position, across tiles)
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int b0 = tile * T;
       const int a_b0 = p.in_batch_mod > 0 ? b0 % p.in_batch_mod : b0;
       const int r_b0 = p.res_batch_mod > 0 ? b0 % p.res_batch_mod : b0;
-      for (int kb = 0; kb < n_kb; ++kb) {
-        const int s = kb % kTcStages;
-        const uint32_t ph = (kb / kTcStages) & 1;
+      for (int kb = 0; kb < n_kb; ++kb, ++ring) {
+        const int s = ring % kTcStages;
+        const uint32_t ph = (ring / kTcStages) & 1;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem_al + s * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
@@ -194,21 +200,29 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
           ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], ck * KC, 0);
         }
       }
+      }
     }
   } else if (warp == 9) {
     // ===================================== MMA issuer =====================================
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, N);
-      for (int kb = 0; kb < n_kb; ++kb) {
-        const int s = kb % kTcStages;
-        const uint32_t ph = (kb / kTcStages) & 1;
+      int ring = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it % Cfg::kAccBufs;
+      const uint32_t use = (uint32_t)(it / Cfg::kAccBufs);            // how often this buffer has been used before
+      ptx::mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);              // epilogue has drained the previous use
+      ptx::tc_fence_after_sync();
+      const uint32_t acc_base = tmem_base + (uint32_t)(buf * Cfg::kColsPerTile);
+      for (int kb = 0; kb < n_kb; ++kb, ++ring) {
+        const int s = ring % kTcStages;
+        const uint32_t ph = (ring / kTcStages) & 1;
         ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after_sync();
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
         const uint64_t da = ptx::make_kmajor_desc<Cfg::kRowBytes>(sa);
         const uint64_t db = ptx::make_kmajor_desc<Cfg::kRowBytes>(sa + Cfg::kABytes);
         const bool second = HAS_RES && kb >= n_kb_main;
-        const uint32_t d_addr = tmem_base + (second ? (uint32_t)N : 0u);
+        const uint32_t d_addr = acc_base + (second ? (uint32_t)N : 0u);
         const bool first_of_acc = second ? (kb == n_kb_main) : (kb == 0);
 #pragma unroll
         for (int k = 0; k < KC / 16; ++k) {
@@ -217,7 +231,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         }
         ptx::umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
       }
-      ptx::umma_commit(&tmem_full_bar);           // accumulators complete
+      ptx::umma_commit(&tmem_full_bar[buf]);      // this tile's accumulators complete
+      }
     }
   } else {
     // ===================================== epilogue (warps 0..7) =====================================
@@ -249,17 +264,21 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     }
 
     const int m = 32 * q + lane;
-    const int64_t row = (int64_t)blockIdx.x * 128 + m;
+    const int col0 = half * NH;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const int buf = it % Cfg::kAccBufs;
+    const uint32_t use = (uint32_t)(it / Cfg::kAccBufs);
+    const int64_t row = (int64_t)tile * 128 + m;
     const bool valid = active && row < (int64_t)p.batch * p.L;
     const int b = (int)(row >> p.log2L), l = (int)(row & (p.L - 1));
-    const int col0 = half * NH;
-    const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * Cfg::kColsPerTile);
     const float* bias_smp = p.bias.sample ? p.bias.sample + (int64_t)b * p.bias.sample_stride : nullptr;
     const float* scale_smp = p.scale.sample ? p.scale.sample + (int64_t)b * p.scale.sample_stride : nullptr;
     const float* shift_smp = p.shift.sample ? p.shift.sample + (int64_t)b * p.shift.sample_stride : nullptr;
     const int rb = p.res_batch_mod > 0 ? b % p.res_batch_mod : b;
 
-    ptx::mbar_wait(&tmem_full_bar, 0);
+    ptx::mbar_wait(&tmem_full_bar[buf], use & 1);
     ptx::tc_fence_after_sync();
 
     // one group of W columns starting at GEMM column n0: TMEM -> registers -> full post-processing -> global.
@@ -331,7 +350,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
 #pragma unroll
               for (int j = 0; j < SW; ++j) {
                 float x = v[j] + s_col[0][n0 + j];
-                if constexpr (SMP) { if (bias_smp) x += __ldg(bias_smp + n0 + j); }
+                if constexpr (SMP) { if (bias_smp && valid) x += __ldg(bias_smp + n0 + j); }
                 x = valid ? x : 0.f;
                 s1 += x;
                 s2 = fmaf(x, x, s2);
@@ -373,7 +392,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         else run(AX{}, std::true_type{});
       }
     }
+    // hand the accumulator buffer back to the MMA warp (one arrival per epilogue warp)
     ptx::tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+    }   // tile loop
   }
 
   __syncthreads();
@@ -509,7 +532,8 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
   p.res_dtype = c.res_dtype; p.res_bias = c.res_bias;
   p.out = c.out; p.out_bstride = c.out_bstride; p.out_lstride = c.out_lstride; p.out_dtype = c.out_dtype;
   int64_t rows = (int64_t)c.batch * Lp;
-  L.grid = dim3((unsigned)((rows + 127) / 128));
+  p.num_tiles = (int)((rows + 127) / 128);
+  L.grid = dim3((unsigned)p.num_tiles);      // clipped to the resident-CTA capacity at launch (persistent CTAs)
   return true;
 }
 
@@ -517,6 +541,7 @@ template <int KC, int N, bool HAS_RES>
 inline cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStream_t st) {
   using Cfg = ConvTcCfg<KC, N, HAS_RES>;
   static bool attr = false;
+  static int resident = 0;                   // CTAs of this instantiation that fit on the device at once
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
@@ -525,9 +550,19 @@ inline cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, 
     e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
+    int per_sm = 0, dev = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_tc_kernel<KC, N, HAS_RES>, kTcThreads, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // TMEM: kTmemCols per CTA out of 512 per SM
+    int by_tmem = 512 / (int)Cfg::kTmemCols;
+    if (per_sm > by_tmem) per_sm = by_tmem;
+    resident = (per_sm > 0 ? per_sm : 1) * sms;
     attr = true;
   }
-  conv_tc_kernel<KC, N, HAS_RES><<<L.grid, kTcThreads, Cfg::kSmemBytes, st>>>(L.prm, iter_ptr);
+  dim3 grid(L.grid.x < (unsigned)resident ? L.grid.x : (unsigned)resident);
+  conv_tc_kernel<KC, N, HAS_RES><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(L.prm, iter_ptr);
   return cudaGetLastError();
 }
 
