@@ -157,16 +157,7 @@ int preload_kernels() {
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<32>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<64>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<128>));
-  CDS_CUDA((cds::conv_tc_preload_t<64, 16, false>()));  CDS_CUDA((cds::conv_tc_preload_t<64, 16, true>()));
-  CDS_CUDA((cds::conv_tc_preload_t<32, 16, false>()));  CDS_CUDA((cds::conv_tc_preload_t<32, 16, true>()));
-  CDS_CUDA((cds::conv_tc_preload_t<64, 32, false>()));  CDS_CUDA((cds::conv_tc_preload_t<64, 32, true>()));
-  CDS_CUDA((cds::conv_tc_preload_t<64, 64, false>()));  CDS_CUDA((cds::conv_tc_preload_t<64, 64, true>()));
-  CDS_CUDA((cds::conv_tc_preload_t<64, 128, false>())); CDS_CUDA((cds::conv_tc_preload_t<64, 128, true>()));
-  CDS_CUDA((cds::conv_tc_preload_t<64, 256, false>())); CDS_CUDA((cds::conv_tc_preload_t<64, 256, true>()));
-  CDS_CUDA((cds::conv_tc_preload_t<32, 32, false>()));  CDS_CUDA((cds::conv_tc_preload_t<32, 32, true>()));
-  CDS_CUDA((cds::conv_tc_preload_t<32, 64, false>()));  CDS_CUDA((cds::conv_tc_preload_t<32, 64, true>()));
-  CDS_CUDA((cds::conv_tc_preload_t<32, 128, false>())); CDS_CUDA((cds::conv_tc_preload_t<32, 128, true>()));
-  CDS_CUDA((cds::conv_tc_preload_t<32, 256, false>())); CDS_CUDA((cds::conv_tc_preload_t<32, 256, true>()));
+  CDS_CUDA(cds::conv_tc_preload_all());
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<16>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<32>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<64>));

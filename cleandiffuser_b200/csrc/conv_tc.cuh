@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -30,7 +32,7 @@ namespace cds {
 constexpr int kTcThreads = 320;   // warps 0-7 epilogue (TMEM lane quarter = warp % 4, column slice = warp / 4),
                                   // warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer
 constexpr int kTcEpiThreads = 256;
-constexpr int kTcStages = 4;
+constexpr int kTcMaxStages = 4;
 
 struct ConvTcParams {
   CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
@@ -71,13 +73,17 @@ __device__ __forceinline__ float tc_act(int act, float x) {
   }
 }
 
-template <int KC, int N, bool HAS_RES>
+// N = columns of one CTA tile; SPLIT = 2 when the layer's C_out = 2N columns are shared by two CTAs (more CTAs in flight for
+// the deep, narrow-batch layers: L = 4 / 8 have only 128 / 256 row tiles), each owning 4 of the 8 GroupNorm groups.
+template <int KC, int N, bool HAS_RES, int SPLIT = 1>
 struct ConvTcCfg {
   static constexpr int kRowBytes = KC * 2;
   static constexpr int kABytes = 128 * kRowBytes;
   static constexpr int kBBytes = N * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kTcStages * kStageBytes + 1024;
+  static constexpr int kStages = (KC == 64 && (N == 64 || N == 128)) ? 3 : 4;   // 3 stages let 2-3 such CTAs share an SM
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kCols = N * SPLIT;                                 // columns of the whole layer
   static constexpr int kColsPerTile = N * (HAS_RES ? 2 : 1);             // main (+ shortcut) accumulator
   static constexpr int kAccBufs = 2 * kColsPerTile <= 512 ? 2 : 1;       // double-buffered when TMEM allows
   static constexpr uint32_t kTmemCols = (kAccBufs * kColsPerTile) < 32 ? 32 : (kAccBufs * kColsPerTile);
@@ -136,19 +142,20 @@ __device__ __forceinline__ void store_row(void* base, int64_t off, int dtype, co
   }
 }
 
-template <int KC, int N, bool HAS_RES>
-__global__ void __launch_bounds__(kTcThreads, ConvTcCfg<KC, N, HAS_RES>::kMinBlocks)
+template <int KC, int N, bool HAS_RES, int SPLIT>
+__global__ void __launch_bounds__(kTcThreads, ConvTcCfg<KC, N, HAS_RES, SPLIT>::kMinBlocks)
 conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ iter_ptr) {
-  using Cfg = ConvTcCfg<KC, N, HAS_RES>;
+  using Cfg = ConvTcCfg<KC, N, HAS_RES, SPLIT>;
+  constexpr int kTcStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kTcStages];
-  __shared__ __align__(8) uint64_t empty_bar[kTcStages];
+  __shared__ __align__(8) uint64_t full_bar[kTcMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kTcMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];    // MMA -> epilogue, per accumulator buffer
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];   // epilogue -> MMA
   __shared__ uint32_t tmem_base_holder;
   // per-column constants of the epilogue, staged once per CTA while the main loop runs:
   // 0 bias  1 GN gamma  2 GN beta  3 FiLM scale  4 FiLM shift  5 shortcut bias   (iteration-indexed "step" parts)
-  __shared__ __align__(16) float s_col[6][N];
+  __shared__ __align__(16) float s_col[6][Cfg::kCols];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // operand ring, 1024-byte aligned (swizzle atoms)
@@ -180,7 +187,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     if (ptx::elect_one()) {
       int ring = 0;                                   // k-blocks issued so far (smem ring position, across tiles)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int b0 = tile * T;
+      const int b0 = (tile / SPLIT) * T;
+      const int n_off = (tile % SPLIT) * N;           // first layer column of this CTA tile
       const int a_b0 = p.in_batch_mod > 0 ? b0 % p.in_batch_mod : b0;
       const int r_b0 = p.res_batch_mod > 0 ? b0 % p.res_batch_mod : b0;
       for (int kb = 0; kb < n_kb; ++kb, ++ring) {
@@ -193,11 +201,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         if (!HAS_RES || kb < n_kb_main) {
           const int tap = kb / p.kchunks, ck = kb - tap * p.kchunks;
           ptx::tma_load_3d(sa, &p.tm_a, &full_bar[s], ck * KC, tap - p.pad, a_b0);
-          ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KC, tap * p.C_out * p.phases);
+          ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KC, tap * p.C_out * p.phases + n_off);
         } else {
           const int ck = kb - n_kb_main;
           ptx::tma_load_3d(sa, &p.tm_a2, &full_bar[s], ck * KC, 0, r_b0);
-          ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], ck * KC, 0);
+          ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], ck * KC, n_off);
         }
       }
       }
@@ -250,7 +258,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       const float* sstep = p.scale.step ? p.scale.step + (int64_t)iter * p.scale.step_stride : nullptr;
       const float* hstep = p.shift.step ? p.shift.step + (int64_t)iter * p.shift.step_stride : nullptr;
       const bool scale_any = p.scale.step || p.scale.sample;
-      for (int n = threadIdx.x; n < N; n += kTcEpiThreads) {
+      for (int n = threadIdx.x; n < Cfg::kCols; n += kTcEpiThreads) {
         const bool real = n < n_real;
         const int c = real ? n % p.C_out : 0;
         s_col[0][n] = (real && bstep) ? __ldg(bstep + c) : 0.f;
@@ -269,7 +277,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
     const int buf = it % Cfg::kAccBufs;
     const uint32_t use = (uint32_t)(it / Cfg::kAccBufs);
-    const int64_t row = (int64_t)tile * 128 + m;
+    const int64_t row = (int64_t)(tile / SPLIT) * 128 + m;
+    const int n_off = (tile % SPLIT) * N;
     const bool valid = active && row < (int64_t)p.batch * p.L;
     const int b = (int)(row >> p.log2L), l = (int)(row & (p.L - 1));
     const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * Cfg::kColsPerTile);
@@ -292,15 +301,16 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       ptx::tmem_ld<W>(t_row + (uint32_t)n0, v);
       if constexpr (HAS_RES) ptx::tmem_ld<W>(t_row + (uint32_t)(N + n0), r2);
       if (!valid) return;
-      const int phase = n0 / p.C_out >= p.phases ? 0 : n0 / p.C_out;
-      const int c0 = n0 - phase * p.C_out;                       // first channel of the group
+      const int ng0 = n_off + n0;                                 // layer column of the group's first element
+      const int phase = ng0 / p.C_out >= p.phases ? 0 : ng0 / p.C_out;
+      const int c0 = ng0 - phase * p.C_out;                      // its channel
       float resv[W];
-      const bool io_vec = n_real == N;
+      const bool io_vec = n_real == Cfg::kCols;
       const bool add_res = p.res != nullptr && io_vec;
       if (add_res) load_row<W>(p.res, (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + c0, p.res_dtype, resv);
 #pragma unroll
       for (int j = 0; j < W; ++j) {
-        const int n = n0 + j, c = c0 + j;
+        const int n = ng0 + j, c = c0 + j;
         float x = v[j] + s_col[0][n];
         if constexpr (SMP) { if (bias_smp && c < p.C_out) x += __ldg(bias_smp + c); }
         if constexpr (GN) x = fmaf((x - mean) * rstd, s_col[1][n], s_col[2][n]);
@@ -336,10 +346,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
           // GroupNorm (8 groups, N == C_out): this thread's slice holds 4 whole groups of CPG columns.  Groups and
           // 16-column sub-chunks are rolled loops (the body stays resident in the instruction cache); statistics and
           // post-processing of a group both read the accumulator from TMEM, which is cheap.
-          constexpr int CPG = N / 8;
+          constexpr int CPG = Cfg::kCols / 8;
           constexpr int SW = CPG < 16 ? CPG : 16;
 #pragma unroll 1
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < NH / CPG; ++g) {
             const int g0 = col0 + g * CPG;
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -349,8 +359,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
               ptx::tmem_ld<SW>(t_row + (uint32_t)n0, v);
 #pragma unroll
               for (int j = 0; j < SW; ++j) {
-                float x = v[j] + s_col[0][n0 + j];
-                if constexpr (SMP) { if (bias_smp && valid) x += __ldg(bias_smp + n0 + j); }
+                float x = v[j] + s_col[0][n_off + n0 + j];
+                if constexpr (SMP) { if (bias_smp && valid) x += __ldg(bias_smp + n_off + n0 + j); }
                 x = valid ? x : 0.f;
                 s1 += x;
                 s2 = fmaf(x, x, s2);
@@ -483,18 +493,31 @@ inline bool conv_tc_eligible(const cds_conv_op& c) {
 
 struct ConvTcLaunch {
   ConvTcParams prm;
-  int kc = 0, n = 0;
+  int kc = 0, n = 0, split = 1;   // n = CTA tile width, split*n = layer width
   bool has_res = false;
   dim3 grid;
 };
+
+// Share a layer's columns between two CTAs?  Yes for the wide layers (C_out >= 128: halves the per-CTA epilogue and main
+// loop and lets two CTAs share an SM) and for C_out = 64 when there are too few row tiles to fill the machine.
+inline int conv_tc_pick_split(const cds_conv_op& c, int n_total, int m_tiles) {
+  if (c.phases != 1 || n_total < 64) return 1;
+  if (n_total >= 128) return 2;
+  return m_tiles < 296 ? 2 : 1;
+}
 
 inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
   ConvTcLaunch& L = *out;
   memset(&L.prm, 0, sizeof(L.prm));
   const int kc = conv_tc_pick_kc(c);
-  L.kc = kc; L.n = conv_tc_width(c); L.has_res = c.res_w != nullptr;
   ConvTcParams& p = L.prm;
   const int Lp = c.L_out, T = 128 / Lp;
+  const int64_t rows = (int64_t)c.batch * Lp;
+  const int m_tiles = (int)((rows + 127) / 128);
+  const int n_total = conv_tc_width(c);
+  L.kc = kc; L.has_res = c.res_w != nullptr;
+  L.split = conv_tc_pick_split(c, n_total, m_tiles);
+  L.n = n_total / L.split;
   const uint64_t in_b = c.in_batch_mod > 0 ? (uint64_t)c.in_batch_mod : (uint64_t)c.batch;
   {
     uint64_t dims[3] = {(uint64_t)c.C_in, (uint64_t)c.L_in, in_b};
@@ -519,7 +542,7 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
     if (!encode_bf16_map(&p.tm_a2, c.res_in, 3, dims, str, box, kc)) return false;
     uint64_t d2[2] = {(uint64_t)c.res_C, (uint64_t)c.C_out};
     uint64_t s2[1] = {(uint64_t)c.res_C};
-    uint32_t b2[2] = {(uint32_t)kc, (uint32_t)c.C_out};
+    uint32_t b2[2] = {(uint32_t)kc, (uint32_t)L.n};
     if (!encode_bf16_map(&p.tm_b2, c.res_w, 2, d2, s2, b2, kc)) return false;
   }
   p.batch = c.batch; p.L = Lp; p.log2L = ilog2(Lp); p.C_out = c.C_out; p.taps = c.taps; p.pad = c.pad;
@@ -531,55 +554,68 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
   p.res = c.res; p.res_bstride = c.res_bstride; p.res_lstride = c.res_lstride; p.res_batch_mod = c.res_batch_mod;
   p.res_dtype = c.res_dtype; p.res_bias = c.res_bias;
   p.out = c.out; p.out_bstride = c.out_bstride; p.out_lstride = c.out_lstride; p.out_dtype = c.out_dtype;
-  int64_t rows = (int64_t)c.batch * Lp;
-  p.num_tiles = (int)((rows + 127) / 128);
+  p.num_tiles = m_tiles * L.split;
   L.grid = dim3((unsigned)p.num_tiles);      // clipped to the resident-CTA capacity at launch (persistent CTAs)
   return true;
 }
 
-template <int KC, int N, bool HAS_RES>
+template <int KC, int N, bool HAS_RES, int SPLIT>
 inline cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStream_t st) {
-  using Cfg = ConvTcCfg<KC, N, HAS_RES>;
+  using Cfg = ConvTcCfg<KC, N, HAS_RES, SPLIT>;
   static bool attr = false;
   static int resident = 0;                   // CTAs of this instantiation that fit on the device at once
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     // several CTAs per SM for the narrow tiles: ask for the maximum shared-memory carve-out
-    e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    int per_sm = 0, dev = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_tc_kernel<KC, N, HAS_RES>, kTcThreads, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // TMEM: kTmemCols per CTA out of 512 per SM
+    // residency we design for: launch-bounds blocks, TMEM (kTmemCols of 512 columns per SM), 227 KB shared memory
+    int want = Cfg::kMinBlocks;
     int by_tmem = 512 / (int)Cfg::kTmemCols;
-    if (per_sm > by_tmem) per_sm = by_tmem;
-    resident = (per_sm > 0 ? per_sm : 1) * sms;
+    int by_smem = (227 * 1024) / (Cfg::kSmemBytes + 8 * 1024);
+    if (want > by_tmem) want = by_tmem;
+    if (want > by_smem) want = by_smem;
+    if (want < 1) want = 1;
+    if (getenv("CDS_DEBUG"))
+      fprintf(stderr, "[cds] conv_tc<%d,%d,%d,%d>: designed %d CTA/SM (tmem %d, smem %d), smem %d B, %d stages\n", KC, N,
+              (int)HAS_RES, SPLIT, want, by_tmem, by_smem, Cfg::kSmemBytes, Cfg::kStages);
+    resident = want * sms;
     attr = true;
   }
   dim3 grid(L.grid.x < (unsigned)resident ? L.grid.x : (unsigned)resident);
-  conv_tc_kernel<KC, N, HAS_RES><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(L.prm, iter_ptr);
+  conv_tc_kernel<KC, N, HAS_RES, SPLIT><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(L.prm, iter_ptr);
   return cudaGetLastError();
 }
 
+// every (KC, N, RES, SPLIT) the dispatcher can pick; X(kc, n, split)
+#define CDS_TC_VARIANTS(X)                                                                              \
+  X(64, 16, 1) X(64, 32, 1) X(64, 64, 1) X(64, 128, 1) X(64, 256, 1) X(64, 32, 2) X(64, 64, 2) X(64, 128, 2) \
+  X(32, 16, 1) X(32, 32, 1) X(32, 64, 1) X(32, 128, 1) X(32, 256, 1) X(32, 32, 2) X(32, 64, 2) X(32, 128, 2)
+
 inline cudaError_t conv_tc_launch(const ConvTcLaunch& L, const int* iter_ptr, cudaStream_t st) {
-#define CDS_TC_CASE(KC_, N_)                                                                     \
-  if (L.kc == KC_ && L.n == N_)                                                                  \
-    return L.has_res ? conv_tc_launch_t<KC_, N_, true>(L, iter_ptr, st) : conv_tc_launch_t<KC_, N_, false>(L, iter_ptr, st);
-  CDS_TC_CASE(64, 16) CDS_TC_CASE(64, 32) CDS_TC_CASE(64, 64) CDS_TC_CASE(64, 128) CDS_TC_CASE(64, 256)
-  CDS_TC_CASE(32, 16) CDS_TC_CASE(32, 32) CDS_TC_CASE(32, 64) CDS_TC_CASE(32, 128) CDS_TC_CASE(32, 256)
+#define CDS_TC_CASE(KC_, N_, S_)                                                                 \
+  if (L.kc == KC_ && L.n == N_ && L.split == S_)                                                 \
+    return L.has_res ? conv_tc_launch_t<KC_, N_, true, S_>(L, iter_ptr, st) : conv_tc_launch_t<KC_, N_, false, S_>(L, iter_ptr, st);
+  CDS_TC_VARIANTS(CDS_TC_CASE)
 #undef CDS_TC_CASE
   return cudaErrorInvalidValue;
 }
 
-template <int KC, int N, bool HAS_RES>
-inline cudaError_t conv_tc_preload_t() {
+inline cudaError_t conv_tc_preload_all() {
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, conv_tc_kernel<KC, N, HAS_RES>);
+  cudaError_t e;
+#define CDS_TC_PRE(KC_, N_, S_)                                                                   \
+  if ((e = cudaFuncGetAttributes(&a, conv_tc_kernel<KC_, N_, false, S_>)) != cudaSuccess) return e; \
+  if ((e = cudaFuncGetAttributes(&a, conv_tc_kernel<KC_, N_, true, S_>)) != cudaSuccess) return e;
+  CDS_TC_VARIANTS(CDS_TC_PRE)
+#undef CDS_TC_PRE
+  return cudaSuccess;
 }
 
 }  // namespace cds

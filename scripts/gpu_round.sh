@@ -20,6 +20,7 @@ for st in $STAGES; do
       timeout 500 python bench.py --steps ${BENCH_STEPS:-3} --warmup 3 > gpurun_out/bench_fp32.json 2> gpurun_out/bench_fp32.err
       echo "[bench fp32] exit $?"; head -c 2500 gpurun_out/bench_fp32.json; tail -4 gpurun_out/bench_fp32.err ;;
     bench16)
+      export CDS_DEBUG=1
       timeout 400 python bench.py --math bf16 --steps ${BENCH_STEPS:-3} --warmup 3 --no-cpu-baseline > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err
       echo "[bench bf16] exit $?"; head -c 2500 gpurun_out/bench_bf16.json; tail -4 gpurun_out/bench_bf16.err ;;
     ncu)
