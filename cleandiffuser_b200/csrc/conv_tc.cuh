@@ -51,9 +51,10 @@ struct ConvTcParams {
 
 __device__ __forceinline__ float fast_mish(float x) {
   // x * tanh(softplus(x)) with tanh(log(1+e)) = n/(n+2), n = e*(e+2), e = exp(x)
+  // (for x >= 20 the ratio rounds to exactly 1.0f, which is torch's softplus threshold behaviour: mish(x) = x)
   float e = __expf(fminf(x, 20.f));
   float n = e * (e + 2.f);
-  return x > 20.f ? x : x * __fdividef(n, n + 2.f);
+  return x * __fdividef(n, n + 2.f);
 }
 // ACT is a compile-time constant inside the unrolled epilogue loops (a runtime switch there multiplies the code size
 // by the number of activations and thrashes the instruction cache); kActOther keeps the generic runtime switch.
@@ -88,7 +89,7 @@ struct ConvTcCfg {
   static constexpr int kAccBufs = 2 * kColsPerTile <= 512 ? 2 : 1;       // double-buffered when TMEM allows
   static constexpr uint32_t kTmemCols = (kAccBufs * kColsPerTile) < 32 ? 32 : (kAccBufs * kColsPerTile);
   static constexpr int kEpiSplit = N >= 32 ? 2 : 1;     // epilogue warps per TMEM lane quarter (column split)
-  static constexpr int kMinBlocks = N <= 64 ? 3 : (N <= 128 ? 2 : 1);
+  static constexpr int kMinBlocks = N <= 128 ? 2 : 1;   // 102 registers per thread: the epilogue keeps 16-32 columns live
 };
 
 // W consecutive activations (bf16 or fp32) <-> registers, 8/16-byte vector accesses
@@ -290,100 +291,140 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     ptx::mbar_wait(&tmem_full_bar[buf], use & 1);
     ptx::tc_fence_after_sync();
 
-    // one group of W columns starting at GEMM column n0: TMEM -> registers -> full post-processing -> global.
-    // W, GN, ACT and SMP (any per-trajectory bias/scale/shift vector) are compile-time so the unrolled body is branch-free.
-    auto finish = [&](auto w_tag, auto gn_tag, auto act_tag, auto smp_tag, int n0, float mean, float rstd) {
-      constexpr int W = decltype(w_tag)::value;
-      constexpr bool GN = decltype(gn_tag)::value;
+    // 16 finished columns -> global.  `v` holds accumulator + bias (GroupNorm already applied if any).
+    auto emit16 = [&](auto act_tag, auto smp_tag, auto& v, auto h_tag, int n0) {
       constexpr int ACT = decltype(act_tag)::value;
       constexpr bool SMP = decltype(smp_tag)::value;
-      float v[W], r2[W];
-      ptx::tmem_ld<W>(t_row + (uint32_t)n0, v);
-      if constexpr (HAS_RES) ptx::tmem_ld<W>(t_row + (uint32_t)(N + n0), r2);
-      if (!valid) return;
-      const int ng0 = n_off + n0;                                 // layer column of the group's first element
-      const int phase = ng0 / p.C_out >= p.phases ? 0 : ng0 / p.C_out;
-      const int c0 = ng0 - phase * p.C_out;                      // its channel
-      float resv[W];
+      constexpr int VO = 16 * decltype(h_tag)::value;            // offset of this 16-column chunk inside v[]
+      const int ng0 = n_off + n0;                                 // layer column of the chunk's first element
+      const int phase = (p.phases == 1 || ng0 < p.C_out) ? 0 : 1;
+      const int c0 = ng0 - phase * p.C_out;                       // its channel
       const bool io_vec = n_real == Cfg::kCols;
       const bool add_res = p.res != nullptr && io_vec;
-      if (add_res) load_row<W>(p.res, (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + c0, p.res_dtype, resv);
-#pragma unroll
-      for (int j = 0; j < W; ++j) {
-        const int n = ng0 + j, c = c0 + j;
-        float x = v[j] + s_col[0][n];
-        if constexpr (SMP) { if (bias_smp && c < p.C_out) x += __ldg(bias_smp + c); }
-        if constexpr (GN) x = fmaf((x - mean) * rstd, s_col[1][n], s_col[2][n]);
-        x = tc_act<ACT>(p.act, x);
-        float sc = s_col[3][n], sh = s_col[4][n];
+      float r2[16], resv[16];
+      if constexpr (HAS_RES) ptx::tmem_ld<16>(t_row + (uint32_t)(N + n0), r2);
+      if (!valid) return;
+      if (add_res) load_row<16>(p.res, (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + c0, p.res_dtype, resv);
+      const float4* sc4 = reinterpret_cast<const float4*>(&s_col[3][ng0]);
+      const float4* sh4 = reinterpret_cast<const float4*>(&s_col[4][ng0]);
+      const float4* rb4 = reinterpret_cast<const float4*>(&s_col[5][ng0]);
+      // one output element: activation, FiLM, identity residual, shortcut accumulator (+ its bias)
+      auto elem = [&](int j, float a, float d, float rbias) {
+        const int c = c0 + j;
+        float x = tc_act<ACT>(p.act, v[VO + j]);
         if constexpr (SMP) {
-          if (scale_smp && c < p.C_out) sc += __ldg(scale_smp + c);
-          if (shift_smp && c < p.C_out) sh += __ldg(shift_smp + c);
+          if (scale_smp && c < p.C_out) a += __ldg(scale_smp + c);
+          if (shift_smp && c < p.C_out) d += __ldg(shift_smp + c);
         }
-        x = fmaf(x, sc, sh);
+        x = fmaf(x, a, d);
         if (add_res) x += resv[j];
-        if constexpr (HAS_RES) x += r2[j] + s_col[5][n];
-        v[j] = x;
+        if constexpr (HAS_RES) x += r2[j] + rbias;
+        resv[j] = x;                                              // reuse as the output staging registers
+      };
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 sc = sc4[k], sh = sh4[k];
+        float4 rbq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (HAS_RES) rbq = rb4[k];
+        elem(4 * k + 0, sc.x, sh.x, rbq.x);
+        elem(4 * k + 1, sc.y, sh.y, rbq.y);
+        elem(4 * k + 2, sc.z, sh.z, rbq.z);
+        elem(4 * k + 3, sc.w, sh.w, rbq.w);
       }
       const int64_t oo = (int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + c0;
       if (io_vec) {
-        store_row<W>(p.out, oo, p.out_dtype, v);
+        store_row<16>(p.out, oo, p.out_dtype, resv);
       } else {
-        for (int j = 0; j < W && c0 + j < p.C_out; ++j) {
-          if (p.out_dtype == CDS_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[oo + j] = __float2bfloat16_rn(v[j]);
-          else reinterpret_cast<float*>(p.out)[oo + j] = v[j];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j < p.C_out) {
+            if (p.out_dtype == CDS_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[oo + j] = __float2bfloat16_rn(resv[j]);
+            else reinterpret_cast<float*>(p.out)[oo + j] = resv[j];
+          }
+        }
+      }
+    };
+
+    // v[j] += bias(column) for WC columns starting at local column n0 (float4 reads of the staged constants)
+    auto add_bias = [&](auto smp_tag, auto wc_tag, auto& v, int n0) {
+      constexpr bool SMP = decltype(smp_tag)::value;
+      constexpr int WC = decltype(wc_tag)::value;
+      const float4* b4 = reinterpret_cast<const float4*>(&s_col[0][n_off + n0]);
+#pragma unroll
+      for (int k = 0; k < WC / 4; ++k) {
+        const float4 bb = b4[k];
+        v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
+      }
+      if constexpr (SMP) {
+        if (bias_smp && valid) {
+#pragma unroll
+          for (int j = 0; j < WC; ++j) { const int c = (n_off + n0 + j) % p.C_out; v[j] += __ldg(bias_smp + c); }
         }
       }
     };
 
     // the whole slice of this thread, for one compile-time (ACT, SMP) combination
     auto run = [&](auto act_tag, auto smp_tag) {
-      constexpr bool SMP = decltype(smp_tag)::value;
-      using F = std::false_type;
-      using Tt = std::true_type;
       if constexpr (N >= 32) {
         if (p.groups > 0) {
-          // GroupNorm (8 groups, N == C_out): this thread's slice holds 4 whole groups of CPG columns.  Groups and
-          // 16-column sub-chunks are rolled loops (the body stays resident in the instruction cache); statistics and
-          // post-processing of a group both read the accumulator from TMEM, which is cheap.
+          // GroupNorm (8 groups over the layer's kCols columns).  A chunk of WC = max(16, CPG) columns is loaded from TMEM
+          // ONCE, holds GPC = WC / CPG whole groups, and is normalised in registers: per-thread sums over the group's
+          // columns, then a butterfly over the L lanes (= positions) of the trajectory.
           constexpr int CPG = Cfg::kCols / 8;
-          constexpr int SW = CPG < 16 ? CPG : 16;
+          constexpr int WC = CPG > 16 ? CPG : 16;
+          constexpr int GPC = WC / CPG;
+          const float inv_cnt = 1.f / (float)(p.L * CPG);
 #pragma unroll 1
-          for (int g = 0; g < NH / CPG; ++g) {
-            const int g0 = col0 + g * CPG;
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-            for (int sub = 0; sub < CPG / SW; ++sub) {
-              float v[SW];
-              const int n0 = g0 + sub * SW;
-              ptx::tmem_ld<SW>(t_row + (uint32_t)n0, v);
+          for (int ch = 0; ch < NH / WC; ++ch) {
+            const int n0 = col0 + ch * WC;
+            float v[WC];
+            ptx::tmem_ld<WC>(t_row + (uint32_t)n0, v);
+            add_bias(smp_tag, std::integral_constant<int, WC>{}, v, n0);
+            float s1[GPC], s2[GPC];
 #pragma unroll
-              for (int j = 0; j < SW; ++j) {
-                float x = v[j] + s_col[0][n_off + n0 + j];
-                if constexpr (SMP) { if (bias_smp && valid) x += __ldg(bias_smp + n_off + n0 + j); }
-                x = valid ? x : 0.f;
-                s1 += x;
-                s2 = fmaf(x, x, s2);
+            for (int g = 0; g < GPC; ++g) {
+              s1[g] = 0.f; s2[g] = 0.f;
+#pragma unroll
+              for (int j = 0; j < CPG; ++j) { const float x = v[g * CPG + j]; s1[g] += x; s2[g] = fmaf(x, x, s2[g]); }
+            }
+            for (int off = p.L >> 1; off >= 1; off >>= 1) {
+#pragma unroll
+              for (int g = 0; g < GPC; ++g) {
+                s1[g] += __shfl_xor_sync(0xffffffffu, s1[g], off);
+                s2[g] += __shfl_xor_sync(0xffffffffu, s2[g], off);
               }
             }
-            for (int off = p.L >> 1; off >= 1; off >>= 1) {       // over the L lanes (positions) of this trajectory
-              s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-              s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+            const float4* ga4 = reinterpret_cast<const float4*>(&s_col[1][n_off + n0]);
+            const float4* be4 = reinterpret_cast<const float4*>(&s_col[2][n_off + n0]);
+#pragma unroll
+            for (int g = 0; g < GPC; ++g) {
+              const float mean = s1[g] * inv_cnt;
+              const float rstd = rsqrtf(fmaxf(s2[g] * inv_cnt - mean * mean, 0.f) + p.gn_eps);
+#pragma unroll
+              for (int k = 0; k < CPG / 4; ++k) {
+                const float4 ga = ga4[g * (CPG / 4) + k], be = be4[g * (CPG / 4) + k];
+                const int o = g * CPG + 4 * k;
+                v[o + 0] = fmaf((v[o + 0] - mean) * rstd, ga.x, be.x); v[o + 1] = fmaf((v[o + 1] - mean) * rstd, ga.y, be.y);
+                v[o + 2] = fmaf((v[o + 2] - mean) * rstd, ga.z, be.z); v[o + 3] = fmaf((v[o + 3] - mean) * rstd, ga.w, be.w);
+              }
             }
-            const float inv_cnt = 1.f / (float)(p.L * CPG);
-            const float mean = s1 * inv_cnt;
-            const float rstd = rsqrtf(fmaxf(s2 * inv_cnt - mean * mean, 0.f) + p.gn_eps);
-#pragma unroll 1
-            for (int sub = 0; sub < CPG / SW; ++sub)
-              finish(std::integral_constant<int, SW>{}, Tt{}, act_tag, smp_tag, g0 + sub * SW, mean, rstd);
+            emit16(act_tag, smp_tag, v, std::integral_constant<int, 0>{}, n0);
+            if constexpr (WC == 32) emit16(act_tag, smp_tag, v, std::integral_constant<int, 1>{}, n0 + 16);
           }
         } else {
 #pragma unroll 1
-          for (int ch = 0; ch < NH / 16; ++ch)
-            finish(std::integral_constant<int, 16>{}, F{}, act_tag, smp_tag, col0 + ch * 16, 0.f, 1.f);
+          for (int ch = 0; ch < NH / 16; ++ch) {
+            float v[16];
+            ptx::tmem_ld<16>(t_row + (uint32_t)(col0 + ch * 16), v);
+            add_bias(smp_tag, std::integral_constant<int, 16>{}, v, col0 + ch * 16);
+            emit16(act_tag, smp_tag, v, std::integral_constant<int, 0>{}, col0 + ch * 16);
+          }
         }
       } else {
-        finish(std::integral_constant<int, 16>{}, F{}, act_tag, smp_tag, 0, 0.f, 1.f);
+        float v[16];
+        ptx::tmem_ld<16>(t_row, v);
+        add_bias(smp_tag, std::integral_constant<int, 16>{}, v, 0);
+        emit16(act_tag, smp_tag, v, std::integral_constant<int, 0>{}, 0);
       }
     };
 
