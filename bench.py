@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="trajectories per GPU (default: the BASELINE config)")
-    ap.add_argument("--math", default=os.environ.get("CDS_MATH", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--math", default=os.environ.get("CDS_MATH", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
