@@ -78,6 +78,8 @@ int validate(const cds_op& op, Step* out) {
       const cds_update_op& u = op.u.update;
       if (u.batch <= 0 || u.row <= 0 || !u.x || !u.pred || !u.coef) return fail(CDS_ERR_INVALID, "update: bad arguments");
       if (u.mask && !u.prior) return fail(CDS_ERR_INVALID, "update: mask without prior");
+      if (u.x_cast && (u.cast_C_in <= 0 || u.cast_C_out < u.cast_C_in || u.row % u.cast_C_in != 0))
+        return fail(CDS_ERR_INVALID, "update: bad x_cast geometry");
       return CDS_OK;
     }
     case CDS_OP_LNMOD: {
@@ -111,7 +113,7 @@ int validate(const cds_op& op, Step* out) {
   }
 }
 
-int launch(const Step& s, const int* iter_ptr, int sm_count, cudaStream_t st) {
+int launch(const Step& s, const int* iter_ptr, int sm_count, cudaStream_t st, int* advance = nullptr) {
   switch (s.op.kind) {
     case CDS_OP_CONV:
       if (s.tc) CDS_CUDA(cds::conv_tc_launch(s.tcl, iter_ptr, st));
@@ -119,7 +121,7 @@ int launch(const Step& s, const int* iter_ptr, int sm_count, cudaStream_t st) {
       return CDS_OK;
     case CDS_OP_UPDATE: {
       const cds_update_op& u = s.op.u.update;
-      cds::solver_update_kernel<<<elementwise_grid((int64_t)u.batch * u.row, sm_count), 256, 0, st>>>(u, iter_ptr);
+      cds::solver_update_kernel<<<elementwise_grid((int64_t)u.batch * u.row, sm_count), 256, 0, st>>>(u, iter_ptr, advance);
       CDS_CUDA(cudaGetLastError());
       return CDS_OK;
     }
@@ -171,6 +173,20 @@ int preload_kernels() {
 }
 
 }  // namespace
+
+// ---- debug timeline of one tensor-core conv launch (cds_debug_trace)
+namespace cds {
+static long long* g_trace_buf = nullptr;
+static int64_t g_trace_cap = 0;       // entries
+static int g_trace_target = -1, g_trace_count = 0, g_trace_grid = 0;
+long long* conv_tc_trace_hook(int grid) {
+  if (!g_trace_buf) return nullptr;
+  const int ord = g_trace_count++;
+  if (ord != g_trace_target || (int64_t)grid * kTraceSlots > g_trace_cap) return nullptr;
+  g_trace_grid = grid;
+  return g_trace_buf;
+}
+}  // namespace cds
 
 struct cds_plan {
   int device = 0;
@@ -247,21 +263,45 @@ int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
   if (n_iters <= 0 || p->steps.empty()) return fail(CDS_ERR_INVALID, "plan_finalize: empty program");
   CDS_CUDA(cudaSetDevice(p->device));
   { int rc = preload_kernels(); if (rc != CDS_OK) return rc; }
-  CDS_CUDA(cudaMalloc(&p->d_iter, sizeof(int)));
-  CDS_CUDA(cudaMemset(p->d_iter, 0, sizeof(int)));
+  CDS_CUDA(cudaMalloc(&p->d_iter, 2 * sizeof(int)));      // [0] iteration counter, [1] finished-block count of the update
+  CDS_CUDA(cudaMemset(p->d_iter, 0, 2 * sizeof(int)));
   CDS_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
   p->n_iters = n_iters;
   p->finalized = true;
   return CDS_OK;
 }
 
-static int enqueue_iteration(cds_plan* p, cudaStream_t st) {
+// the iteration counter is advanced by the program's last operator when that is a solver update (fused), else by a
+// one-thread kernel
+static bool advance_fused(const cds_plan* p) {
+  for (int i = (int)p->steps.size() - 1; i >= 0; --i)
+    if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) return p->steps[i].op.kind == CDS_OP_UPDATE;
+  return false;
+}
+
+static int enqueue_once(cds_plan* p, cudaStream_t st) {
   for (const Step& s : p->steps) {
+    if (!(s.op.flags & CDS_OPF_ONCE)) continue;
     int rc = launch(s, p->d_iter, p->sm_count, st);
     if (rc != CDS_OK) return rc;
   }
-  cds::advance_iter_kernel<<<1, 1, 0, st>>>(p->d_iter);
-  CDS_CUDA(cudaGetLastError());
+  return CDS_OK;
+}
+
+static int enqueue_iteration(cds_plan* p, cudaStream_t st) {
+  const bool fused = advance_fused(p);
+  int last = -1;
+  for (int i = 0; i < (int)p->steps.size(); ++i) if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) last = i;
+  for (int i = 0; i < (int)p->steps.size(); ++i) {
+    const Step& s = p->steps[i];
+    if (s.op.flags & CDS_OPF_ONCE) continue;
+    int rc = launch(s, p->d_iter, p->sm_count, st, (fused && i == last) ? p->d_iter : nullptr);
+    if (rc != CDS_OK) return rc;
+  }
+  if (!fused) {
+    cds::advance_iter_kernel<<<1, 1, 0, st>>>(p->d_iter);
+    CDS_CUDA(cudaGetLastError());
+  }
   return CDS_OK;
 }
 
@@ -283,6 +323,7 @@ int cds_plan_run(cds_plan* p, int32_t first, int32_t count, void* stream, int32_
   }
   cds::set_iter_kernel<<<1, 1, 0, st>>>(p->d_iter, first);
   CDS_CUDA(cudaGetLastError());
+  { int rc = enqueue_once(p, st); if (rc != CDS_OK) return rc; }
   for (int i = 0; i < count; ++i) {
     if (use_graph) {
       CDS_CUDA(cudaGraphLaunch(p->exec, st));
@@ -300,22 +341,41 @@ int cds_plan_profile(cds_plan* p, int32_t iter, void* stream, float* ms_per_op, 
   if (iter < 0 || iter >= p->n_iters) return fail(CDS_ERR_INVALID, "plan_profile: bad iteration");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CDS_CUDA(cudaSetDevice(p->device));
-  std::vector<cudaEvent_t> ev(n_ops + 1);
+  std::vector<cudaEvent_t> ev(2 * n_ops);
   for (auto& e : ev) CDS_CUDA(cudaEventCreate(&e));
   cds::set_iter_kernel<<<1, 1, 0, st>>>(p->d_iter, iter);
-  CDS_CUDA(cudaEventRecord(ev[0], st));
-  for (int i = 0; i < n_ops; ++i) {
-    int rc = launch(p->steps[i], p->d_iter, p->sm_count, st);
-    if (rc != CDS_OK) return rc;
-    CDS_CUDA(cudaEventRecord(ev[i + 1], st));
+  for (int pass = 0; pass < 2; ++pass) {           // pass 0: the CDS_OPF_ONCE operators, pass 1: the iteration program
+    for (int i = 0; i < n_ops; ++i) {
+      const bool once = (p->steps[i].op.flags & CDS_OPF_ONCE) != 0;
+      if (once != (pass == 0)) continue;
+      CDS_CUDA(cudaEventRecord(ev[2 * i], st));
+      int rc = launch(p->steps[i], p->d_iter, p->sm_count, st);
+      if (rc != CDS_OK) return rc;
+      CDS_CUDA(cudaEventRecord(ev[2 * i + 1], st));
+    }
   }
   CDS_CUDA(cudaStreamSynchronize(st));
-  for (int i = 0; i < n_ops; ++i) CDS_CUDA(cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]));
+  for (int i = 0; i < n_ops; ++i) CDS_CUDA(cudaEventElapsedTime(&ms_per_op[i], ev[2 * i], ev[2 * i + 1]));
   for (auto& e : ev) cudaEventDestroy(e);
   return CDS_OK;
 }
 
-int cds_plan_launches_per_iter(const cds_plan* p) { return p ? (int)p->steps.size() + 1 : 0; }
+int cds_plan_launches_per_iter(const cds_plan* p) {
+  if (!p) return 0;
+  int n = advance_fused(p) ? 0 : 1;
+  for (const Step& s : p->steps) if (!(s.op.flags & CDS_OPF_ONCE)) ++n;
+  return n;
+}
+
+int cds_debug_trace(void* device_buffer, int64_t capacity_entries, int32_t target_launch) {
+  cds::g_trace_buf = reinterpret_cast<long long*>(device_buffer);
+  cds::g_trace_cap = capacity_entries;
+  cds::g_trace_target = target_launch;
+  cds::g_trace_count = 0;
+  int g = cds::g_trace_grid;
+  cds::g_trace_grid = 0;
+  return g;
+}
 
 int cds_run_op(int device, const cds_op* op, int32_t iter, void* stream) {
   if (!op) return fail(CDS_ERR_INVALID, "run_op: null op");

@@ -47,15 +47,30 @@ struct ConvTcParams {
   const void* res; int64_t res_bstride; int res_lstride; int res_batch_mod; int res_dtype;
   const float* res_bias;
   void* out; int64_t out_bstride; int out_lstride; int out_dtype;
+  long long* trace;               // debug: per-CTA clock64 timeline (kTraceSlots entries per CTA), normally NULL
 };
+constexpr int kTraceSlots = 64;
+// [0] globaltimer at entry  [1] clock at entry  [2] clock after the prologue barrier  [3] clock at exit  [4] globaltimer at exit
+// [5] tiles done by this CTA;  tile t (t < 14): [8+4t] producer issued its last k-block, [9+4t] MMA saw its first operands,
+// [10+4t] epilogue saw the accumulator, [11+4t] epilogue done
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define CDS_TRACE(slot, val) do { if (p.trace) p.trace[(int64_t)blockIdx.x * kTraceSlots + (slot)] = (val); } while (0)
 
-__device__ __forceinline__ float fast_mish(float x) {
-  // x * tanh(softplus(x)) with tanh(log(1+e)) = n/(n+2), n = e*(e+2), e = exp(x)
-  // (for x >= 20 the ratio rounds to exactly 1.0f, which is torch's softplus threshold behaviour: mish(x) = x)
-  float e = __expf(fminf(x, 20.f));
-  float n = e * (e + 2.f);
-  return x * __fdividef(n, n + 2.f);
+// MUFU approximations with flush-to-zero: ONE instruction each (the non-ftz forms expand into range fix-ups)
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// mish(y) + add as 7 issue slots:  tanh(softplus(y)) = 1 - 2 / (e^2 + 2e + 2),  e = exp(y).
+// e = inf (y > 88) gives 1 - 2/inf = 1, i.e. mish(y) = y, which is torch's softplus-threshold behaviour; no clamp needed.
+__device__ __forceinline__ float mish_fma(float y, float add) {
+  const float e = ex2_ftz(y * 1.4426950408889634f);
+  const float d = fmaf(e, e + 2.f, 2.f);
+  const float w = fmaf(-2.f, rcp_ftz(d), 1.f);
+  return fmaf(y, w, add);
 }
+__device__ __forceinline__ float fast_mish(float x) { return mish_fma(x, 0.f); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
 // ACT is a compile-time constant inside the unrolled epilogue loops (a runtime switch there multiplies the code size
 // by the number of activations and thrashes the instruction cache); kActOther keeps the generic runtime switch.
 constexpr int kActOther = -1;
@@ -65,11 +80,68 @@ __device__ __forceinline__ float tc_act(int act, float x) {
   else if constexpr (ACT == CDS_ACT_MISH) return fast_mish(x);
   else {
     switch (act) {
-      case CDS_ACT_SILU: return x * __fdividef(1.f, 1.f + __expf(-x));
-      case CDS_ACT_GELU_TANH: { float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);   // tanh(u) = 1 - 2/(e^{2u}+1)
-                                float th = 1.f - __fdividef(2.f, __expf(2.f * u) + 1.f); return 0.5f * x * (1.f + th); }
-      case CDS_ACT_MISH_SILU: { float m = fast_mish(x); return m * __fdividef(1.f, 1.f + __expf(-m)); }
+      case CDS_ACT_MISH: return fast_mish(x);
+      case CDS_ACT_SILU: return x * fast_sigmoid(x);
+      case CDS_ACT_GELU_TANH: { float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);   // 0.5 (1 + tanh(u)) = sigmoid(2u)
+                                return x * fast_sigmoid(2.f * u); }
+      case CDS_ACT_MISH_SILU: { float m = fast_mish(x); return m * fast_sigmoid(m); }
       default: return x;
+    }
+  }
+}
+
+// GroupNorm coefficients of GPC groups from per-thread partial sums: all-reduce (s1, s2) over the L lanes that hold the
+// trajectory's positions (lane groups of L consecutive lanes), return a = rstd and c = -mean * rstd per group so that
+// (v - mean) * rstd = fma(v, a, c).  With V = 2 GPC >= 4 values the butterfly is "transposed": every round halves the
+// number of values a lane carries (reduce-scatter), the survivors finish with log2(L / V) plain rounds, the lanes that
+// end up with S1 and S2 of the same group swap them, compute (a, c), and V indexed shuffles hand every lane all groups:
+// 2 V + log2(L / V) shuffles instead of V log2(L).
+template <int GPC>
+__device__ __forceinline__ void gn_coeffs(float (&s1)[GPC], float (&s2)[GPC], int L, int log2L, int lane, float inv_cnt,
+                                          float eps, float (&a)[GPC], float (&c)[GPC]) {
+  constexpr int V = 2 * GPC;
+  constexpr unsigned kFull = 0xffffffffu;
+  if (GPC >= 2 && L >= V) {
+    float x[V];
+#pragma unroll
+    for (int g = 0; g < GPC; ++g) { x[g] = s1[g]; x[GPC + g] = s2[g]; }
+    int off = L >> 1, log2V = 0;
+#pragma unroll
+    for (int half = V / 2; half >= 1; half >>= 1, off >>= 1, ++log2V) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const float send = up ? x[i] : x[i + half];
+        const float keep = up ? x[i + half] : x[i];
+        x[i] = keep + __shfl_xor_sync(kFull, send, off);
+      }
+    }
+    for (; off >= 1; off >>= 1) x[0] += __shfl_xor_sync(kFull, x[0], off);
+    const float other = __shfl_xor_sync(kFull, x[0], L >> 1);
+    const bool st = (lane & (L >> 1)) != 0;
+    const float S1 = st ? other : x[0], S2 = st ? x[0] : other;
+    const float mean = S1 * inv_cnt;
+    const float rstd = rsqrt_ftz(fmaxf(fmaf(S2, inv_cnt, -mean * mean), 0.f) + eps);
+    const float av = rstd, cv = -mean * rstd;
+    const int base = lane & ~(L - 1), sh = log2L - log2V;
+#pragma unroll
+    for (int g = 0; g < GPC; ++g) {
+      a[g] = __shfl_sync(kFull, av, base | (g << sh));
+      c[g] = __shfl_sync(kFull, cv, base | (g << sh));
+    }
+  } else {
+    for (int off = L >> 1; off >= 1; off >>= 1) {
+#pragma unroll
+      for (int g = 0; g < GPC; ++g) {
+        s1[g] += __shfl_xor_sync(kFull, s1[g], off);
+        s2[g] += __shfl_xor_sync(kFull, s2[g], off);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < GPC; ++g) {
+      const float mean = s1[g] * inv_cnt;
+      const float rstd = rsqrt_ftz(fmaxf(fmaf(s2[g], inv_cnt, -mean * mean), 0.f) + eps);
+      a[g] = rstd; c[g] = -mean * rstd;
     }
   }
 }
@@ -164,6 +236,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   uint8_t* smem_al = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
 
   const int T = 128 >> p.log2L;                       // trajectories per tile
+  if (threadIdx.x == 0) { CDS_TRACE(0, gtimer()); CDS_TRACE(1, clock64()); }
   const int n_kb_main = p.taps * p.kchunks;
   const int n_kb = n_kb_main + (HAS_RES ? p.kchunks2 : 0);
 
@@ -182,10 +255,32 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_holder;
+  if (threadIdx.x == 0) CDS_TRACE(2, clock64());
+  // programmatic dependent launch: the next kernel of the stream may start its own prologue and weight prefetch now; it
+  // blocks in grid_dep_wait() until this grid has completed before it touches anything a predecessor wrote
+  if (threadIdx.x == 0) ptx::grid_dep_launch_dependents();
 
   if (warp == 8) {
     // ===================================== TMA producer =====================================
     if (ptx::elect_one()) {
+      // Weights do not depend on the previous kernel: arm the first ring fill and fetch its W tiles BEFORE waiting for the
+      // predecessor grid (programmatic dependent launch); the activation tiles of those stages follow after the wait.
+      int pre = 0;
+      if (blockIdx.x < p.num_tiles) {
+        const int n_off0 = (blockIdx.x % SPLIT) * N;
+        pre = n_kb < kTcStages ? n_kb : kTcStages;
+        for (int kb = 0; kb < pre; ++kb) {
+          uint8_t* sb = smem_al + kb * Cfg::kStageBytes + Cfg::kABytes;
+          ptx::mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
+          if (!HAS_RES || kb < n_kb_main) {
+            const int tap = kb / p.kchunks, ck = kb - tap * p.kchunks;
+            ptx::tma_load_2d(sb, &p.tm_b, &full_bar[kb], ck * KC, tap * p.C_out * p.phases + n_off0);
+          } else {
+            ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[kb], (kb - n_kb_main) * KC, n_off0);
+          }
+        }
+      }
+      ptx::grid_dep_wait();
       int ring = 0;                                   // k-blocks issued so far (smem ring position, across tiles)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int b0 = (tile / SPLIT) * T;
@@ -195,20 +290,24 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       for (int kb = 0; kb < n_kb; ++kb, ++ring) {
         const int s = ring % kTcStages;
         const uint32_t ph = (ring / kTcStages) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+        const bool w_done = ring < pre;               // this stage was armed and its W tile fetched before the wait
+        if (!w_done) {
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          ptx::mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        }
         uint8_t* sa = smem_al + s * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
-        ptx::mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
         if (!HAS_RES || kb < n_kb_main) {
           const int tap = kb / p.kchunks, ck = kb - tap * p.kchunks;
           ptx::tma_load_3d(sa, &p.tm_a, &full_bar[s], ck * KC, tap - p.pad, a_b0);
-          ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KC, tap * p.C_out * p.phases + n_off);
+          if (!w_done) ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KC, tap * p.C_out * p.phases + n_off);
         } else {
           const int ck = kb - n_kb_main;
           ptx::tma_load_3d(sa, &p.tm_a2, &full_bar[s], ck * KC, 0, r_b0);
-          ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], ck * KC, n_off);
+          if (!w_done) ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], ck * KC, n_off);
         }
       }
+      { const int t_i = (tile - blockIdx.x) / gridDim.x; if (t_i < 14) CDS_TRACE(8 + 4 * t_i, clock64()); }
       }
     }
   } else if (warp == 9) {
@@ -227,6 +326,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         const uint32_t ph = (ring / kTcStages) & 1;
         ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after_sync();
+        if (kb == 0 && it < 14) CDS_TRACE(9 + 4 * it, clock64());
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
         const uint64_t da = ptx::make_kmajor_desc<Cfg::kRowBytes>(sa);
         const uint64_t db = ptx::make_kmajor_desc<Cfg::kRowBytes>(sa + Cfg::kABytes);
@@ -245,6 +345,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     }
   } else {
     // ===================================== epilogue (warps 0..7) =====================================
+    // thread = one output row (TMEM lane m) x NH columns.  Everything per ELEMENT is branch-free: the operator's options
+    // pick one of a few compile-time specialised chunk loops (CTA-uniform dispatch, once per tile).
+    ptx::grid_dep_wait();                           // iteration counter, tables, residual inputs: all written by predecessors
     const int iter = iter_ptr ? *iter_ptr : 0;
     constexpr int EW = Cfg::kEpiSplit;
     constexpr int NH = N / EW;                      // columns per thread
@@ -272,6 +375,15 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       ptx::named_bar_sync(1, kTcEpiThreads);
     }
 
+    // CTA-uniform option flags
+    const bool has_gn = p.groups > 0;
+    const bool smp = p.bias.sample || p.scale.sample || p.shift.sample;
+    const bool has_scale = p.scale.step || p.scale.sample;
+    const bool has_shift = p.shift.step || p.shift.sample;
+    const bool io_vec = n_real == Cfg::kCols;
+    const bool add_res = p.res != nullptr;
+    const int film = (smp || has_scale) ? 2 : (has_shift ? 1 : 0);
+
     const int m = 32 * q + lane;
     const int col0 = half * NH;
     int it = 0;
@@ -287,67 +399,94 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     const float* scale_smp = p.scale.sample ? p.scale.sample + (int64_t)b * p.scale.sample_stride : nullptr;
     const float* shift_smp = p.shift.sample ? p.shift.sample + (int64_t)b * p.shift.sample_stride : nullptr;
     const int rb = p.res_batch_mod > 0 ? b % p.res_batch_mod : b;
+    const int64_t res_row = (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride;
 
     ptx::mbar_wait(&tmem_full_bar[buf], use & 1);
     ptx::tc_fence_after_sync();
+    if (threadIdx.x == 0 && it < 14) CDS_TRACE(10 + 4 * it, clock64());
 
-    // 16 finished columns -> global.  `v` holds accumulator + bias (GroupNorm already applied if any).
-    auto emit16 = [&](auto act_tag, auto smp_tag, auto& v, auto h_tag, int n0) {
+    // ---- 16 finished pre-activation columns (y) -> activation, FiLM, residual(s), store.  n0 = CTA-tile column.
+    // FILM: 0 none, 1 additive per-iteration row (staged in smem), 2 anything (scale and/or per-trajectory rows)
+    auto post16 = [&](auto act_tag, auto film_tag, auto& yv, auto off_tag, int n0) {
       constexpr int ACT = decltype(act_tag)::value;
-      constexpr bool SMP = decltype(smp_tag)::value;
-      constexpr int VO = 16 * decltype(h_tag)::value;            // offset of this 16-column chunk inside v[]
+      constexpr int FILM = decltype(film_tag)::value;
+      constexpr int YO = decltype(off_tag)::value;                 // offset of these 16 columns inside yv[]
       const int ng0 = n_off + n0;                                 // layer column of the chunk's first element
       const int phase = (p.phases == 1 || ng0 < p.C_out) ? 0 : 1;
       const int c0 = ng0 - phase * p.C_out;                       // its channel
-      const bool io_vec = n_real == Cfg::kCols;
-      const bool add_res = p.res != nullptr && io_vec;
-      float r2[16], resv[16];
-      if constexpr (HAS_RES) ptx::tmem_ld<16>(t_row + (uint32_t)(N + n0), r2);
-      if (!valid) return;
-      if (add_res) load_row<16>(p.res, (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride + c0, p.res_dtype, resv);
-      const float4* sc4 = reinterpret_cast<const float4*>(&s_col[3][ng0]);
-      const float4* sh4 = reinterpret_cast<const float4*>(&s_col[4][ng0]);
-      const float4* rb4 = reinterpret_cast<const float4*>(&s_col[5][ng0]);
-      // one output element: activation, FiLM, identity residual, shortcut accumulator (+ its bias)
-      auto elem = [&](int j, float a, float d, float rbias) {
-        const int c = c0 + j;
-        float x = tc_act<ACT>(p.act, v[VO + j]);
-        if constexpr (SMP) {
-          if (scale_smp && c < p.C_out) a += __ldg(scale_smp + c);
-          if (shift_smp && c < p.C_out) d += __ldg(shift_smp + c);
-        }
-        x = fmaf(x, a, d);
-        if (add_res) x += resv[j];
-        if constexpr (HAS_RES) x += r2[j] + rbias;
-        resv[j] = x;                                              // reuse as the output staging registers
-      };
+      float addv[16];                                             // everything that is ADDED after the activation
+      if constexpr (FILM == 1) {
+        const float4* sh4 = reinterpret_cast<const float4*>(&s_col[4][ng0]);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 sc = sc4[k], sh = sh4[k];
-        float4 rbq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (HAS_RES) rbq = rb4[k];
-        elem(4 * k + 0, sc.x, sh.x, rbq.x);
-        elem(4 * k + 1, sc.y, sh.y, rbq.y);
-        elem(4 * k + 2, sc.z, sh.z, rbq.z);
-        elem(4 * k + 3, sc.w, sh.w, rbq.w);
+        for (int k = 0; k < 4; ++k) { const float4 s = sh4[k]; addv[4 * k] = s.x; addv[4 * k + 1] = s.y; addv[4 * k + 2] = s.z; addv[4 * k + 3] = s.w; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) addv[j] = 0.f;
       }
+      if (add_res) {
+        float resv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) resv[j] = 0.f;
+        if (valid) load_row<16>(p.res, res_row + c0, p.res_dtype, resv);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) addv[j] += resv[j];
+      }
+      if constexpr (HAS_RES) {
+        float r2[16];
+        ptx::tmem_ld<16>(t_row + (uint32_t)(N + n0), r2);
+        const float4* rb4 = reinterpret_cast<const float4*>(&s_col[5][ng0]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 s = rb4[k];
+          addv[4 * k] += r2[4 * k] + s.x; addv[4 * k + 1] += r2[4 * k + 1] + s.y;
+          addv[4 * k + 2] += r2[4 * k + 2] + s.z; addv[4 * k + 3] += r2[4 * k + 3] + s.w;
+        }
+      }
+      float o[16];
+      if constexpr (FILM == 2) {
+        float sc[16], sh[16];
+        const float4* sc4 = reinterpret_cast<const float4*>(&s_col[3][ng0]);
+        const float4* sh4 = reinterpret_cast<const float4*>(&s_col[4][ng0]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 a = sc4[k], d = sh4[k];
+          sc[4 * k] = a.x; sc[4 * k + 1] = a.y; sc[4 * k + 2] = a.z; sc[4 * k + 3] = a.w;
+          sh[4 * k] = d.x; sh[4 * k + 1] = d.y; sh[4 * k + 2] = d.z; sh[4 * k + 3] = d.w;
+        }
+        if (scale_smp && valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (c0 + j < p.C_out) sc[j] += __ldg(scale_smp + c0 + j);
+        }
+        if (shift_smp && valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (c0 + j < p.C_out) sh[j] += __ldg(shift_smp + c0 + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = fmaf(tc_act<ACT>(p.act, yv[YO + j]), sc[j], sh[j]) + addv[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if constexpr (ACT == CDS_ACT_MISH) o[j] = mish_fma(yv[YO + j], addv[j]);
+          else o[j] = tc_act<ACT>(p.act, yv[YO + j]) + addv[j];
+        }
+      }
+      if (!valid) return;
       const int64_t oo = (int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + c0;
       if (io_vec) {
-        store_row<16>(p.out, oo, p.out_dtype, resv);
+        store_row<16>(p.out, oo, p.out_dtype, o);
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (c0 + j < p.C_out) {
-            if (p.out_dtype == CDS_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[oo + j] = __float2bfloat16_rn(resv[j]);
-            else reinterpret_cast<float*>(p.out)[oo + j] = resv[j];
+            if (p.out_dtype == CDS_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[oo + j] = __float2bfloat16_rn(o[j]);
+            else reinterpret_cast<float*>(p.out)[oo + j] = o[j];
           }
         }
       }
     };
 
-    // v[j] += bias(column) for WC columns starting at local column n0 (float4 reads of the staged constants)
-    auto add_bias = [&](auto smp_tag, auto wc_tag, auto& v, int n0) {
-      constexpr bool SMP = decltype(smp_tag)::value;
+    // v[j] += bias(column) for WC columns starting at CTA-tile column n0 (float4 reads of the staged constants)
+    auto add_bias = [&](auto wc_tag, auto& v, int n0) {
       constexpr int WC = decltype(wc_tag)::value;
       const float4* b4 = reinterpret_cast<const float4*>(&s_col[0][n_off + n0]);
 #pragma unroll
@@ -355,99 +494,91 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         const float4 bb = b4[k];
         v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
       }
-      if constexpr (SMP) {
-        if (bias_smp && valid) {
+      if (bias_smp && valid) {
 #pragma unroll
-          for (int j = 0; j < WC; ++j) { const int c = (n_off + n0 + j) % p.C_out; v[j] += __ldg(bias_smp + c); }
-        }
+        for (int j = 0; j < WC; ++j) { const int c = (n_off + n0 + j) % p.C_out; v[j] += __ldg(bias_smp + c); }
       }
     };
 
-    // the whole slice of this thread, for one compile-time (ACT, SMP) combination
-    auto run = [&](auto act_tag, auto smp_tag) {
-      if constexpr (N >= 32) {
-        if (p.groups > 0) {
-          // GroupNorm (8 groups over the layer's kCols columns).  A chunk of WC = max(16, CPG) columns is loaded from TMEM
-          // ONCE, holds GPC = WC / CPG whole groups, and is normalised in registers: per-thread sums over the group's
-          // columns, then a butterfly over the L lanes (= positions) of the trajectory.
-          constexpr int CPG = Cfg::kCols / 8;
-          constexpr int WC = CPG > 16 ? CPG : 16;
-          constexpr int GPC = WC / CPG;
-          const float inv_cnt = 1.f / (float)(p.L * CPG);
+    // the whole column slice of this thread for one compile-time (GN, ACT, FILM) combination
+    auto run = [&](auto gn_tag, auto act_tag, auto film_tag) {
+      constexpr bool GN = decltype(gn_tag)::value;
+      if constexpr (GN && N >= 32) {
+        // GroupNorm (8 groups over the layer's kCols columns).  A chunk of WC = max(16, CPG) columns is read from TMEM
+        // once and holds GPC = WC / CPG whole groups: per-thread sums over the group's columns, all-reduce over the L
+        // lanes (= positions) of the trajectory, then y = ((v - mean) * rstd) * gamma + beta as two FMAs per element.
+        constexpr int CPG = Cfg::kCols / 8;
+        constexpr int WC = CPG > 16 ? CPG : 16;
+        constexpr int GPC = WC / CPG;
+        const float inv_cnt = 1.f / (float)(p.L * CPG);
 #pragma unroll 1
-          for (int ch = 0; ch < NH / WC; ++ch) {
-            const int n0 = col0 + ch * WC;
-            float v[WC];
-            ptx::tmem_ld<WC>(t_row + (uint32_t)n0, v);
-            add_bias(smp_tag, std::integral_constant<int, WC>{}, v, n0);
-            float s1[GPC], s2[GPC];
+        for (int ch = 0; ch < NH / WC; ++ch) {
+          const int n0 = col0 + ch * WC;
+          float v[WC];
+          ptx::tmem_ld<WC>(t_row + (uint32_t)n0, v);
+          add_bias(std::integral_constant<int, WC>{}, v, n0);
+          float s1[GPC], s2[GPC], ga[GPC], gc[GPC];
 #pragma unroll
-            for (int g = 0; g < GPC; ++g) {
-              s1[g] = 0.f; s2[g] = 0.f;
+          for (int g = 0; g < GPC; ++g) {
+            s1[g] = 0.f; s2[g] = 0.f;
 #pragma unroll
-              for (int j = 0; j < CPG; ++j) { const float x = v[g * CPG + j]; s1[g] += x; s2[g] = fmaf(x, x, s2[g]); }
-            }
-            for (int off = p.L >> 1; off >= 1; off >>= 1) {
-#pragma unroll
-              for (int g = 0; g < GPC; ++g) {
-                s1[g] += __shfl_xor_sync(0xffffffffu, s1[g], off);
-                s2[g] += __shfl_xor_sync(0xffffffffu, s2[g], off);
-              }
-            }
-            const float4* ga4 = reinterpret_cast<const float4*>(&s_col[1][n_off + n0]);
-            const float4* be4 = reinterpret_cast<const float4*>(&s_col[2][n_off + n0]);
-#pragma unroll
-            for (int g = 0; g < GPC; ++g) {
-              const float mean = s1[g] * inv_cnt;
-              const float rstd = rsqrtf(fmaxf(s2[g] * inv_cnt - mean * mean, 0.f) + p.gn_eps);
-#pragma unroll
-              for (int k = 0; k < CPG / 4; ++k) {
-                const float4 ga = ga4[g * (CPG / 4) + k], be = be4[g * (CPG / 4) + k];
-                const int o = g * CPG + 4 * k;
-                v[o + 0] = fmaf((v[o + 0] - mean) * rstd, ga.x, be.x); v[o + 1] = fmaf((v[o + 1] - mean) * rstd, ga.y, be.y);
-                v[o + 2] = fmaf((v[o + 2] - mean) * rstd, ga.z, be.z); v[o + 3] = fmaf((v[o + 3] - mean) * rstd, ga.w, be.w);
-              }
-            }
-            emit16(act_tag, smp_tag, v, std::integral_constant<int, 0>{}, n0);
-            if constexpr (WC == 32) emit16(act_tag, smp_tag, v, std::integral_constant<int, 1>{}, n0 + 16);
+            for (int j = 0; j < CPG; ++j) { const float x = v[g * CPG + j]; s1[g] += x; s2[g] = fmaf(x, x, s2[g]); }
           }
-        } else {
-#pragma unroll 1
-          for (int ch = 0; ch < NH / 16; ++ch) {
-            float v[16];
-            ptx::tmem_ld<16>(t_row + (uint32_t)(col0 + ch * 16), v);
-            add_bias(smp_tag, std::integral_constant<int, 16>{}, v, col0 + ch * 16);
-            emit16(act_tag, smp_tag, v, std::integral_constant<int, 0>{}, col0 + ch * 16);
+          gn_coeffs<GPC>(s1, s2, p.L, p.log2L, lane, inv_cnt, p.gn_eps, ga, gc);
+          const float4* ga4 = reinterpret_cast<const float4*>(&s_col[1][n_off + n0]);
+          const float4* be4 = reinterpret_cast<const float4*>(&s_col[2][n_off + n0]);
+#pragma unroll
+          for (int k = 0; k < WC / 4; ++k) {
+            const float4 gm = ga4[k], be = be4[k];
+            const int g = (4 * k) / CPG;
+            v[4 * k + 0] = fmaf(fmaf(v[4 * k + 0], ga[g], gc[g]), gm.x, be.x);
+            v[4 * k + 1] = fmaf(fmaf(v[4 * k + 1], ga[g], gc[g]), gm.y, be.y);
+            v[4 * k + 2] = fmaf(fmaf(v[4 * k + 2], ga[g], gc[g]), gm.z, be.z);
+            v[4 * k + 3] = fmaf(fmaf(v[4 * k + 3], ga[g], gc[g]), gm.w, be.w);
           }
+          post16(act_tag, film_tag, v, std::integral_constant<int, 0>{}, n0);
+          if constexpr (WC == 32) post16(act_tag, film_tag, v, std::integral_constant<int, 16>{}, n0 + 16);
         }
       } else {
-        float v[16];
-        ptx::tmem_ld<16>(t_row, v);
-        add_bias(smp_tag, std::integral_constant<int, 16>{}, v, 0);
-        emit16(act_tag, smp_tag, v, std::integral_constant<int, 0>{}, 0);
+#pragma unroll 1
+        for (int ch = 0; ch < NH / 16; ++ch) {
+          float v[16];
+          ptx::tmem_ld<16>(t_row + (uint32_t)(col0 + ch * 16), v);
+          add_bias(std::integral_constant<int, 16>{}, v, col0 + ch * 16);
+          post16(act_tag, film_tag, v, std::integral_constant<int, 0>{}, col0 + ch * 16);
+        }
       }
     };
 
     if (active) {
-      const bool smp = bias_smp || scale_smp || shift_smp;      // CTA-uniform
+      using T = std::true_type;
+      using F = std::false_type;
       using A0 = std::integral_constant<int, CDS_ACT_NONE>;
       using A1 = std::integral_constant<int, CDS_ACT_MISH>;
       using AX = std::integral_constant<int, kActOther>;
-      if (!smp) {
-        if (p.act == CDS_ACT_MISH) run(A1{}, std::false_type{});
-        else if (p.act == CDS_ACT_NONE) run(A0{}, std::false_type{});
-        else run(AX{}, std::false_type{});
+      using F0 = std::integral_constant<int, 0>;
+      using F1 = std::integral_constant<int, 1>;
+      using F2 = std::integral_constant<int, 2>;
+      if (has_gn) {
+        if (p.act == CDS_ACT_MISH) {
+          if (film == 0) run(T{}, A1{}, F0{});
+          else if (film == 1) run(T{}, A1{}, F1{});
+          else run(T{}, A1{}, F2{});
+        } else {
+          run(T{}, AX{}, F2{});
+        }
       } else {
-        if (p.act == CDS_ACT_MISH) run(A1{}, std::true_type{});
-        else if (p.act == CDS_ACT_NONE) run(A0{}, std::true_type{});
-        else run(AX{}, std::true_type{});
+        if (p.act == CDS_ACT_NONE && film == 0) run(F{}, A0{}, F0{});
+        else run(F{}, AX{}, F2{});
       }
     }
     // hand the accumulator buffer back to the MMA warp (one arrival per epilogue warp)
     ptx::tc_fence_before_sync();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+    if (threadIdx.x == 0 && it < 14) CDS_TRACE(11 + 4 * it, clock64());
     }   // tile loop
+    if (threadIdx.x == 0) CDS_TRACE(5, (long long)it);
   }
 
   __syncthreads();
@@ -455,6 +586,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (threadIdx.x == 0) { CDS_TRACE(3, clock64()); CDS_TRACE(4, gtimer()); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -502,7 +634,7 @@ inline int conv_tc_pick_kc(const cds_conv_op& c) {
 inline int conv_tc_width(const cds_conv_op& c) {
   int n = c.C_out * c.phases;
   if (n == 32 || n == 64 || n == 128 || n == 256) return (c.phases == 1 || c.C_out % 16 == 0) ? n : 0;
-  if (n <= 16 && c.phases == 1 && c.taps == 1 && c.groups == 0 && !c.res_w) return 16;
+  if (n <= 16 && c.phases == 1 && c.taps == 1 && c.groups == 0 && !c.res_w && !c.res) return 16;
   return 0;
 }
 
@@ -600,11 +732,17 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
   return true;
 }
 
+// debug: returns the trace buffer if THIS tensor-core launch is the one selected by cds_debug_trace (cds_api.cu), else NULL
+long long* conv_tc_trace_hook(int grid);
+
+// Launch wrapper of one instantiation.  The instantiations are compiled in conv_tc_inst.cu (several translation units, built
+// in parallel); every other translation unit only sees the extern declarations below.
 template <int KC, int N, bool HAS_RES, int SPLIT>
-inline cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStream_t st) {
+cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStream_t st) {
   using Cfg = ConvTcCfg<KC, N, HAS_RES, SPLIT>;
   static bool attr = false;
   static int resident = 0;                   // CTAs of this instantiation that fit on the device at once
+  static bool pdl = true;                    // chain with programmatic dependent launch (CDS_PDL=0: plain stream order)
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
@@ -622,22 +760,47 @@ inline cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, 
     int by_smem = (227 * 1024) / (Cfg::kSmemBytes + 8 * 1024);
     if (want > by_tmem) want = by_tmem;
     if (want > by_smem) want = by_smem;
+    if (const char* cap = getenv("CDS_TC_MAXCTAS")) { int c = atoi(cap); if (c >= 1 && c < want) want = c; }
     if (want < 1) want = 1;
     if (getenv("CDS_DEBUG"))
       fprintf(stderr, "[cds] conv_tc<%d,%d,%d,%d>: designed %d CTA/SM (tmem %d, smem %d), smem %d B, %d stages\n", KC, N,
               (int)HAS_RES, SPLIT, want, by_tmem, by_smem, Cfg::kSmemBytes, Cfg::kStages);
     resident = want * sms;
+    const char* pdl_env = getenv("CDS_PDL");
+    pdl = !(pdl_env && pdl_env[0] == '0');
     attr = true;
   }
   dim3 grid(L.grid.x < (unsigned)resident ? L.grid.x : (unsigned)resident);
-  conv_tc_kernel<KC, N, HAS_RES, SPLIT><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(L.prm, iter_ptr);
-  return cudaGetLastError();
+  ConvTcParams prm = L.prm;
+  prm.trace = conv_tc_trace_hook((int)grid.x);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<KC, N, HAS_RES, SPLIT>, prm, iter_ptr);
+}
+// touch the kernel once (module load) so that nothing lazy happens inside a stream capture
+template <int KC, int N, bool HAS_RES, int SPLIT>
+cudaError_t conv_tc_preload_t() {
+  cudaFuncAttributes a;
+  return cudaFuncGetAttributes(&a, conv_tc_kernel<KC, N, HAS_RES, SPLIT>);
 }
 
-// every (KC, N, RES, SPLIT) the dispatcher can pick; X(kc, n, split)
+// every (KC, N, SPLIT) the dispatcher can pick (each with and without the shortcut accumulator); X(kc, n, split)
 #define CDS_TC_VARIANTS(X)                                                                              \
   X(64, 16, 1) X(64, 32, 1) X(64, 64, 1) X(64, 128, 1) X(64, 256, 1) X(64, 32, 2) X(64, 64, 2) X(64, 128, 2) \
   X(32, 16, 1) X(32, 32, 1) X(32, 64, 1) X(32, 128, 1) X(32, 256, 1) X(32, 32, 2) X(32, 64, 2) X(32, 128, 2)
+
+#ifndef CDS_TC_INSTANTIATE
+#define CDS_TC_EXTERN(KC_, N_, S_)                                                                                      \
+  extern template cudaError_t conv_tc_launch_t<KC_, N_, false, S_>(const ConvTcLaunch&, const int*, cudaStream_t);      \
+  extern template cudaError_t conv_tc_launch_t<KC_, N_, true, S_>(const ConvTcLaunch&, const int*, cudaStream_t);       \
+  extern template cudaError_t conv_tc_preload_t<KC_, N_, false, S_>();                                                  \
+  extern template cudaError_t conv_tc_preload_t<KC_, N_, true, S_>();
+CDS_TC_VARIANTS(CDS_TC_EXTERN)
+#undef CDS_TC_EXTERN
 
 inline cudaError_t conv_tc_launch(const ConvTcLaunch& L, const int* iter_ptr, cudaStream_t st) {
 #define CDS_TC_CASE(KC_, N_, S_)                                                                 \
@@ -649,14 +812,14 @@ inline cudaError_t conv_tc_launch(const ConvTcLaunch& L, const int* iter_ptr, cu
 }
 
 inline cudaError_t conv_tc_preload_all() {
-  cudaFuncAttributes a;
   cudaError_t e;
-#define CDS_TC_PRE(KC_, N_, S_)                                                                   \
-  if ((e = cudaFuncGetAttributes(&a, conv_tc_kernel<KC_, N_, false, S_>)) != cudaSuccess) return e; \
-  if ((e = cudaFuncGetAttributes(&a, conv_tc_kernel<KC_, N_, true, S_>)) != cudaSuccess) return e;
+#define CDS_TC_PRE(KC_, N_, S_)                                                       \
+  if ((e = conv_tc_preload_t<KC_, N_, false, S_>()) != cudaSuccess) return e;         \
+  if ((e = conv_tc_preload_t<KC_, N_, true, S_>()) != cudaSuccess) return e;
   CDS_TC_VARIANTS(CDS_TC_PRE)
 #undef CDS_TC_PRE
   return cudaSuccess;
 }
+#endif  // !CDS_TC_INSTANTIATE
 
 }  // namespace cds

@@ -17,7 +17,9 @@ __device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
 
 // reads x, pred (+pred_uncond, noise, prior, xhat_prev), writes x (+xhat_prev): 12..28 B / element
-__global__ void __launch_bounds__(256) solver_update_kernel(const cds_update_op p, const int* __restrict__ iter_ptr) {
+// `advance` (or NULL): [0] = the iteration counter, [1] = blocks finished; the last block to finish bumps the counter, which
+// saves the one-thread advance kernel at the end of every iteration (every block has read the counter before it signals).
+__global__ void __launch_bounds__(256) solver_update_kernel(const cds_update_op p, const int* iter_ptr, int* advance) {
   const int iter = *iter_ptr;
   const float* row = p.coef + (int64_t)iter * CDS_ROW_FLOATS;
   const float alpha = row[CDS_ROW_ALPHA], sigma = row[CDS_ROW_SIGMA];
@@ -71,6 +73,17 @@ __global__ void __launch_bounds__(256) solver_update_kernel(const cds_update_op 
     }
     if (p.mask) { const float m = p.mask[e]; out = add_(mul_(out, 1.f - m), mul_(p.prior[i], m)); }
     p.x[i] = out;
+    if (p.x_cast) {
+      const int64_t r = i / p.cast_C_in;
+      reinterpret_cast<__nv_bfloat16*>(p.x_cast)[r * p.cast_C_out + (i - r * p.cast_C_in)] = __float2bfloat16_rn(out);
+    }
+  }
+  if (advance) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&advance[1], 1) == (int)gridDim.x - 1) { advance[1] = 0; advance[0] = iter + 1; }
+    }
   }
 }
 

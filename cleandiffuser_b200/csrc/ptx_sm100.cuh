@@ -126,6 +126,12 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[W]) {
 #undef CDS_R8
 #undef CDS_R16
 
+// programmatic dependent launch: wait = block until the grids this one depends on have completed and their memory is visible
+// (returns at once when the launch carried no programmatic dependency); launch_dependents = this CTA no longer holds back the
+// launch of the next grid in the stream
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // named barrier among a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");

@@ -10,7 +10,8 @@ import os
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "libcds.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+OPF_ONCE = 1          # cds_op.flags: run once per plan run (before its first iteration), not in every iteration
 OP_CONV, OP_UPDATE, OP_LNMOD, OP_ATTN, OP_PREP, OP_CAST = range(6)
 ACT_NONE, ACT_MISH, ACT_SILU, ACT_GELU_TANH, ACT_MISH_SILU = range(5)
 MATH_FP32, MATH_BF16_TC = 0, 1
@@ -70,6 +71,7 @@ class UpdateOp(C.Structure):
         ("pred", _f32p), ("pred_uncond", _f32p), ("w_cfg", C.c_float), ("w_uncond", C.c_float),
         ("noise", _f32p), ("prior", _f32p), ("mask", _f32p), ("x_min", _f32p), ("x_max", _f32p),
         ("xhat_prev", _f32p), ("coef", _f32p), ("predict_noise", C.c_int32), ("final_clip", C.c_int32),
+        ("x_cast", C.c_void_p), ("cast_C_in", C.c_int32), ("cast_C_out", C.c_int32),
     ]
 
 
@@ -79,7 +81,7 @@ class _OpUnion(C.Union):
 
 
 class Op(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("u", _OpUnion)]
+    _fields_ = [("kind", C.c_int32), ("flags", C.c_int32), ("u", _OpUnion)]
 
 
 class CdsError(RuntimeError):
@@ -93,7 +95,7 @@ _lib = None
 # every symbol include/cds.h declares (tests check that the built library exports all of them)
 EXPORTS = ["cds_version", "cds_op_size", "cds_conv_tc_supported", "cds_last_error", "cds_device_sm_count", "cds_plan_create", "cds_plan_destroy",
            "cds_plan_append", "cds_plan_finalize", "cds_plan_run", "cds_plan_profile", "cds_plan_launches_per_iter",
-           "cds_run_op"]
+           "cds_run_op", "cds_debug_trace"]
 
 
 def lib_path():
@@ -123,6 +125,7 @@ def load():
     lib.cds_plan_profile.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     lib.cds_plan_launches_per_iter.argtypes = [C.c_void_p]
     lib.cds_run_op.argtypes = [C.c_int, C.POINTER(Op), C.c_int32, C.c_void_p]
+    lib.cds_debug_trace.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
     if lib.cds_version() != ABI_VERSION:
         raise RuntimeError(f"libcds ABI {lib.cds_version()} != binding ABI {ABI_VERSION}: rebuild the extension")
     if lib.cds_op_size() != C.sizeof(Op):

@@ -118,6 +118,12 @@ class SamplerPlan:
         u.coef = self.coef.data_ptr()
         u.predict_noise = 1 if predict_noise else 0
         u.final_clip = 1 if consistency else 0
+        # tensor-core UNets read x_t through a channel-padded bf16 copy (CDS_OP_CAST).  When that cast converts the very
+        # buffer the update writes, the update emits the copy itself and the cast runs only once per sample() call.
+        for cop in p.ops:
+            if cop.kind == cabi.OP_CAST and cop.u.cast.in_ == self.x.data_ptr() and cop.u.cast.batch == batch:
+                cop.flags |= cabi.OPF_ONCE
+                u.x_cast, u.cast_C_in, u.cast_C_out = cop.u.cast.out, cop.u.cast.C_in, cop.u.cast.C_out
         self._update_op = op
         p.ops.append(op)
 

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CDS_ABI_VERSION 1
+#define CDS_ABI_VERSION 2
 
 typedef enum cds_status {
   CDS_OK = 0,
@@ -146,11 +146,18 @@ typedef struct cds_update_op {
   const float* coef;
   int32_t predict_noise;
   int32_t final_clip;            /* CM only: clip the combined prediction to [x_min, x_max] */
+  /* optional bf16 copy of the new x_t in the channel-padded form the tensor-core UNets read (what CDS_OP_CAST produces):
+   * element (r, c) of the dense (rows, cast_C_in) view of x goes to x_cast[r*cast_C_out + c]; pad channels are never
+   * written (a CDS_OPF_ONCE cast zeroes them and converts the initial x_t).  NULL = no copy. */
+  void* x_cast; int32_t cast_C_in; int32_t cast_C_out;
 } cds_update_op;
+
+/* cds_op.flags */
+enum { CDS_OPF_ONCE = 1 /* run once per cds_plan_run, before its first iteration, instead of in every iteration */ };
 
 typedef struct cds_op {
   int32_t kind;                  /* cds_op_kind */
-  int32_t reserved;
+  int32_t flags;
   union { cds_conv_op conv; cds_update_op update; cds_lnmod_op lnmod; cds_attn_op attn; cds_prep_op prep; cds_cast_op cast; } u;
 } cds_op;
 
@@ -175,15 +182,23 @@ int cds_plan_destroy(cds_plan* plan);
 int cds_plan_append(cds_plan* plan, const cds_op* ops, int32_t n_ops);
 /* Validate shapes, choose kernels, allocate the 4-byte device iteration counter. n_iters = rows in coef tables. */
 int cds_plan_finalize(cds_plan* plan, int32_t n_iters);
-/* Enqueue iterations [first, first+count) on `stream` (a cudaStream_t).  The first call captures the
- * program into a CUDA graph; later calls replay it.  use_graph = 0 launches kernels directly (debug/ncu). */
+/* Enqueue iterations [first, first+count) on `stream` (a cudaStream_t): CDS_OPF_ONCE operators first, then `count`
+ * replays of the iteration program.  The first call captures the program into a CUDA graph; later calls replay it.
+ * use_graph = 0 launches kernels directly (debug/ncu).  Consecutive tensor-core conv kernels are chained with
+ * programmatic dependent launch (the next kernel's prologue and weight prefetch overlap the previous kernel's tail);
+ * CDS_PDL=0 in the environment switches that off. */
 int cds_plan_run(cds_plan* plan, int32_t first, int32_t count, void* stream, int32_t use_graph);
 /* Run iteration `iter` once with direct launches, bracketing every operator with CUDA events on `stream`;
- * ms_per_op[i] receives the device time of operator i (n_ops entries).  Synchronises `stream`.  For bench.py's
- * live per-kernel roofline; note that it advances x_t like a normal iteration. */
+ * ms_per_op[i] receives the device time of operator i (n_ops entries; CDS_OPF_ONCE operators are run and timed first).
+ * Synchronises `stream`.  For bench.py's live per-kernel roofline; note that it advances x_t like a normal iteration. */
 int cds_plan_profile(cds_plan* plan, int32_t iter, void* stream, float* ms_per_op, int32_t n_ops);
 /* Number of kernel launches one iteration of the program performs (for bench.py's gpu_launches). */
 int cds_plan_launches_per_iter(const cds_plan* plan);
+
+/* Debug: record a clock64 timeline (64 slots per CTA, layout in csrc/conv_tc.cuh) of the `target_launch`-th tensor-core conv
+ * launch issued from now on into `device_buffer` (int64 entries); NULL switches tracing off.  Returns the grid size of the
+ * launch traced since the previous call (0 if none). */
+int cds_debug_trace(void* device_buffer, int64_t capacity_entries, int32_t target_launch);
 
 /* Stand-alone operator launch (parity tests of single kernels): runs `op` once with iteration index `iter`. */
 int cds_run_op(int device, const cds_op* op, int32_t iter, void* stream);

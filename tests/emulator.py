@@ -222,12 +222,23 @@ def run_update(u, it):
         m = _arr(u.mask, (u.row,), (1,))
         out = out * (f(1) - m) + _arr(u.prior, (u.batch, u.row), (u.row, 1)) * m
     x[...] = out.astype(np.float32)
+    if u.x_cast:                     # bf16 channel-padded copy of the new x_t (pad channels untouched)
+        rows = n // u.cast_C_in
+        y = _load(u.x_cast, (rows, u.cast_C_out), (u.cast_C_out, 1), cabi.BF16)
+        y[:, :u.cast_C_in] = x.reshape(rows, u.cast_C_in)
+        _store(u.x_cast, (rows, u.cast_C_out), (u.cast_C_out, 1), cabi.BF16, y)
 
 
 def run_program(ops, n_iters, first=0):
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        for op in ops:                       # CDS_OPF_ONCE operators: once per run, before the first iteration
+            if op.flags & cabi.OPF_ONCE:
+                assert op.kind == cabi.OP_CAST, op.kind
+                run_cast(op.u.cast)
         for it in range(first, first + n_iters):
             for op in ops:
+                if op.flags & cabi.OPF_ONCE:
+                    continue
                 if op.kind == cabi.OP_CONV:
                     run_conv(op.u.conv, it)
                 elif op.kind == cabi.OP_UPDATE:

@@ -195,3 +195,25 @@ def test_cfg2_bf16_tensor_cores_full_batch(monkeypatch):
                                       solver="ddpm", temperature=0.5, fix_mask=mask[None], predict_noise=False)
     err = (x_full[pick] - x_ref).abs()
     assert err.max() < 0.2 and err.mean() < 0.02, (float(err.max()), float(err.mean()))
+
+
+@pytest.mark.parametrize("name", ["disc_dup_ddpm_x0", "cont_ddim_eps", "cont_sde_dpmsolverpp_2M_x0"])
+def test_sampler_bf16_tensor_cores_goldens(golden, name, monkeypatch):
+    """Reverse loop on the tensor-core programs (once-cast + update-fused bf16 x_t copy + programmatic dependent launch)
+    against the reference goldens, with the stated bf16 tolerance; CDS_PDL=0 must give the same bits."""
+    monkeypatch.setenv("CDS_MATH", "bf16")
+    spec = cases.sampler_cases()[name]
+    outs = []
+    for graph in ("1", "0"):
+        monkeypatch.setenv("CDS_GRAPH", graph)
+        agent, inp, kw = build_agent(spec, device=DEV)
+        for k in ("condition_cfg", "warm_start_reference"):
+            if kw.get(k) is not None:
+                kw[k] = kw[k].to(DEV)
+        tape = NoiseTape(tape_of(golden["samplers"], name))
+        with tape.active(), torch.no_grad():
+            x0, _ = agent.sample(inp["prior"].to(DEV), **kw)
+        outs.append(x0.cpu())
+        err = np.abs(x0.cpu().numpy() - golden["samplers"][name + "/x0"])
+        assert err.max() < 0.2 and err.mean() < 0.02, (name, graph, float(err.max()), float(err.mean()))
+    assert torch.equal(outs[0], outs[1])         # graph replay == direct launches

@@ -23,7 +23,7 @@ class EmuHandle:
         emulator.run_program(self.ops, count, first)
 
     def launches_per_iter(self):
-        return len(self.ops) + 1
+        return len(self.ops)
 
     def close(self):
         pass
@@ -109,3 +109,27 @@ def test_bf16_program_uses_tensor_core_ops(monkeypatch):
     # two-phase transposed up-sampling and the 14-channel 1x1 head included -- runs on tcgen05
     assert p.ops[0].kind == cabi.OP_CAST
     assert kinds.count(cabi.MATH_BF16_TC) == len(kinds) == 40, kinds
+
+
+@pytest.mark.parametrize("name", ["disc_dup_ddpm_x0", "cont_ddim_eps", "cont_cfg2branch_2M"])
+def test_lowered_sampler_bf16(golden, name, monkeypatch):
+    """bf16 programs inside the reverse loop: the x_t hand-over cast runs ONCE per call (CDS_OPF_ONCE) and every solver
+    update refreshes the channel-padded bf16 copy itself (cds_update_op.x_cast)."""
+    monkeypatch.setenv("CDS_MATH", "bf16")
+    from cleandiffuser_b200.engine import cabi
+    spec = cases.sampler_cases()[name]
+    agent, inp, kw = build_agent(spec)
+    tape = NoiseTape(tape_of(golden["samplers"], name))
+    with tape.active(), torch.no_grad():
+        x0, _ = agent.sample(inp["prior"], **kw)
+    plan = next(iter(agent._engine_plans.values()))
+    ops = plan.program.ops
+    casts = [op for op in ops if op.kind == cabi.OP_CAST]
+    assert len(casts) == 1 and casts[0].flags & cabi.OPF_ONCE
+    upd = ops[-1].u.update
+    assert ops[-1].kind == cabi.OP_UPDATE and upd.x_cast == casts[0].u.cast.out and upd.cast_C_out == 32
+    err = np.abs(x0.numpy() - golden["samplers"][name + "/x0"])
+    # two-branch CFG multiplies the bf16 noise of the two predictions by |w| + |1 - w| (w_cfg = 2.5 in this case): a few
+    # outliers, same mean
+    max_tol = 1.5 if "cfg2branch" in name else 0.2
+    assert err.max() < max_tol and err.mean() < 0.02, (float(err.max()), float(err.mean()))
