@@ -11,6 +11,7 @@
 #include "attention.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv_ps.cuh"
 #include "elementwise.cuh"
 
 namespace {
@@ -38,6 +39,8 @@ struct Step {            // one validated operator + its kernel choice
   int conv_bn = 0;
   bool tc = false;       // tensor-core conv: tensor maps + launch geometry prepared at append time
   cds::ConvTcLaunch tcl;
+  bool ps = false;       // ... served by the position-sliced kernel (short sequences, conv_ps.cuh)
+  cds::ConvPsLaunch psl;
 };
 
 int elementwise_grid(int64_t total, int sm_count) {
@@ -62,6 +65,12 @@ int validate(const cds_op& op, Step* out) {
       if (c.math == CDS_MATH_BF16_TC) {
         if (!cds::conv_tc_eligible(c))
           return fail(CDS_ERR_INVALID, "conv: op is not eligible for the tensor-core kernel (ask cds_conv_tc_supported)");
+        if (cds::conv_ps_eligible(c)) {
+          if (!cds::conv_ps_prepare(c, &out->psl))
+            return fail(CDS_ERR_CUDA, "conv: cuTensorMapEncodeTiled failed (position-sliced, C_in=%d C_out=%d)", c.C_in, c.C_out);
+          out->tc = out->ps = true;
+          return CDS_OK;
+        }
         if (!cds::conv_tc_prepare(c, &out->tcl))
           return fail(CDS_ERR_CUDA, "conv: cuTensorMapEncodeTiled failed (C_in=%d L=%d C_out=%d)", c.C_in, c.L_in, c.C_out);
         out->tc = true;
@@ -116,7 +125,8 @@ int validate(const cds_op& op, Step* out) {
 int launch(const Step& s, const int* iter_ptr, int sm_count, cudaStream_t st, int* advance = nullptr) {
   switch (s.op.kind) {
     case CDS_OP_CONV:
-      if (s.tc) CDS_CUDA(cds::conv_tc_launch(s.tcl, iter_ptr, st));
+      if (s.ps) CDS_CUDA(cds::conv_ps_launch(s.psl, iter_ptr, st));
+      else if (s.tc) CDS_CUDA(cds::conv_tc_launch(s.tcl, iter_ptr, st));
       else CDS_CUDA(cds::conv_simt_launch(s.op.u.conv, s.conv_bn, iter_ptr, st));
       return CDS_OK;
     case CDS_OP_UPDATE: {
@@ -160,6 +170,7 @@ int preload_kernels() {
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<64>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::conv_gemm_f32_kernel<128>));
   CDS_CUDA(cds::conv_tc_preload_all());
+  CDS_CUDA(cds::conv_ps_preload_all());
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<16>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<32>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<64>));
