@@ -39,6 +39,7 @@ struct Step {            // one validated operator + its kernel choice
   int conv_bn = 0;
   bool tc = false;       // tensor-core conv: tensor maps + launch geometry prepared at append time
   cds::ConvTcLaunch tcl;
+  bool skip = false;     // solver update that was fused into the preceding conv's epilogue (finalize)
   bool ps = false;       // ... served by the position-sliced kernel (short sequences, conv_ps.cuh)
   cds::ConvPsLaunch psl;
 };
@@ -278,6 +279,30 @@ int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
   CDS_CUDA(cudaMemset(p->d_iter, 0, 2 * sizeof(int)));
   CDS_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
   p->n_iters = n_iters;
+  // peephole: [tensor-core narrow output head, fp32 dense out] -> [solver update reading it as its only prediction, last
+  // operator of the iteration]: the update moves into the head's epilogue (no prediction round trip, one launch less)
+  // OPT-IN (CDS_FUSE_UPDATE=1): measured slower on B200 than the separate streaming kernel (cfg2: 64 us vs 19 + 21 us) --
+  // the update's IEEE divisions serialise behind the head's tile loop on 296 CTAs instead of filling the machine.
+  const char* fuse_env = getenv("CDS_FUSE_UPDATE");
+  if (fuse_env && fuse_env[0] == '1') {
+    int last = -1, prev = -1;
+    for (int i = 0; i < (int)p->steps.size(); ++i)
+      if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) { prev = last; last = i; }
+    if (last >= 0 && prev >= 0 && p->steps[last].op.kind == CDS_OP_UPDATE && p->steps[prev].op.kind == CDS_OP_CONV &&
+        p->steps[prev].tc && !p->steps[prev].ps && p->steps[prev].tcl.n == 16) {
+      const cds_update_op& u = p->steps[last].op.u.update;
+      const cds_conv_op& c = p->steps[prev].op.u.conv;
+      const bool dense = c.out_dtype == CDS_F32 && c.out_lstride == c.C_out && c.out_bstride == (int64_t)c.L_out * c.C_out;
+      if (dense && u.pred == c.out && !u.pred_uncond && (int64_t)u.batch * u.row == (int64_t)c.batch * c.L_out * c.C_out &&
+          u.row == c.L_out * c.C_out && (!u.x_cast || u.cast_C_in == c.C_out) && !c.res &&
+          c.phases == 1 && c.act == CDS_ACT_NONE && !c.scale.step && !c.scale.sample && !c.shift.step && !c.shift.sample &&
+          !c.bias.sample) {
+        cds::ConvTcParams& prm = p->steps[prev].tcl.prm;
+        prm.upd = u; prm.upd_on = 1; prm.advance = p->d_iter;
+        p->steps[last].skip = true;
+      }
+    }
+  }
   p->finalized = true;
   return CDS_OK;
 }
@@ -286,7 +311,7 @@ int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
 // one-thread kernel
 static bool advance_fused(const cds_plan* p) {
   for (int i = (int)p->steps.size() - 1; i >= 0; --i)
-    if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) return p->steps[i].op.kind == CDS_OP_UPDATE;
+    if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) return p->steps[i].op.kind == CDS_OP_UPDATE;   // also when that update is `skip`
   return false;
 }
 
@@ -305,7 +330,7 @@ static int enqueue_iteration(cds_plan* p, cudaStream_t st) {
   for (int i = 0; i < (int)p->steps.size(); ++i) if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) last = i;
   for (int i = 0; i < (int)p->steps.size(); ++i) {
     const Step& s = p->steps[i];
-    if (s.op.flags & CDS_OPF_ONCE) continue;
+    if ((s.op.flags & CDS_OPF_ONCE) || s.skip) continue;      // a skipped update runs (and advances) inside the head's epilogue
     int rc = launch(s, p->d_iter, p->sm_count, st, (fused && i == last) ? p->d_iter : nullptr);
     if (rc != CDS_OK) return rc;
   }
@@ -360,8 +385,10 @@ int cds_plan_profile(cds_plan* p, int32_t iter, void* stream, float* ms_per_op, 
       const bool once = (p->steps[i].op.flags & CDS_OPF_ONCE) != 0;
       if (once != (pass == 0)) continue;
       CDS_CUDA(cudaEventRecord(ev[2 * i], st));
-      int rc = launch(p->steps[i], p->d_iter, p->sm_count, st);
-      if (rc != CDS_OK) return rc;
+      if (!p->steps[i].skip) {
+        int rc = launch(p->steps[i], p->d_iter, p->sm_count, st);
+        if (rc != CDS_OK) return rc;
+      }
       CDS_CUDA(cudaEventRecord(ev[2 * i + 1], st));
     }
   }
@@ -374,7 +401,7 @@ int cds_plan_profile(cds_plan* p, int32_t iter, void* stream, float* ms_per_op, 
 int cds_plan_launches_per_iter(const cds_plan* p) {
   if (!p) return 0;
   int n = advance_fused(p) ? 0 : 1;
-  for (const Step& s : p->steps) if (!(s.op.flags & CDS_OPF_ONCE)) ++n;
+  for (const Step& s : p->steps) if (!(s.op.flags & CDS_OPF_ONCE) && !s.skip) ++n;
   return n;
 }
 

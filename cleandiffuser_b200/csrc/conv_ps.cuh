@@ -46,7 +46,7 @@ struct ConvPsCfg {
   static constexpr int kATile = 128 * kRowBytes;
   static constexpr int kBTile = N * kRowBytes;
   static constexpr int kStageBytes = P * kATile + kTapsMax * kBTile;
-  static constexpr int kStages = 2;
+  static constexpr int kStages = KC == 64 ? 2 : 4;     // ~208 KB of operands in flight either way; finer chunks pipeline better
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
   static constexpr uint32_t kTmemCols = P * N * (HAS_RES ? 2 : 1);
   static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
@@ -103,7 +103,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
         uint8_t* sb = smem_al + s * Cfg::kStageBytes + P * Cfg::kATile;
         if (!HAS_RES || c < n_main) {
           for (int j = 0; j < p.taps; ++j)
-            ptx::tma_load_2d(sb + j * Cfg::kBTile, &p.tm_b, &full_bar[s], c * KC, j * p.C_out + n_off);
+            ptx::tma_load_2d(sb + (p.taps - 1 - j) * Cfg::kBTile, &p.tm_b, &full_bar[s], c * KC, j * p.C_out + n_off);   // slot = taps-1-j
         } else {
           ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], (c - n_main) * KC, n_off);
         }
@@ -146,19 +146,29 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
         const uint32_t sb = sa + P * Cfg::kATile;
         if (!HAS_RES || c < n_main) {
-#pragma unroll
+          // The W tiles sit in REVERSED tap order (slot r = taps-1-j) and the accumulators D_l' in position order, so for one
+          // input position l the valid outputs l' = lo..hi pair up with consecutive slots: ONE MMA of N' = (hi-lo+1)*N columns
+          // instead of (hi-lo+1) MMAs of N columns -- small-N MMAs are bound by re-reading the A tile from shared memory
+          // ((M+N)*32 B per K=16 step at 128 B/clk), N' >= 128 is tensor-bound.  The very first K step of the tile cannot
+          // merge (the accumulate flag differs between already-started and fresh accumulators).
           for (int l = 0; l < P; ++l) {
             const uint64_t da = ptx::make_kmajor_desc<Cfg::kRowBytes>(sa + l * Cfg::kATile);
+            const int lo = (l + p.pad - p.taps + 1) > 0 ? (l + p.pad - p.taps + 1) : 0;
+            const int hi = (l + p.pad) < (P - 1) ? (l + p.pad) : (P - 1);
+            const int slot0 = p.taps - 1 - (l - lo + p.pad);              // slot of the tap that feeds output position lo
+            const uint64_t db = ptx::make_kmajor_desc<Cfg::kRowBytes>(sb + slot0 * Cfg::kBTile);
+            const uint32_t idesc_m = ptx::make_idesc_bf16(128, (hi - lo + 1) * N);
 #pragma unroll
-            for (int lp = 0; lp < P; ++lp) {
-              const int j = l - lp + p.pad;           // tap that maps input position l to output position lp
-              if (j < 0 || j >= p.taps) continue;
-              const uint64_t db = ptx::make_kmajor_desc<Cfg::kRowBytes>(sb + j * Cfg::kBTile);
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k)
-                ptx::umma_bf16(tmem_base + (uint32_t)(lp * N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                               (((started >> lp) & 1u) | (uint32_t)(k > 0)));
-              started |= 1u << lp;
+            for (int k = 0; k < KC / 16; ++k) {
+              if (c == 0 && k == 0) {
+                for (int lp = lo; lp <= hi; ++lp) {
+                  const uint64_t dbj = ptx::make_kmajor_desc<Cfg::kRowBytes>(sb + (slot0 + lp - lo) * Cfg::kBTile);
+                  ptx::umma_bf16(tmem_base + (uint32_t)(lp * N), da, dbj, idesc, (started >> lp) & 1u);
+                  started |= 1u << lp;
+                }
+              } else {
+                ptx::umma_bf16(tmem_base + (uint32_t)(lo * N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_m, 1u);
+              }
             }
           }
         } else {
@@ -207,22 +217,30 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
     ptx::tc_fence_after_sync();
     if (threadIdx.x == 0) CDS_TRACE(10, clock64());
 
-    // ---- pass 1: GroupNorm statistics of (accumulator + bias) over P positions x NH channels, all in this thread
+    // ---- pass 1: GroupNorm statistics of (accumulator + bias) over P positions x NH channels, all in this thread.
+    // TMEM reads are double-buffered: the load of the next position is in flight while this one is summed.
     float s1 = 0.f, s2 = 0.f;
+    {
+      float va[NH], vb[NH];
+      ptx::tmem_ld_nowait<NH>(t_row + (uint32_t)col0, va);
+      auto accumulate = [&](const float (&v)[NH]) {
 #pragma unroll
-    for (int lp = 0; lp < P; ++lp) {
-#pragma unroll
-      for (int h = 0; h < NH / 16; ++h) {
-        float v[16];
-        ptx::tmem_ld<16>(t_row + (uint32_t)(lp * N + col0 + 16 * h), v);
-        const float4* b4 = reinterpret_cast<const float4*>(&s_col[0][col0 + 16 * h]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float4 bb = b4[k];
+        for (int k = 0; k < NH / 4; ++k) {
+          const float4 bb = reinterpret_cast<const float4*>(&s_col[0][col0])[k];
           const float x0 = v[4 * k] + bb.x, x1 = v[4 * k + 1] + bb.y, x2 = v[4 * k + 2] + bb.z, x3 = v[4 * k + 3] + bb.w;
           s1 += (x0 + x1) + (x2 + x3);
           s2 = fmaf(x0, x0, s2); s2 = fmaf(x1, x1, s2); s2 = fmaf(x2, x2, s2); s2 = fmaf(x3, x3, s2);
         }
+      };
+      static_assert(P % 2 == 0, "pass 1 ping-pongs two register buffers");
+#pragma unroll
+      for (int lp = 0; lp < P; lp += 2) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_nowait<NH>(t_row + (uint32_t)((lp + 1) * N + col0), vb);
+        accumulate(va);
+        ptx::tmem_ld_wait();
+        if (lp + 2 < P) ptx::tmem_ld_nowait<NH>(t_row + (uint32_t)((lp + 2) * N + col0), va);
+        accumulate(vb);
       }
     }
     const float inv_cnt = 1.f / (float)(P * NH);
@@ -230,51 +248,57 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
     const float ga = rsqrt_ftz(fmaxf(fmaf(s2, inv_cnt, -mean * mean), 0.f) + p.gn_eps);
     const float gc = -mean * ga;
 
-    // ---- pass 2: normalise, affine, Mish, additive terms, store
+    // ---- pass 2: normalise, affine, Mish, additive terms, store; 16-column chunks, the next chunk's TMEM read in flight
     const bool add_res = p.res != nullptr;
-#pragma unroll 1
-    for (int lp = 0; lp < P; ++lp) {
+    constexpr int kChunks = P * (NH / 16);
+    float vbuf[2][16];
+    ptx::tmem_ld_nowait<16>(t_row + (uint32_t)col0, vbuf[0]);
 #pragma unroll
-      for (int h = 0; h < NH / 16; ++h) {
-        const int n0 = col0 + 16 * h;                 // CTA-tile column
-        float v[16], addv[16];
-        ptx::tmem_ld<16>(t_row + (uint32_t)(lp * N + n0), v);
-        const float4* sh4 = reinterpret_cast<const float4*>(&s_col[3][n0]);
+    for (int ci = 0; ci < kChunks; ++ci) {
+      const int lp = ci / (NH / 16), h = ci % (NH / 16);
+      const int n0 = col0 + 16 * h;                   // CTA-tile column
+      float (&v)[16] = vbuf[ci & 1];
+      float addv[16];
+      const float4* sh4 = reinterpret_cast<const float4*>(&s_col[3][n0]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const float4 s = sh4[k]; addv[4 * k] = s.x; addv[4 * k + 1] = s.y; addv[4 * k + 2] = s.z; addv[4 * k + 3] = s.w; }
-        if (add_res) {
-          float resv[16];
+      for (int k = 0; k < 4; ++k) { const float4 s = sh4[k]; addv[4 * k] = s.x; addv[4 * k + 1] = s.y; addv[4 * k + 2] = s.z; addv[4 * k + 3] = s.w; }
+      if (add_res) {
+        float resv[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) resv[j] = 0.f;
-          if (valid) load_row<16>(p.res, (int64_t)rb * p.res_bstride + (int64_t)lp * p.res_lstride + n_off + n0, CDS_BF16, resv);
+        for (int j = 0; j < 16; ++j) resv[j] = 0.f;
+        if (valid) load_row<16>(p.res, (int64_t)rb * p.res_bstride + (int64_t)lp * p.res_lstride + n_off + n0, CDS_BF16, resv);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) addv[j] += resv[j];
-        }
-        if constexpr (HAS_RES) {
-          float r2[16];
-          ptx::tmem_ld<16>(t_row + (uint32_t)(P * N + lp * N + n0), r2);
-          const float4* rb4 = reinterpret_cast<const float4*>(&s_col[4][n0]);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 s = rb4[k];
-            addv[4 * k] += r2[4 * k] + s.x; addv[4 * k + 1] += r2[4 * k + 1] + s.y;
-            addv[4 * k + 2] += r2[4 * k + 2] + s.z; addv[4 * k + 3] += r2[4 * k + 3] + s.w;
-          }
-        }
-        const float4* b4 = reinterpret_cast<const float4*>(&s_col[0][n0]);
-        const float4* ga4 = reinterpret_cast<const float4*>(&s_col[1][n0]);
-        const float4* be4 = reinterpret_cast<const float4*>(&s_col[2][n0]);
-        float o[16];
+        for (int j = 0; j < 16; ++j) addv[j] += resv[j];
+      }
+      ptx::tmem_ld_wait();
+      if (ci + 1 < kChunks) {
+        const int lp1 = (ci + 1) / (NH / 16), h1 = (ci + 1) % (NH / 16);
+        ptx::tmem_ld_nowait<16>(t_row + (uint32_t)(lp1 * N + col0 + 16 * h1), vbuf[(ci + 1) & 1]);
+      }
+      if constexpr (HAS_RES) {
+        float r2[16];
+        ptx::tmem_ld<16>(t_row + (uint32_t)(P * N + lp * N + n0), r2);      // (its wait also completes the prefetch above)
+        const float4* rb4 = reinterpret_cast<const float4*>(&s_col[4][n0]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float4 bb = b4[k], gm = ga4[k], be = be4[k];
-          o[4 * k + 0] = mish_fma(fmaf(fmaf(v[4 * k + 0] + bb.x, ga, gc), gm.x, be.x), addv[4 * k + 0]);
-          o[4 * k + 1] = mish_fma(fmaf(fmaf(v[4 * k + 1] + bb.y, ga, gc), gm.y, be.y), addv[4 * k + 1]);
-          o[4 * k + 2] = mish_fma(fmaf(fmaf(v[4 * k + 2] + bb.z, ga, gc), gm.z, be.z), addv[4 * k + 2]);
-          o[4 * k + 3] = mish_fma(fmaf(fmaf(v[4 * k + 3] + bb.w, ga, gc), gm.w, be.w), addv[4 * k + 3]);
+          const float4 s = rb4[k];
+          addv[4 * k] += r2[4 * k] + s.x; addv[4 * k + 1] += r2[4 * k + 1] + s.y;
+          addv[4 * k + 2] += r2[4 * k + 2] + s.z; addv[4 * k + 3] += r2[4 * k + 3] + s.w;
         }
-        if (valid) store_row<16>(p.out, (int64_t)b * p.out_bstride + (int64_t)lp * p.out_lstride + n_off + n0, CDS_BF16, o);
       }
+      const float4* b4 = reinterpret_cast<const float4*>(&s_col[0][n0]);
+      const float4* ga4 = reinterpret_cast<const float4*>(&s_col[1][n0]);
+      const float4* be4 = reinterpret_cast<const float4*>(&s_col[2][n0]);
+      float o[16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 bb = b4[k], gm = ga4[k], be = be4[k];
+        o[4 * k + 0] = mish_fma(fmaf(fmaf(v[4 * k + 0] + bb.x, ga, gc), gm.x, be.x), addv[4 * k + 0]);
+        o[4 * k + 1] = mish_fma(fmaf(fmaf(v[4 * k + 1] + bb.y, ga, gc), gm.y, be.y), addv[4 * k + 1]);
+        o[4 * k + 2] = mish_fma(fmaf(fmaf(v[4 * k + 2] + bb.z, ga, gc), gm.z, be.z), addv[4 * k + 2]);
+        o[4 * k + 3] = mish_fma(fmaf(fmaf(v[4 * k + 3] + bb.w, ga, gc), gm.w, be.w), addv[4 * k + 3]);
+      }
+      if (valid) store_row<16>(p.out, (int64_t)b * p.out_bstride + (int64_t)lp * p.out_lstride + n_off + n0, CDS_BF16, o);
     }
     if (threadIdx.x == 0) { CDS_TRACE(11, clock64()); CDS_TRACE(5, 1LL); }
     ptx::tc_fence_before_sync();
@@ -290,6 +314,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
 
 // ------------------------------------------------------------------------------------------------ host side
 constexpr int kPsPositions = 4;
+constexpr int kPsKC = 32;            // channel chunk: 32 (SWIZZLE_64B tiles, 4-stage ring) pipelines better than 64 (2 stages)
 
 // CTA tile width: a quarter of the layer (two GroupNorm groups); 0 = the kernel is not instantiated for this layer
 inline int conv_ps_width(const cds_conv_op& c) {
@@ -325,7 +350,7 @@ inline bool conv_ps_prepare(const cds_conv_op& c, ConvPsLaunch* out) {
   ConvPsLaunch& L = *out;
   memset(&L.prm, 0, sizeof(L.prm));
   ConvPsParams& p = L.prm;
-  constexpr int kc = 64;
+  constexpr int kc = kPsKC;
   L.n = conv_ps_width(c);
   L.has_res = c.res_w != nullptr;
   const uint64_t in_b = c.in_batch_mod > 0 ? (uint64_t)c.in_batch_mod : (uint64_t)c.batch;
@@ -366,15 +391,15 @@ inline bool conv_ps_prepare(const cds_conv_op& c, ConvPsLaunch* out) {
 
 template <int N, bool HAS_RES>
 cudaError_t conv_ps_launch_t(const ConvPsLaunch& L, const int* iter_ptr, cudaStream_t st) {
-  using Cfg = ConvPsCfg<64, N, kPsPositions, HAS_RES>;
+  using Cfg = ConvPsCfg<kPsKC, N, kPsPositions, HAS_RES>;
   static bool attr = false;
   static bool pdl = true;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_ps_kernel<64, N, kPsPositions, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_ps_kernel<kPsKC, N, kPsPositions, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     if (getenv("CDS_DEBUG"))
-      fprintf(stderr, "[cds] conv_ps<64,%d,%d,%d>: smem %d B, tmem %u columns\n", N, kPsPositions, (int)HAS_RES, Cfg::kSmemBytes,
+      fprintf(stderr, "[cds] conv_ps<%d,%d,%d,%d>: smem %d B, tmem %u columns\n", kPsKC, N, kPsPositions, (int)HAS_RES, Cfg::kSmemBytes,
               Cfg::kTmemCols);
     const char* pdl_env = getenv("CDS_PDL");
     pdl = !(pdl_env && pdl_env[0] == '0');
@@ -388,12 +413,12 @@ cudaError_t conv_ps_launch_t(const ConvPsLaunch& L, const int* iter_ptr, cudaStr
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv_ps_kernel<64, N, kPsPositions, HAS_RES>, prm, iter_ptr);
+  return cudaLaunchKernelEx(&cfg, conv_ps_kernel<kPsKC, N, kPsPositions, HAS_RES>, prm, iter_ptr);
 }
 template <int N, bool HAS_RES>
 cudaError_t conv_ps_preload_t() {
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, conv_ps_kernel<64, N, kPsPositions, HAS_RES>);
+  return cudaFuncGetAttributes(&a, conv_ps_kernel<kPsKC, N, kPsPositions, HAS_RES>);
 }
 
 #ifndef CDS_PS_INSTANTIATE

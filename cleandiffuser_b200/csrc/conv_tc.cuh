@@ -25,6 +25,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "elementwise.cuh"
 #include "ptx_sm100.cuh"
 
 namespace cds {
@@ -47,6 +48,9 @@ struct ConvTcParams {
   const void* res; int64_t res_bstride; int res_lstride; int res_batch_mod; int res_dtype;
   const float* res_bias;
   void* out; int64_t out_bstride; int out_lstride; int out_dtype;
+  // solver update fused into the epilogue of the network's narrow output head (upd_on): the prediction never goes to
+  // HBM, x_t is updated in place by the thread that holds the accumulator; `advance` as in solver_update_kernel
+  cds_update_op upd; int upd_on; int* advance;
   long long* trace;               // debug: per-CTA clock64 timeline (kTraceSlots entries per CTA), normally NULL
 };
 constexpr int kTraceSlots = 64;
@@ -229,6 +233,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   // per-column constants of the epilogue, staged once per CTA while the main loop runs:
   // 0 bias  1 GN gamma  2 GN beta  3 FiLM scale  4 FiLM shift  5 shortcut bias   (iteration-indexed "step" parts)
   __shared__ __align__(16) float s_col[6][Cfg::kCols];
+  // fused solver update (narrow head only): the tile's predictions, re-read with a coalesced element <-> thread mapping
+  __shared__ float s_pred[N == 16 ? 128 * 16 : 1];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // operand ring, 1024-byte aligned (swizzle atoms)
@@ -384,6 +390,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     const bool add_res = p.res != nullptr;
     const int film = (smp || has_scale) ? 2 : (has_shift ? 1 : 0);
 
+    UpdRow upd_row = {};
+    if (N == 16 && p.upd_on) upd_row = load_upd_row(p.upd, iter);
     const int m = 32 * q + lane;
     const int col0 = half * NH;
     int it = 0;
@@ -470,10 +478,14 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
           else o[j] = tc_act<ACT>(p.act, yv[YO + j]) + addv[j];
         }
       }
-      if (!valid) return;
+      if (!valid && !(N == 16 && p.upd_on)) return;
       const int64_t oo = (int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + c0;
       if (io_vec) {
         store_row<16>(p.out, oo, p.out_dtype, o);
+      } else if (N == 16 && p.upd_on) {
+        // the head's prediction feeds the solver update (below, after the tile's rows are all staged)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s_pred[(N == 16 ? m : 0) * 16 + j] = o[j];
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -576,6 +588,20 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     ptx::tc_fence_before_sync();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+    if (N == 16 && p.upd_on) {
+      // fused reverse-process update of the tile's 128 rows x C_out elements (contiguous in x_t): all 256 epilogue threads,
+      // consecutive threads <-> consecutive elements
+      ptx::named_bar_sync(1, kTcEpiThreads);
+      const int64_t row0 = (int64_t)tile * 128;                       // SPLIT == 1 for the narrow head
+      const int64_t rows_left = (int64_t)p.batch * p.L - row0;
+      const int cnt = (int)(rows_left < 128 ? rows_left : 128) * p.C_out;
+      const int traj = p.L * p.C_out;                                 // tiles start on trajectory boundaries (128 % L == 0)
+      for (int k = threadIdx.x; k < cnt; k += kTcEpiThreads) {
+        const int r = k / p.C_out, j = k - r * p.C_out;
+        solver_update_element(p.upd, upd_row, row0 * p.C_out + k, k % traj, (row0 + r) * p.upd.cast_C_out + j, s_pred[r * 16 + j]);
+      }
+      ptx::named_bar_sync(1, kTcEpiThreads);
+    }
     if (threadIdx.x == 0 && it < 14) CDS_TRACE(11 + 4 * it, clock64());
     }   // tile loop
     if (threadIdx.x == 0) CDS_TRACE(5, (long long)it);
@@ -586,6 +612,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (N == 16 && p.upd_on && p.advance) advance_iteration_when_last(p.advance, iter_ptr ? *iter_ptr : 0);
   if (threadIdx.x == 0) { CDS_TRACE(3, clock64()); CDS_TRACE(4, gtimer()); }
 }
 

@@ -16,79 +16,107 @@ __device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
 
-// reads x, pred (+pred_uncond, noise, prior, xhat_prev), writes x (+xhat_prev): 12..28 B / element
-// `advance` (or NULL): [0] = the iteration counter, [1] = blocks finished; the last block to finish bumps the counter, which
-// saves the one-thread advance kernel at the end of every iteration (every block has read the counter before it signals).
-__global__ void __launch_bounds__(256) solver_update_kernel(const cds_update_op p, const int* iter_ptr, int* advance) {
-  const int iter = *iter_ptr;
+// per-iteration scalars of the update (one row of the coefficient table)
+struct UpdRow {
+  float alpha, sigma, k0, k1, k2, k3, k4;
+  int kind;
+  const float* noise;          // this iteration's noise slot or NULL
+};
+__device__ __forceinline__ UpdRow load_upd_row(const cds_update_op& p, int iter) {
   const float* row = p.coef + (int64_t)iter * CDS_ROW_FLOATS;
-  const float alpha = row[CDS_ROW_ALPHA], sigma = row[CDS_ROW_SIGMA];
-  const float k0 = row[CDS_ROW_K0], k1 = row[CDS_ROW_K1], k2 = row[CDS_ROW_K2], k3 = row[CDS_ROW_K3], k4 = row[CDS_ROW_K4];
-  const int kind = (int)row[CDS_ROW_KIND];
+  UpdRow r;
+  r.alpha = row[CDS_ROW_ALPHA]; r.sigma = row[CDS_ROW_SIGMA];
+  r.k0 = row[CDS_ROW_K0]; r.k1 = row[CDS_ROW_K1]; r.k2 = row[CDS_ROW_K2]; r.k3 = row[CDS_ROW_K3]; r.k4 = row[CDS_ROW_K4];
+  r.kind = (int)row[CDS_ROW_KIND];
   const int slot = (int)row[CDS_ROW_NOISE] - 1;
-  const int64_t total = (int64_t)p.batch * p.row;
-  const float* noise = slot >= 0 ? p.noise + (int64_t)slot * total : nullptr;
+  r.noise = slot >= 0 ? p.noise + (int64_t)slot * p.batch * p.row : nullptr;
+  return r;
+}
 
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int e = (int)(i % p.row);
-    const float x = p.x[i];
-    float pr = p.pred[i];
-    if (p.pred_uncond) pr = add_(mul_(p.w_cfg, pr), mul_(p.w_uncond, p.pred_uncond[i]));
-
-    float out;
-    if (kind == CDS_UPD_CM) {
-      // f = c_skip*x + c_out*net ; clip (consistency_model.py:257-261)
-      out = add_(mul_(k0, x), mul_(k1, pr));
-      if (p.final_clip) {
-        if (p.x_min) out = fmaxf(out, p.x_min[e]);
-        if (p.x_max) out = fminf(out, p.x_max[e]);
-      }
-    } else {
-      // clip_prediction (diffusionsde.py:208-223)
-      if (p.predict_noise) {
-        if (p.x_max) pr = fmaxf(pr, div_(sub_(x, mul_(alpha, p.x_max[e])), sigma));
-        if (p.x_min) pr = fminf(pr, div_(sub_(x, mul_(alpha, p.x_min[e])), sigma));
-      } else {
-        if (p.x_min) pr = fmaxf(pr, p.x_min[e]);
-        if (p.x_max) pr = fminf(pr, p.x_max[e]);
-      }
-      float eps, xhat;
-      if (p.predict_noise) { eps = pr; xhat = div_(sub_(x, mul_(sigma, pr)), alpha); }
-      else { xhat = pr; eps = div_(sub_(x, mul_(alpha, pr)), sigma); }
-
-      if (kind == CDS_UPD_DDPM) {
-        out = add_(mul_(k0, sub_(x, mul_(sigma, eps))), mul_(k1, eps));
-        if (noise) out = add_(out, mul_(k2, noise[i]));
-      } else if (kind == CDS_UPD_DDIM) {
-        out = add_(mul_(k0, div_(sub_(x, mul_(sigma, eps)), alpha)), mul_(k1, eps));
-      } else {
-        float target;
-        if (kind == CDS_UPD_EPS) target = eps;
-        else if (kind == CDS_UPD_X2M) target = sub_(mul_(k3, xhat), mul_(k4, p.xhat_prev[i]));
-        else target = xhat;
-        out = sub_(mul_(k0, x), mul_(k1, target));
-        if (noise) out = add_(out, mul_(k2, noise[i]));
-        if (p.xhat_prev) p.xhat_prev[i] = xhat;
-      }
+// One element of the reverse-process update: i = flat index into x (batch*row), `pr` = the network prediction for it (after
+// the CFG combine).  Reads x (+noise, prior, xhat_prev), writes x (+xhat_prev, +the bf16 channel-padded copy).
+// e = i % row (index inside the trajectory), cast_off = element offset in x_cast (ignored when x_cast is NULL)
+__device__ __forceinline__ void solver_update_element(const cds_update_op& p, const UpdRow& r, int64_t i, int e, int64_t cast_off,
+                                                      float pr) {
+  const float x = p.x[i];
+  const float alpha = r.alpha, sigma = r.sigma;
+  float out;
+  if (r.kind == CDS_UPD_CM) {
+    // f = c_skip*x + c_out*net ; clip (consistency_model.py:257-261)
+    out = add_(mul_(r.k0, x), mul_(r.k1, pr));
+    if (p.final_clip) {
+      if (p.x_min) out = fmaxf(out, p.x_min[e]);
+      if (p.x_max) out = fminf(out, p.x_max[e]);
     }
-    if (p.mask) { const float m = p.mask[e]; out = add_(mul_(out, 1.f - m), mul_(p.prior[i], m)); }
-    p.x[i] = out;
-    if (p.x_cast) {
-      const int64_t r = i / p.cast_C_in;
-      reinterpret_cast<__nv_bfloat16*>(p.x_cast)[r * p.cast_C_out + (i - r * p.cast_C_in)] = __float2bfloat16_rn(out);
+  } else {
+    // clip_prediction (diffusionsde.py:208-223)
+    if (p.predict_noise) {
+      if (p.x_max) pr = fmaxf(pr, div_(sub_(x, mul_(alpha, p.x_max[e])), sigma));
+      if (p.x_min) pr = fminf(pr, div_(sub_(x, mul_(alpha, p.x_min[e])), sigma));
+    } else {
+      if (p.x_min) pr = fmaxf(pr, p.x_min[e]);
+      if (p.x_max) pr = fminf(pr, p.x_max[e]);
+    }
+    float eps, xhat;
+    if (p.predict_noise) { eps = pr; xhat = div_(sub_(x, mul_(sigma, pr)), alpha); }
+    else { xhat = pr; eps = div_(sub_(x, mul_(alpha, pr)), sigma); }
+
+    if (r.kind == CDS_UPD_DDPM) {
+      out = add_(mul_(r.k0, sub_(x, mul_(sigma, eps))), mul_(r.k1, eps));
+      if (r.noise) out = add_(out, mul_(r.k2, r.noise[i]));
+    } else if (r.kind == CDS_UPD_DDIM) {
+      out = add_(mul_(r.k0, div_(sub_(x, mul_(sigma, eps)), alpha)), mul_(r.k1, eps));
+    } else {
+      float target;
+      if (r.kind == CDS_UPD_EPS) target = eps;
+      else if (r.kind == CDS_UPD_X2M) target = sub_(mul_(r.k3, xhat), mul_(r.k4, p.xhat_prev[i]));
+      else target = xhat;
+      out = sub_(mul_(r.k0, x), mul_(r.k1, target));
+      if (r.noise) out = add_(out, mul_(r.k2, r.noise[i]));
+      if (p.xhat_prev) p.xhat_prev[i] = xhat;
     }
   }
-  if (advance) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(&advance[1], 1) == (int)gridDim.x - 1) { advance[1] = 0; advance[0] = iter + 1; }
-    }
+  if (p.mask) { const float m = p.mask[e]; out = add_(mul_(out, 1.f - m), mul_(p.prior[i], m)); }
+  p.x[i] = out;
+  if (p.x_cast) reinterpret_cast<__nv_bfloat16*>(p.x_cast)[cast_off] = __float2bfloat16_rn(out);
+}
+
+// the last block of a grid to finish bumps the iteration counter ([0] = counter, [1] = blocks finished): saves the
+// one-thread advance kernel at the end of every iteration.  Every block has read the counter before it signals.
+__device__ __forceinline__ void advance_iteration_when_last(int* advance, int iter) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&advance[1], 1) == (int)gridDim.x - 1) { advance[1] = 0; advance[0] = iter + 1; }
   }
 }
 
+// reads x, pred (+pred_uncond, noise, prior, xhat_prev), writes x (+xhat_prev): 12..28 B / element
+static __global__ void __launch_bounds__(256) solver_update_kernel(const cds_update_op p, const int* iter_ptr, int* advance) {
+  const int iter = *iter_ptr;
+  const UpdRow r = load_upd_row(p, iter);
+  const int64_t total = (int64_t)p.batch * p.row;
+  const bool small = total < (int64_t)0x7fffffff;            // 32-bit index arithmetic (64-bit divisions are ~20x dearer)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float pr = p.pred[i];
+    if (p.pred_uncond) pr = add_(mul_(p.w_cfg, pr), mul_(p.w_uncond, p.pred_uncond[i]));
+    int e;
+    int64_t cast_off = 0;
+    if (small) {
+      const unsigned iu = (unsigned)i;
+      e = (int)(iu % (unsigned)p.row);
+      if (p.x_cast) { const unsigned rr = iu / (unsigned)p.cast_C_in; cast_off = (int64_t)rr * p.cast_C_out + (iu - rr * (unsigned)p.cast_C_in); }
+    } else {
+      e = (int)(i % p.row);
+      if (p.x_cast) { const int64_t rr = i / p.cast_C_in; cast_off = rr * p.cast_C_out + (i - rr * p.cast_C_in); }
+    }
+    solver_update_element(p, r, i, e, cast_off, pr);
+  }
+  if (advance) advance_iteration_when_last(advance, iter);
+}
+
 // x += K2*z (re-noise, only when the row has a noise slot); xin = K3*x.   8..16 B / element
-__global__ void __launch_bounds__(256) cm_prep_kernel(const cds_prep_op p, const int* __restrict__ iter_ptr) {
+static __global__ void __launch_bounds__(256) cm_prep_kernel(const cds_prep_op p, const int* __restrict__ iter_ptr) {
   const int iter = *iter_ptr;
   const float* row = p.coef + (int64_t)iter * CDS_ROW_FLOATS;
   const float k2 = row[CDS_ROW_K2], k3 = row[CDS_ROW_K3];
@@ -103,7 +131,7 @@ __global__ void __launch_bounds__(256) cm_prep_kernel(const cds_prep_op p, const
 }
 
 // one warp per token row: LayerNorm (biased variance, no affine) then x*(1+scale)+shift.  8 B / element
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const cds_lnmod_op p) {
+static __global__ void __launch_bounds__(256) ln_modulate_kernel(const cds_lnmod_op p) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t n_rows = (int64_t)p.batch * p.L;
@@ -125,7 +153,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const cds_lnmod_op p) 
 }
 
 // fp32 (rows, C_in) -> bf16 (rows, C_out) zero padded; one thread per output pair.  4*C_in + 2*C_out B / row
-__global__ void __launch_bounds__(256) cast_pad_kernel(const cds_cast_op p) {
+static __global__ void __launch_bounds__(256) cast_pad_kernel(const cds_cast_op p) {
   const int64_t rows = (int64_t)p.batch * p.L;
   const int pairs = p.C_out >> 1;
   const int64_t total = rows * pairs;
@@ -139,7 +167,7 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const cds_cast_op p) {
   }
 }
 
-__global__ void set_iter_kernel(int* iter_ptr, int value) { *iter_ptr = value; }
-__global__ void advance_iter_kernel(int* iter_ptr) { *iter_ptr += 1; }
+static __global__ void set_iter_kernel(int* iter_ptr, int value) { *iter_ptr = value; }
+static __global__ void advance_iter_kernel(int* iter_ptr) { *iter_ptr += 1; }
 
 }  // namespace cds

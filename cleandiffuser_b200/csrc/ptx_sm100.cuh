@@ -122,6 +122,27 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[W]) {
 #pragma unroll
   for (int i = 0; i < W; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the same load WITHOUT the wait: issue several, then tmem_ld_wait() once (the destination registers are undefined until then)
+template <int W>
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, float (&v)[W]) {
+  static_assert(W == 16 || W == 32, "unsupported tcgen05.ld width");
+  uint32_t* r = reinterpret_cast<uint32_t*>(&v[0]);
+  if constexpr (W == 16) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : CDS_R16(0)
+        : "r"(taddr));
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : CDS_R16(0), CDS_R16(16)
+        : "r"(taddr));
+  }
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 #undef CDS_R4
 #undef CDS_R8
 #undef CDS_R16
