@@ -251,9 +251,15 @@ def main():
             step_resident()
             torch.cuda.synchronize()
             log(f"warm-up step {i} done")
+        runtime.STATS["time_loop"] = True
+        runtime.STATS["loop_events"] = []
         with ClockSampler(local_rank) as clk:
             ms = timed(step_resident, args.steps)
-        log(f"timed: {ms / args.steps:.1f} ms/step")
+        runtime.STATS["time_loop"] = False
+        loop_ms = [a.elapsed_time(b) for a, b in runtime.STATS["loop_events"]]
+        loop_ms_mean = sum(loop_ms) / max(len(loop_ms), 1)
+        log(f"timed: {ms / args.steps:.1f} ms/step; reverse loop alone {loop_ms_mean:.2f} ms "
+            f"({loop_ms_mean * 1e3 / S_STEPS:.1f} us / iteration)")
         launches = runtime.STATS["launches"] * args.steps
         step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
@@ -321,7 +327,7 @@ def main():
                 "config": config, "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": prior_host.numel() * 4,
                         "d2h_bytes_per_step": B * H * D * 4, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "loop_ms_per_step": loop_ms_mean, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "engine": {"calls": runtime.STATS["engine_calls"], "fallbacks": runtime.STATS["fallbacks"]}}
         print(json.dumps(line), flush=True)
     if world > 1:

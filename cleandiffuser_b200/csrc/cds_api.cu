@@ -210,6 +210,10 @@ struct cds_plan {
   cudaStream_t cap_stream = nullptr;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
+  // the same program unrolled `multi` times in ONE graph (CDS_GRAPH_ITERS, default 10): fewer graph launches per run
+  int multi = 0;
+  cudaGraph_t graph_multi = nullptr;
+  cudaGraphExec_t exec_multi = nullptr;
 };
 
 extern "C" {
@@ -248,6 +252,8 @@ int cds_plan_destroy(cds_plan* p) {
   cudaSetDevice(p->device);
   if (p->exec) cudaGraphExecDestroy(p->exec);
   if (p->graph) cudaGraphDestroy(p->graph);
+  if (p->exec_multi) cudaGraphExecDestroy(p->exec_multi);
+  if (p->graph_multi) cudaGraphDestroy(p->graph_multi);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   if (p->d_iter) cudaFree(p->d_iter);
   delete p;
@@ -356,12 +362,28 @@ int cds_plan_run(cds_plan* p, int32_t first, int32_t count, void* stream, int32_
     if (rc != CDS_OK) return rc;
     if (e != cudaSuccess) return fail(CDS_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
     CDS_CUDA(cudaGraphInstantiate(&p->exec, p->graph, 0));
+    const char* gi = getenv("CDS_GRAPH_ITERS");
+    p->multi = gi ? atoi(gi) : 10;
+    if (p->multi > 1 && p->multi <= p->n_iters) {
+      CDS_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+      int rc2 = CDS_OK;
+      for (int k = 0; k < p->multi && rc2 == CDS_OK; ++k) rc2 = enqueue_iteration(p, p->cap_stream);
+      cudaError_t e2 = cudaStreamEndCapture(p->cap_stream, &p->graph_multi);
+      if (rc2 != CDS_OK) return rc2;
+      if (e2 != cudaSuccess) return fail(CDS_ERR_CUDA, "graph capture (x%d) failed: %s", p->multi, cudaGetErrorString(e2));
+      CDS_CUDA(cudaGraphInstantiate(&p->exec_multi, p->graph_multi, 0));
+    } else {
+      p->multi = 0;
+    }
   }
   cds::set_iter_kernel<<<1, 1, 0, st>>>(p->d_iter, first);
   CDS_CUDA(cudaGetLastError());
   { int rc = enqueue_once(p, st); if (rc != CDS_OK) return rc; }
   for (int i = 0; i < count; ++i) {
-    if (use_graph) {
+    if (use_graph && p->exec_multi && count - i >= p->multi) {
+      CDS_CUDA(cudaGraphLaunch(p->exec_multi, st));
+      i += p->multi - 1;
+    } else if (use_graph) {
       CDS_CUDA(cudaGraphLaunch(p->exec, st));
     } else {
       int rc = enqueue_iteration(p, st);

@@ -39,6 +39,14 @@ struct ConvPsParams {
   long long* trace;
 };
 
+// 16 epilogue warps (TMEM lane quarter = warp % 4, column slice = (warp / 4) % 2, position half = warp / 8), TMA producer
+// (warp 16), MMA issuer / TMEM owner (warp 17).  The epilogue is MUFU/FMA-throughput work: 4 warps per scheduler overlap the
+// two pipes far better than 2.
+constexpr int kPsEpiWarps = 16;
+constexpr int kPsEpiThreads = kPsEpiWarps * 32;
+constexpr int kPsThreads = kPsEpiThreads + 64;
+constexpr int kPsWarpTma = kPsEpiWarps, kPsWarpMma = kPsEpiWarps + 1;
+
 template <int KC, int N, int P, bool HAS_RES>
 struct ConvPsCfg {
   static constexpr int kTapsMax = 5;
@@ -54,7 +62,7 @@ struct ConvPsCfg {
 };
 
 template <int KC, int N, int P, bool HAS_RES>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kPsThreads, 1)
 conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ iter_ptr) {
   using Cfg = ConvPsCfg<KC, N, P, HAS_RES>;
   constexpr int kStages = Cfg::kStages;
@@ -65,6 +73,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
   __shared__ uint32_t tmem_base_holder;
   // per-column constants: 0 bias  1 GN gamma  2 GN beta  3 additive time row  4 shortcut bias
   __shared__ __align__(16) float s_col[5][N];
+  __shared__ float2 s_part[2][2][128];             // GroupNorm partial (sum, sum of squares) [position half][column slice][trajectory]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -84,19 +93,19 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
     ptx::mbar_init(&tmem_full_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == kPsWarpTma && lane == 0) {
     ptx::prefetch_tensormap(&p.tm_a);
     ptx::prefetch_tensormap(&p.tm_b);
     if (HAS_RES) { ptx::prefetch_tensormap(&p.tm_a2); ptx::prefetch_tensormap(&p.tm_b2); }
   }
-  if (warp == 9) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
+  if (warp == kPsWarpMma) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_holder;
   if (threadIdx.x == 0) { CDS_TRACE(2, clock64()); ptx::grid_dep_launch_dependents(); }
 
-  if (warp == 8) {
+  if (warp == kPsWarpTma) {
     // ===================================== TMA producer =====================================
     if (ptx::elect_one()) {
       auto load_w = [&](int c, int s) {               // weight tiles of chunk c into stage s
@@ -133,7 +142,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
       }
       CDS_TRACE(8, clock64());
     }
-  } else if (warp == 9) {
+  } else if (warp == kPsWarpMma) {
     // ===================================== MMA issuer =====================================
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, N);
@@ -187,17 +196,20 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
       ptx::umma_commit(&tmem_full_bar);
     }
   } else {
-    // ===================================== epilogue (warps 0..7) =====================================
-    // thread = one trajectory (TMEM lane) x NH = N/2 columns = ONE GroupNorm group, all P positions.
+    // ===================================== epilogue (warps 0..15) =====================================
+    // thread = one trajectory (TMEM lane) x NH = N/2 columns (ONE GroupNorm group) x PH = P/2 positions; the two position
+    // halves of a group exchange their partial statistics through shared memory.
     ptx::grid_dep_wait();
     const int iter = iter_ptr ? *iter_ptr : 0;
     constexpr int NH = N / 2;
     static_assert(NH == 16 || NH == 32, "one GroupNorm group of 16 or 32 channels per epilogue column slice");
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, half = (warp >> 2) & 1, ph = warp >> 3;
+    constexpr int PH = P / 2;
+    const int lp0 = ph * PH;                          // first position of this thread
     {
       const float* bstep = p.bias.step ? p.bias.step + (int64_t)iter * p.bias.step_stride : nullptr;
       const float* hstep = p.shift.step ? p.shift.step + (int64_t)iter * p.shift.step_stride : nullptr;
-      for (int n = threadIdx.x; n < N; n += kTcEpiThreads) {
+      for (int n = threadIdx.x; n < N; n += kPsEpiThreads) {
         const int c = n_off + n;
         s_col[0][n] = bstep ? __ldg(bstep + c) : 0.f;
         s_col[1][n] = __ldg(p.gn_gamma + c);
@@ -205,7 +217,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
         s_col[3][n] = hstep ? __ldg(hstep + c) : 0.f;
         s_col[4][n] = (HAS_RES && p.res_bias) ? __ldg(p.res_bias + c) : 0.f;
       }
-      ptx::named_bar_sync(1, kTcEpiThreads);
+      ptx::named_bar_sync(1, kPsEpiThreads);
     }
     const int b = b0 + 32 * q + lane;
     const bool valid = b < p.batch;
@@ -222,7 +234,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
     float s1 = 0.f, s2 = 0.f;
     {
       float va[NH], vb[NH];
-      ptx::tmem_ld_nowait<NH>(t_row + (uint32_t)col0, va);
+      ptx::tmem_ld_nowait<NH>(t_row + (uint32_t)(lp0 * N + col0), va);
       auto accumulate = [&](const float (&v)[NH]) {
 #pragma unroll
         for (int k = 0; k < NH / 4; ++k) {
@@ -232,17 +244,19 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
           s2 = fmaf(x0, x0, s2); s2 = fmaf(x1, x1, s2); s2 = fmaf(x2, x2, s2); s2 = fmaf(x3, x3, s2);
         }
       };
-      static_assert(P % 2 == 0, "pass 1 ping-pongs two register buffers");
-#pragma unroll
-      for (int lp = 0; lp < P; lp += 2) {
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_nowait<NH>(t_row + (uint32_t)((lp + 1) * N + col0), vb);
-        accumulate(va);
-        ptx::tmem_ld_wait();
-        if (lp + 2 < P) ptx::tmem_ld_nowait<NH>(t_row + (uint32_t)((lp + 2) * N + col0), va);
-        accumulate(vb);
-      }
+      static_assert(PH == 2, "pass 1 ping-pongs two register buffers over the two positions of this thread");
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_nowait<NH>(t_row + (uint32_t)((lp0 + 1) * N + col0), vb);
+      accumulate(va);
+      ptx::tmem_ld_wait();
+      accumulate(vb);
     }
+    // first chunk of pass 2 is already on its way while the halves exchange their partial sums
+    float vbuf[2][16];
+    ptx::tmem_ld_nowait<16>(t_row + (uint32_t)(lp0 * N + col0), vbuf[0]);
+    s_part[ph][half][32 * q + lane] = make_float2(s1, s2);
+    ptx::named_bar_sync(1, kPsEpiThreads);
+    { const float2 o2 = s_part[ph ^ 1][half][32 * q + lane]; s1 += o2.x; s2 += o2.y; }
     const float inv_cnt = 1.f / (float)(P * NH);
     const float mean = s1 * inv_cnt;
     const float ga = rsqrt_ftz(fmaxf(fmaf(s2, inv_cnt, -mean * mean), 0.f) + p.gn_eps);
@@ -250,12 +264,10 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
 
     // ---- pass 2: normalise, affine, Mish, additive terms, store; 16-column chunks, the next chunk's TMEM read in flight
     const bool add_res = p.res != nullptr;
-    constexpr int kChunks = P * (NH / 16);
-    float vbuf[2][16];
-    ptx::tmem_ld_nowait<16>(t_row + (uint32_t)col0, vbuf[0]);
+    constexpr int kChunks = PH * (NH / 16);
 #pragma unroll
     for (int ci = 0; ci < kChunks; ++ci) {
-      const int lp = ci / (NH / 16), h = ci % (NH / 16);
+      const int lp = lp0 + ci / (NH / 16), h = ci % (NH / 16);
       const int n0 = col0 + 16 * h;                   // CTA-tile column
       float (&v)[16] = vbuf[ci & 1];
       float addv[16];
@@ -272,7 +284,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
       }
       ptx::tmem_ld_wait();
       if (ci + 1 < kChunks) {
-        const int lp1 = (ci + 1) / (NH / 16), h1 = (ci + 1) % (NH / 16);
+        const int lp1 = lp0 + (ci + 1) / (NH / 16), h1 = (ci + 1) % (NH / 16);
         ptx::tmem_ld_nowait<16>(t_row + (uint32_t)(lp1 * N + col0 + 16 * h1), vbuf[(ci + 1) & 1]);
       }
       if constexpr (HAS_RES) {
@@ -305,7 +317,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
   }
 
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kPsWarpMma) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
@@ -408,7 +420,7 @@ cudaError_t conv_ps_launch_t(const ConvPsLaunch& L, const int* iter_ptr, cudaStr
   ConvPsParams prm = L.prm;
   prm.trace = conv_tc_trace_hook((int)L.grid.x);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = L.grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
+  cfg.gridDim = L.grid; cfg.blockDim = dim3(kPsThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;

@@ -33,7 +33,7 @@ namespace cds {
 constexpr int kTcThreads = 320;   // warps 0-7 epilogue (TMEM lane quarter = warp % 4, column slice = warp / 4),
                                   // warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer
 constexpr int kTcEpiThreads = 256;
-constexpr int kTcMaxStages = 4;
+constexpr int kTcMaxStages = 10;
 
 struct ConvTcParams {
   CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
@@ -158,7 +158,13 @@ struct ConvTcCfg {
   static constexpr int kABytes = 128 * kRowBytes;
   static constexpr int kBBytes = N * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (KC == 64 && (N == 64 || N == 128)) ? 3 : 4;   // 3 stages let 2-3 such CTAs share an SM
+  // Operand ring: as deep as the shared memory of the designed residency allows (2 CTAs/SM: ~100 KB each; 1 CTA/SM: ~200 KB),
+  // at least 3, at most kTcMaxStages.  A tile is taps x C_in/KC k-blocks (5..20): only a ring that holds more than one tile
+  // lets the TMA producer run ahead of the tile whose accumulator the epilogue is still draining -- with 4 stages and
+  // 5 k-blocks per tile every tile paid one exposed L2 round trip (~1 us) on the narrow layers.
+  static constexpr int kRingBudget = (N <= 128 ? 100 : 200) * 1024;
+  static constexpr int kStagesFit = kRingBudget / kStageBytes;
+  static constexpr int kStages = kStagesFit < 3 ? 3 : (kStagesFit > kTcMaxStages ? kTcMaxStages : kStagesFit);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
   static constexpr int kCols = N * SPLIT;                                 // columns of the whole layer
   static constexpr int kColsPerTile = N * (HAS_RES ? 2 : 1);             // main (+ shortcut) accumulator

@@ -33,12 +33,11 @@ __device__ __forceinline__ UpdRow load_upd_row(const cds_update_op& p, int iter)
   return r;
 }
 
-// One element of the reverse-process update: i = flat index into x (batch*row), `pr` = the network prediction for it (after
-// the CFG combine).  Reads x (+noise, prior, xhat_prev), writes x (+xhat_prev, +the bf16 channel-padded copy).
-// e = i % row (index inside the trajectory), cast_off = element offset in x_cast (ignored when x_cast is NULL)
-__device__ __forceinline__ void solver_update_element(const cds_update_op& p, const UpdRow& r, int64_t i, int e, int64_t cast_off,
-                                                      float pr) {
-  const float x = p.x[i];
+// One element of the reverse-process update as a pure function of its operands: e = index inside the trajectory, x = x_t,
+// pr = the network prediction (after the CFG combine), z = this iteration's noise draw (ignored without a slot), prior = the
+// conditioning value under the mask, hist = previous x0 estimate of the 2M solvers; *xhat_out receives the new estimate.
+__device__ __forceinline__ float solver_update_value(const cds_update_op& p, const UpdRow& r, int e, float x, float pr, float z,
+                                                     float prior, float hist, float* xhat_out) {
   const float alpha = r.alpha, sigma = r.sigma;
   float out;
   if (r.kind == CDS_UPD_CM) {
@@ -63,20 +62,31 @@ __device__ __forceinline__ void solver_update_element(const cds_update_op& p, co
 
     if (r.kind == CDS_UPD_DDPM) {
       out = add_(mul_(r.k0, sub_(x, mul_(sigma, eps))), mul_(r.k1, eps));
-      if (r.noise) out = add_(out, mul_(r.k2, r.noise[i]));
+      if (r.noise) out = add_(out, mul_(r.k2, z));
     } else if (r.kind == CDS_UPD_DDIM) {
       out = add_(mul_(r.k0, div_(sub_(x, mul_(sigma, eps)), alpha)), mul_(r.k1, eps));
     } else {
       float target;
       if (r.kind == CDS_UPD_EPS) target = eps;
-      else if (r.kind == CDS_UPD_X2M) target = sub_(mul_(r.k3, xhat), mul_(r.k4, p.xhat_prev[i]));
+      else if (r.kind == CDS_UPD_X2M) target = sub_(mul_(r.k3, xhat), mul_(r.k4, hist));
       else target = xhat;
       out = sub_(mul_(r.k0, x), mul_(r.k1, target));
-      if (r.noise) out = add_(out, mul_(r.k2, r.noise[i]));
-      if (p.xhat_prev) p.xhat_prev[i] = xhat;
+      if (r.noise) out = add_(out, mul_(r.k2, z));
+      if (xhat_out) *xhat_out = xhat;
     }
   }
-  if (p.mask) { const float m = p.mask[e]; out = add_(mul_(out, 1.f - m), mul_(p.prior[i], m)); }
+  if (p.mask) { const float m = p.mask[e]; out = add_(mul_(out, 1.f - m), mul_(prior, m)); }
+  return out;
+}
+
+// ... applied to element i of x in place: i = flat index into x (batch*row), e = i % row, cast_off = element offset in x_cast
+// (ignored when x_cast is NULL).  Reads x (+noise, prior, xhat_prev), writes x (+xhat_prev, +the bf16 channel-padded copy).
+__device__ __forceinline__ void solver_update_element(const cds_update_op& p, const UpdRow& r, int64_t i, int e, int64_t cast_off,
+                                                      float pr) {
+  float xhat = 0.f;
+  const float out = solver_update_value(p, r, e, p.x[i], pr, r.noise ? r.noise[i] : 0.f, p.mask ? p.prior[i] : 0.f,
+                                        (p.xhat_prev && r.kind == CDS_UPD_X2M) ? p.xhat_prev[i] : 0.f, &xhat);
+  if (p.xhat_prev && r.kind != CDS_UPD_CM && r.kind != CDS_UPD_DDPM && r.kind != CDS_UPD_DDIM) p.xhat_prev[i] = xhat;
   p.x[i] = out;
   if (p.x_cast) reinterpret_cast<__nv_bfloat16*>(p.x_cast)[cast_off] = __float2bfloat16_rn(out);
 }
@@ -92,25 +102,56 @@ __device__ __forceinline__ void advance_iteration_when_last(int* advance, int it
 }
 
 // reads x, pred (+pred_uncond, noise, prior, xhat_prev), writes x (+xhat_prev): 12..28 B / element
+// One thread = 4 consecutive elements (float4 traffic on x / pred / noise / prior) when the row length allows it.
 static __global__ void __launch_bounds__(256) solver_update_kernel(const cds_update_op p, const int* iter_ptr, int* advance) {
   const int iter = *iter_ptr;
   const UpdRow r = load_upd_row(p, iter);
   const int64_t total = (int64_t)p.batch * p.row;
   const bool small = total < (int64_t)0x7fffffff;            // 32-bit index arithmetic (64-bit divisions are ~20x dearer)
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    float pr = p.pred[i];
-    if (p.pred_uncond) pr = add_(mul_(p.w_cfg, pr), mul_(p.w_uncond, p.pred_uncond[i]));
-    int e;
-    int64_t cast_off = 0;
-    if (small) {
-      const unsigned iu = (unsigned)i;
-      e = (int)(iu % (unsigned)p.row);
-      if (p.x_cast) { const unsigned rr = iu / (unsigned)p.cast_C_in; cast_off = (int64_t)rr * p.cast_C_out + (iu - rr * (unsigned)p.cast_C_in); }
-    } else {
-      e = (int)(i % p.row);
-      if (p.x_cast) { const int64_t rr = i / p.cast_C_in; cast_off = rr * p.cast_C_out + (i - rr * p.cast_C_in); }
+  const bool vec4 = small && (p.row % 4 == 0) && !p.pred_uncond && !p.xhat_prev &&
+                    (((uintptr_t)p.x | (uintptr_t)p.pred | (uintptr_t)p.prior | (uintptr_t)r.noise) % 16 == 0);
+  if (vec4) {
+    const unsigned n4 = (unsigned)(total / 4);
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += gridDim.x * blockDim.x) {
+      const unsigned i0 = 4u * g;
+      const int e0 = (int)(i0 % (unsigned)p.row);
+      const float4 xv = reinterpret_cast<const float4*>(p.x)[g];
+      const float4 pv = reinterpret_cast<const float4*>(p.pred)[g];
+      float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), qv = zv;
+      if (r.noise) zv = reinterpret_cast<const float4*>(r.noise)[g];
+      if (p.mask) qv = reinterpret_cast<const float4*>(p.prior)[g];
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ps[4] = {pv.x, pv.y, pv.z, pv.w};
+      const float zs[4] = {zv.x, zv.y, zv.z, zv.w}, qs[4] = {qv.x, qv.y, qv.z, qv.w};
+      float os[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) os[k] = solver_update_value(p, r, e0 + k, xs[k], ps[k], zs[k], qs[k], 0.f, nullptr);
+      reinterpret_cast<float4*>(p.x)[g] = make_float4(os[0], os[1], os[2], os[3]);
+      if (p.x_cast) {
+        unsigned rr = i0 / (unsigned)p.cast_C_in, c = i0 - rr * (unsigned)p.cast_C_in;
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.x_cast);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          dst[(int64_t)rr * p.cast_C_out + c] = __float2bfloat16_rn(os[k]);
+          if (++c == (unsigned)p.cast_C_in) { c = 0; ++rr; }
+        }
+      }
     }
-    solver_update_element(p, r, i, e, cast_off, pr);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      float pr = p.pred[i];
+      if (p.pred_uncond) pr = add_(mul_(p.w_cfg, pr), mul_(p.w_uncond, p.pred_uncond[i]));
+      int e;
+      int64_t cast_off = 0;
+      if (small) {
+        const unsigned iu = (unsigned)i;
+        e = (int)(iu % (unsigned)p.row);
+        if (p.x_cast) { const unsigned rr = iu / (unsigned)p.cast_C_in; cast_off = (int64_t)rr * p.cast_C_out + (iu - rr * (unsigned)p.cast_C_in); }
+      } else {
+        e = (int)(i % p.row);
+        if (p.x_cast) { const int64_t rr = i / p.cast_C_in; cast_off = rr * p.cast_C_out + (i - rr * p.cast_C_in); }
+      }
+      solver_update_element(p, r, i, e, cast_off, pr);
+    }
   }
   if (advance) advance_iteration_when_last(advance, iter);
 }

@@ -353,6 +353,7 @@ def lower_janner(p: Program, net: JannerUNet1d, x: View, horizon: int, has_cond:
             e = net.map_noise(ctx.t_all)
             e = net.map_emb(e + torch.zeros_like(e))
             table.copy_(torch.cat([b.emb_mlp(e) for b in blocks], dim=1))
+        fill.time_only = True      # depends on (weights, timesteps) only: the runtime skips it when neither changed
         p.per_call.append(fill)
         film = {id(b): dict(shift=_vec(step=table, col=o)) for b, o in zip(blocks, offs)}
     else:

@@ -133,3 +133,27 @@ def test_lowered_sampler_bf16(golden, name, monkeypatch):
     # outliers, same mean
     max_tol = 1.5 if "cfg2branch" in name else 0.2
     assert err.max() < max_tol and err.mean() < 0.02, (float(err.max()), float(err.mean()))
+
+
+def test_table_caches_follow_the_request(golden):
+    """Coefficient / time-conditioning tables are cached per (solver, schedule) and per (weights, timesteps): repeated and
+    interleaved requests on ONE agent must still give each request's own result."""
+    name = "disc_dup_ddpm_x0"
+    spec = cases.sampler_cases()[name]
+    agent, inp, kw = build_agent(spec)
+    want = golden["samplers"][name + "/x0"]
+
+    def run(**over):
+        tape = NoiseTape(tape_of(golden["samplers"], name))
+        with tape.active(), torch.no_grad():
+            return agent.sample(inp["prior"], **{**kw, **over})[0].numpy()
+
+    a0 = run()
+    np.testing.assert_allclose(a0, want, rtol=1e-4, atol=3e-4)
+    b = run(solver="ddim")                               # other solver, same plan shapes -> other table
+    assert np.abs(b - a0).max() > 1e-3
+    np.testing.assert_array_equal(run(), a0)             # cached table + cached time rows
+    with torch.no_grad():                                # weights change -> time rows must be rebuilt
+        for p in agent.model_ema["diffusion"].parameters():
+            p.mul_(1.01)
+    assert np.abs(run() - a0).max() > 1e-4
