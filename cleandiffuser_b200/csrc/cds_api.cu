@@ -39,6 +39,7 @@ struct Step {            // one validated operator + its kernel choice
   int conv_bn = 0;
   bool tc = false;       // tensor-core conv: tensor maps + launch geometry prepared at append time
   cds::ConvTcLaunch tcl;
+  int branch = 0;        // (op.flags >> 8) & 0xff
   bool skip = false;     // solver update that was fused into the preceding conv's epilogue (finalize)
   bool ps = false;       // ... served by the position-sliced kernel (short sequences, conv_ps.cuh)
   cds::ConvPsLaunch psl;
@@ -52,6 +53,7 @@ int elementwise_grid(int64_t total, int sm_count) {
 
 int validate(const cds_op& op, Step* out) {
   out->op = op;
+  out->branch = (op.flags & CDS_OPF_BRANCH_MASK) >> CDS_OPF_BRANCH_SHIFT;
   switch (op.kind) {
     case CDS_OP_CONV: {
       const cds_conv_op& c = op.u.conv;
@@ -212,6 +214,12 @@ struct cds_plan {
   cudaGraphExec_t exec = nullptr;
   // the same program unrolled `multi` times in ONE graph (CDS_GRAPH_ITERS, default 10): fewer graph launches per run
   int multi = 0;
+  // parallel branches (cds_op.flags bits 8..15): branch b > 0 is enqueued on side[b-1], forked from / joined to the caller's
+  // stream with events once per iteration
+  int n_branches = 1;
+  std::vector<cudaStream_t> side;
+  cudaEvent_t ev_fork = nullptr;
+  std::vector<cudaEvent_t> ev_join;
   cudaGraph_t graph_multi = nullptr;
   cudaGraphExec_t exec_multi = nullptr;
 };
@@ -255,6 +263,9 @@ int cds_plan_destroy(cds_plan* p) {
   if (p->exec_multi) cudaGraphExecDestroy(p->exec_multi);
   if (p->graph_multi) cudaGraphDestroy(p->graph_multi);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+  for (cudaStream_t s : p->side) cudaStreamDestroy(s);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  for (cudaEvent_t e : p->ev_join) cudaEventDestroy(e);
   if (p->d_iter) cudaFree(p->d_iter);
   delete p;
   return CDS_OK;
@@ -285,12 +296,24 @@ int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
   CDS_CUDA(cudaMemset(p->d_iter, 0, 2 * sizeof(int)));
   CDS_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
   p->n_iters = n_iters;
+  for (const Step& s : p->steps) if (s.branch + 1 > p->n_branches) p->n_branches = s.branch + 1;
+  if (p->n_branches > 1) {
+    CDS_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    for (int b = 1; b < p->n_branches; ++b) {
+      cudaStream_t s; cudaEvent_t e;
+      CDS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+      CDS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      p->side.push_back(s); p->ev_join.push_back(e);
+    }
+    // the branches share the machine: one CTA per SM and kernel, so that kernels of different branches co-reside
+    for (Step& s : p->steps) if (s.tc && !s.ps) s.tcl.max_ctas_per_sm = 1;
+  }
   // peephole: [tensor-core narrow output head, fp32 dense out] -> [solver update reading it as its only prediction, last
   // operator of the iteration]: the update moves into the head's epilogue (no prediction round trip, one launch less)
   // OPT-IN (CDS_FUSE_UPDATE=1): measured slower on B200 than the separate streaming kernel (cfg2: 64 us vs 19 + 21 us) --
   // the update's IEEE divisions serialise behind the head's tile loop on 296 CTAs instead of filling the machine.
   const char* fuse_env = getenv("CDS_FUSE_UPDATE");
-  if (fuse_env && fuse_env[0] == '1') {
+  if (fuse_env && fuse_env[0] == '1' && p->n_branches == 1) {
     int last = -1, prev = -1;
     for (int i = 0; i < (int)p->steps.size(); ++i)
       if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) { prev = last; last = i; }
@@ -316,6 +339,7 @@ int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
 // the iteration counter is advanced by the program's last operator when that is a solver update (fused), else by a
 // one-thread kernel
 static bool advance_fused(const cds_plan* p) {
+  if (p->n_branches > 1) return false;             // several updates per iteration: a one-thread kernel advances after the join
   for (int i = (int)p->steps.size() - 1; i >= 0; --i)
     if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) return p->steps[i].op.kind == CDS_OP_UPDATE;   // also when that update is `skip`
   return false;
@@ -332,13 +356,39 @@ static int enqueue_once(cds_plan* p, cudaStream_t st) {
 
 static int enqueue_iteration(cds_plan* p, cudaStream_t st) {
   const bool fused = advance_fused(p);
-  int last = -1;
-  for (int i = 0; i < (int)p->steps.size(); ++i) if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) last = i;
-  for (int i = 0; i < (int)p->steps.size(); ++i) {
-    const Step& s = p->steps[i];
-    if ((s.op.flags & CDS_OPF_ONCE) || s.skip) continue;      // a skipped update runs (and advances) inside the head's epilogue
-    int rc = launch(s, p->d_iter, p->sm_count, st, (fused && i == last) ? p->d_iter : nullptr);
-    if (rc != CDS_OK) return rc;
+  if (p->n_branches == 1) {
+    int last = -1;
+    for (int i = 0; i < (int)p->steps.size(); ++i) if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) last = i;
+    for (int i = 0; i < (int)p->steps.size(); ++i) {
+      const Step& s = p->steps[i];
+      if ((s.op.flags & CDS_OPF_ONCE) || s.skip) continue;      // a skipped update runs (and advances) inside the head's epilogue
+      int rc = launch(s, p->d_iter, p->sm_count, st, (fused && i == last) ? p->d_iter : nullptr);
+      if (rc != CDS_OK) return rc;
+    }
+  } else {
+    // fork: every side stream waits for the caller's stream; launch the branches round-robin (so that direct launches
+    // interleave like the graph branches do); join: the caller's stream waits for every side stream
+    CDS_CUDA(cudaEventRecord(p->ev_fork, st));
+    for (cudaStream_t s : p->side) CDS_CUDA(cudaStreamWaitEvent(s, p->ev_fork, 0));
+    std::vector<std::vector<int>> per(p->n_branches);
+    for (int i = 0; i < (int)p->steps.size(); ++i) {
+      const Step& s = p->steps[i];
+      if (!(s.op.flags & CDS_OPF_ONCE) && !s.skip) per[s.branch].push_back(i);
+    }
+    for (size_t k = 0;; ++k) {
+      bool any = false;
+      for (int b = 0; b < p->n_branches; ++b) {
+        if (k >= per[b].size()) continue;
+        any = true;
+        int rc = launch(p->steps[per[b][k]], p->d_iter, p->sm_count, b == 0 ? st : p->side[b - 1], nullptr);
+        if (rc != CDS_OK) return rc;
+      }
+      if (!any) break;
+    }
+    for (int b = 1; b < p->n_branches; ++b) {
+      CDS_CUDA(cudaEventRecord(p->ev_join[b - 1], p->side[b - 1]));
+      CDS_CUDA(cudaStreamWaitEvent(st, p->ev_join[b - 1], 0));
+    }
   }
   if (!fused) {
     cds::advance_iter_kernel<<<1, 1, 0, st>>>(p->d_iter);

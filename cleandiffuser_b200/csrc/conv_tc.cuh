@@ -171,7 +171,9 @@ struct ConvTcCfg {
   static constexpr int kAccBufs = 2 * kColsPerTile <= 512 ? 2 : 1;       // double-buffered when TMEM allows
   static constexpr uint32_t kTmemCols = (kAccBufs * kColsPerTile) < 32 ? 32 : (kAccBufs * kColsPerTile);
   static constexpr int kEpiSplit = N >= 32 ? 2 : 1;     // epilogue warps per TMEM lane quarter (column split)
-  static constexpr int kMinBlocks = N <= 128 ? 2 : 1;   // 102 registers per thread: the epilogue keeps 16-32 columns live
+  // designed CTAs per SM: 2 (102 registers per thread: the epilogue keeps 16-32 columns live).  3 CTAs (68 registers) were
+  // measured on the narrow tiles: the spills cost more than the extra residency buys (471 -> 490 us per iteration).
+  static constexpr int kMinBlocks = N <= 128 ? 2 : 1;
 };
 
 // W consecutive activations (bf16 or fp32) <-> registers, 8/16-byte vector accesses
@@ -700,6 +702,7 @@ inline bool conv_tc_eligible(const cds_conv_op& c) {
 struct ConvTcLaunch {
   ConvTcParams prm;
   int kc = 0, n = 0, split = 1;   // n = CTA tile width, split*n = layer width
+  int max_ctas_per_sm = 0;        // > 0: use at most this many CTAs per SM (plans with parallel branches share the SMs)
   bool has_res = false;
   dim3 grid;
 };
@@ -709,6 +712,8 @@ struct ConvTcLaunch {
 inline int conv_tc_pick_split(const cds_conv_op& c, int n_total, int m_tiles) {
   if (c.phases != 1 || n_total < 64) return 1;
   if (n_total >= 128) return 2;
+  const char* e = getenv("CDS_TC_SPLIT64");
+  if (e && e[0] == '1') return 2;                    // experiment: C_out = 64 always as two N = 32 CTAs (3 CTAs/SM residency)
   return m_tiles < 296 ? 2 : 1;
 }
 
@@ -775,6 +780,7 @@ cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStr
   using Cfg = ConvTcCfg<KC, N, HAS_RES, SPLIT>;
   static bool attr = false;
   static int resident = 0;                   // CTAs of this instantiation that fit on the device at once
+  static int sm_count = 0;
   static bool pdl = true;                    // chain with programmatic dependent launch (CDS_PDL=0: plain stream order)
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -799,11 +805,14 @@ cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStr
       fprintf(stderr, "[cds] conv_tc<%d,%d,%d,%d>: designed %d CTA/SM (tmem %d, smem %d), smem %d B, %d stages\n", KC, N,
               (int)HAS_RES, SPLIT, want, by_tmem, by_smem, Cfg::kSmemBytes, Cfg::kStages);
     resident = want * sms;
+    sm_count = sms;
     const char* pdl_env = getenv("CDS_PDL");
     pdl = !(pdl_env && pdl_env[0] == '0');
     attr = true;
   }
-  dim3 grid(L.grid.x < (unsigned)resident ? L.grid.x : (unsigned)resident);
+  unsigned cap = (unsigned)resident;
+  if (L.max_ctas_per_sm > 0 && (unsigned)(L.max_ctas_per_sm * sm_count) < cap) cap = (unsigned)(L.max_ctas_per_sm * sm_count);
+  dim3 grid(L.grid.x < cap ? L.grid.x : cap);
   ConvTcParams prm = L.prm;
   prm.trace = conv_tc_trace_hook((int)grid.x);
   cudaLaunchConfig_t cfg = {};

@@ -29,7 +29,8 @@ __device__ __forceinline__ UpdRow load_upd_row(const cds_update_op& p, int iter)
   r.k0 = row[CDS_ROW_K0]; r.k1 = row[CDS_ROW_K1]; r.k2 = row[CDS_ROW_K2]; r.k3 = row[CDS_ROW_K3]; r.k4 = row[CDS_ROW_K4];
   r.kind = (int)row[CDS_ROW_KIND];
   const int slot = (int)row[CDS_ROW_NOISE] - 1;
-  r.noise = slot >= 0 ? p.noise + (int64_t)slot * p.batch * p.row : nullptr;
+  const int64_t slot_stride = p.noise_slot_stride > 0 ? p.noise_slot_stride : (int64_t)p.batch * p.row;
+  r.noise = slot >= 0 ? p.noise + (int64_t)slot * slot_stride : nullptr;
   return r;
 }
 

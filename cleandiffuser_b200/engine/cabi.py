@@ -10,7 +10,8 @@ import os
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "libcds.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+OPF_BRANCH_SHIFT = 8   # cds_op.flags bits 8..15: branch index (independent chains run on parallel streams)
 OPF_ONCE = 1          # cds_op.flags: run once per plan run (before its first iteration), not in every iteration
 OP_CONV, OP_UPDATE, OP_LNMOD, OP_ATTN, OP_PREP, OP_CAST = range(6)
 ACT_NONE, ACT_MISH, ACT_SILU, ACT_GELU_TANH, ACT_MISH_SILU = range(5)
@@ -69,7 +70,8 @@ class UpdateOp(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("row", C.c_int32), ("x", _f32p),
         ("pred", _f32p), ("pred_uncond", _f32p), ("w_cfg", C.c_float), ("w_uncond", C.c_float),
-        ("noise", _f32p), ("prior", _f32p), ("mask", _f32p), ("x_min", _f32p), ("x_max", _f32p),
+        ("noise", _f32p), ("noise_slot_stride", C.c_int64), ("prior", _f32p), ("mask", _f32p), ("x_min", _f32p),
+        ("x_max", _f32p),
         ("xhat_prev", _f32p), ("coef", _f32p), ("predict_noise", C.c_int32), ("final_clip", C.c_int32),
         ("x_cast", C.c_void_p), ("cast_C_in", C.c_int32), ("cast_C_out", C.c_int32),
     ]

@@ -64,6 +64,19 @@ class _Ctx:
         self.t_all, self.cond_rows = t_all, cond_rows
 
 
+def _n_branches(batch, row, consistency):
+    """Independent sub-batches ("branches") whose kernel chains run on parallel streams: while one chain sits at a kernel
+    boundary (drain, dependency latency, ramp-up: ~3 us of every ~12 us layer) the other chain's kernel keeps the SMs busy.
+    CDS_BRANCHES sets the count (default 2), CDS_BRANCH_MIN_BATCH the smallest sub-batch worth a branch (default 1024)."""
+    want = int(os.environ.get("CDS_BRANCHES", "2"))
+    min_sub = int(os.environ.get("CDS_BRANCH_MIN_BATCH", "1024"))
+    if consistency:
+        return 1
+    while want > 1 and (batch % want != 0 or batch // want < min_sub or (batch // want * row) % 4 != 0):
+        want -= 1
+    return max(want, 1)
+
+
 class SamplerPlan:
     """Everything resident on the device for one (model, batch, x_shape, option set)."""
 
@@ -74,65 +87,84 @@ class SamplerPlan:
         for s in x_shape:
             row *= s
         self.row, self.n_iters = row, n_iters
-        rows = batch * (2 if cfg_mode == 2 else 1)
         self.cfg_mode = cfg_mode
-        p = Program(device, rows, n_iters, math)
-        self.program = p
-        self.x = p.buf(batch, *x_shape)
-        self.prior = p.buf(batch, *x_shape) if has_mask else None
-        self.mask = p.buf(row) if has_mask else None
-        self.x_min = p.buf(row) if has_min else None
-        self.x_max = p.buf(row) if has_max else None
-        self.coef = p.buf(n_iters, cabi.ROW_FLOATS)
-        self.noise = p.buf(max(n_slots, 1), batch, row) if n_slots > 0 else None
-        self.xhat_prev = p.buf(batch, row) if keep_history else None
+        K = _n_branches(batch, row, consistency)
+        self.n_branches = K
+        root = Program(device, batch * (2 if cfg_mode == 2 else 1), n_iters, math)     # owns the shared buffers
+        self.program = root
+        self.x = root.buf(batch, *x_shape)
+        self.prior = root.buf(batch, *x_shape) if has_mask else None
+        self.mask = root.buf(row) if has_mask else None
+        self.x_min = root.buf(row) if has_min else None
+        self.x_max = root.buf(row) if has_max else None
+        self.coef = root.buf(n_iters, cabi.ROW_FLOATS)
+        self.noise = root.buf(max(n_slots, 1), batch, row) if n_slots > 0 else None
+        self.xhat_prev = root.buf(batch, row) if keep_history else None
+        if consistency:
+            self.xin = root.buf(batch, *x_shape)
 
         L = x_shape[0] if len(x_shape) == 2 else 1
         Cn = x_shape[-1]
-        xin = self.x
-        if consistency:
-            self.xin = p.buf(batch, *x_shape)
-            op = cabi.Op()
-            op.kind = cabi.OP_PREP
-            q = op.u.prep
-            q.batch, q.row, q.x, q.xin, q.coef = batch, row, self.x.data_ptr(), self.xin.data_ptr(), self.coef.data_ptr()
-            q.noise = self.noise.data_ptr() if self.noise is not None else None
-            p.ops.append(op)
-            xin = self.xin
-        xview = View(xin, L, Cn)
-        pred = lower_denoiser(p, net, xview, x_shape, cfg_mode != 0, batch if cfg_mode == 2 else 0)
+        self._update_ops = []
+        self._fillers = []                 # (per-call table filler, sub-batch slice)
+        sub = batch // K
+        for k in range(K):
+            off = k * sub                  # first trajectory of this branch
+            sl = slice(off, off + sub)
+            p = root if K == 1 else Program(device, sub * (2 if cfg_mode == 2 else 1), n_iters, math)
+            n_before = len(p.ops)
+            fo = 4 * off * row             # byte offset of the branch inside the (batch, row) fp32 buffers
+            xin_ptr_t, xin_off = self.x, off * row
+            if consistency:
+                op = cabi.Op()
+                op.kind = cabi.OP_PREP
+                q = op.u.prep
+                q.batch, q.row, q.x, q.xin, q.coef = sub, row, self.x.data_ptr() + fo, self.xin.data_ptr() + fo, self.coef.data_ptr()
+                q.noise = self.noise.data_ptr() if self.noise is not None else None
+                p.ops.append(op)
+                xin_ptr_t = self.xin
+            xview = View(xin_ptr_t, L, Cn, offset=xin_off)
+            pred = lower_denoiser(p, net, xview, x_shape, cfg_mode != 0, sub if cfg_mode == 2 else 0)
 
-        op = cabi.Op()
-        op.kind = cabi.OP_UPDATE
-        u = op.u.update
-        u.batch, u.row, u.x = batch, row, self.x.data_ptr()
-        u.pred = pred.ptr
-        if cfg_mode == 2:
-            u.pred_uncond = pred.ptr + 4 * batch * row
-        u.noise = self.noise.data_ptr() if self.noise is not None else None
-        u.prior = self.prior.data_ptr() if has_mask else None
-        u.mask = self.mask.data_ptr() if has_mask else None
-        u.x_min = self.x_min.data_ptr() if has_min else None
-        u.x_max = self.x_max.data_ptr() if has_max else None
-        u.xhat_prev = self.xhat_prev.data_ptr() if keep_history else None
-        u.coef = self.coef.data_ptr()
-        u.predict_noise = 1 if predict_noise else 0
-        u.final_clip = 1 if consistency else 0
-        # tensor-core UNets read x_t through a channel-padded bf16 copy (CDS_OP_CAST).  When that cast converts the very
-        # buffer the update writes, the update emits the copy itself and the cast runs only once per sample() call.
-        for cop in p.ops:
-            if cop.kind == cabi.OP_CAST and cop.u.cast.in_ == self.x.data_ptr() and cop.u.cast.batch == batch:
-                cop.flags |= cabi.OPF_ONCE
-                u.x_cast, u.cast_C_in, u.cast_C_out = cop.u.cast.out, cop.u.cast.C_in, cop.u.cast.C_out
-        self._update_op = op
-        p.ops.append(op)
+            op = cabi.Op()
+            op.kind = cabi.OP_UPDATE
+            u = op.u.update
+            u.batch, u.row, u.x = sub, row, self.x.data_ptr() + fo
+            u.pred = pred.ptr
+            if cfg_mode == 2:
+                u.pred_uncond = pred.ptr + 4 * sub * row
+            if self.noise is not None:
+                u.noise, u.noise_slot_stride = self.noise.data_ptr() + fo, batch * row
+            u.prior = self.prior.data_ptr() + fo if has_mask else None
+            u.mask = self.mask.data_ptr() if has_mask else None
+            u.x_min = self.x_min.data_ptr() if has_min else None
+            u.x_max = self.x_max.data_ptr() if has_max else None
+            u.xhat_prev = self.xhat_prev.data_ptr() + fo if keep_history else None
+            u.coef = self.coef.data_ptr()
+            u.predict_noise = 1 if predict_noise else 0
+            u.final_clip = 1 if consistency else 0
+            # tensor-core UNets read x_t through a channel-padded bf16 copy (CDS_OP_CAST).  When that cast converts the very
+            # buffer the update writes, the update emits the copy itself and the cast runs only once per sample() call.
+            for cop in p.ops[n_before:]:
+                if cop.kind == cabi.OP_CAST and cop.u.cast.in_ == self.x.data_ptr() + fo and cop.u.cast.batch == sub:
+                    cop.flags |= cabi.OPF_ONCE
+                    u.x_cast, u.cast_C_in, u.cast_C_out = cop.u.cast.out, cop.u.cast.C_in, cop.u.cast.C_out
+            self._update_ops.append(op)
+            p.ops.append(op)
+            self._fillers += [(fn, sl) for fn in p.per_call]
+            if p is not root:
+                for o in p.ops:
+                    o.flags |= k << cabi.OPF_BRANCH_SHIFT
+                root.ops += p.ops
+                root.keep += p.keep + [p]
+                root.packers += p.packers
 
         self.handle: Optional[cabi.Plan] = None
         self.version = _weights_version(net)
 
     def build(self, w_cfg: float):
-        u = self._update_op.u.update
-        u.w_cfg, u.w_uncond = float(w_cfg), float(1 - w_cfg)
+        for op in self._update_ops:
+            op.u.update.w_cfg, op.u.update.w_uncond = float(w_cfg), float(1 - w_cfg)
         self.w_cfg = w_cfg
         self.handle = _make_handle(self.device, self.program.ops, self.n_iters)
 
@@ -143,14 +175,13 @@ class SamplerPlan:
                 fn()
             self.version = v
 
-    def run(self, t_all, cond_rows, use_graph=True, t_key=None):
+    def run(self, t_all, cond_emb, use_graph=True, t_key=None):
         # table fillers that depend on (weights, timesteps) only are skipped when neither changed since the last call
         fresh = t_key is None or (t_key, self.version) != getattr(self, "_time_tables_key", None)
         with torch.no_grad():
-            ctx = _Ctx(t_all, cond_rows)
-            for fn in self.program.per_call:
+            for fn, sl in self._fillers:             # every branch fills its own tables from its slice of the condition
                 if fresh or not getattr(fn, "time_only", False):
-                    fn(ctx)
+                    fn(_Ctx(t_all, _cond_rows(self.cfg_mode, None if cond_emb is None else cond_emb[sl])))
         self._time_tables_key = (t_key, self.version) if t_key is not None else None
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
         timed = STATS.get("time_loop") and self.device.type == "cuda"
@@ -197,7 +228,7 @@ def _get_plan(agent, key, factory):
 
 
 def _cond_rows(cfg_mode, cond_emb):
-    if cfg_mode == 0:
+    if cfg_mode == 0 or cond_emb is None:
         return None
     c = cond_emb.to(torch.float32)
     return torch.cat([c, torch.zeros_like(c)], 0) if cfg_mode == 2 else c
@@ -281,7 +312,7 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
             plan.noise[k].copy_(torch.randn_like(xt).reshape(batch, -1))
         idx = torch.as_tensor(order, dtype=torch.long)
         t_all = t_cpu[idx].to(device)      # int64 (discrete) or float32 (continuous), one entry per iteration
-    plan.run(t_all, _cond_rows(cfg_mode, cond_emb), use_graph=os.environ.get("CDS_GRAPH", "1") != "0",
+    plan.run(t_all, cond_emb, use_graph=os.environ.get("CDS_GRAPH", "1") != "0",
              t_key=(t_cpu.numpy().tobytes(), tuple(order)))
     STATS["engine_calls"] += 1
     return plan.x.clone()
@@ -348,7 +379,7 @@ def try_sample_consistency(agent, *, model, xt, prior, sigmas, order, cond_emb, 
         for k in range(n_slots):
             plan.noise[k].copy_(torch.randn_like(xt).reshape(batch, -1))
         t_all = table[:, S.R_T].to(device)             # the network sees c_noise = ln(sigma)/4 as its "time"
-    plan.run(t_all, _cond_rows(cfg_mode, cond_emb), use_graph=os.environ.get("CDS_GRAPH", "1") != "0")
+    plan.run(t_all, cond_emb, use_graph=os.environ.get("CDS_GRAPH", "1") != "0")
     STATS["engine_calls"] += 1
     return plan.x.clone()
 

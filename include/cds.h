@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CDS_ABI_VERSION 2
+#define CDS_ABI_VERSION 3
 
 typedef enum cds_status {
   CDS_OK = 0,
@@ -139,7 +139,8 @@ typedef struct cds_update_op {
   int32_t batch, row;
   float* x;
   const float* pred; const float* pred_uncond; float w_cfg; float w_uncond;  /* w and (1-w), both rounded from double by the host */
-  const float* noise;            /* [n_slots][batch][row] pre-drawn N(0,1) */
+  const float* noise;            /* [n_slots][...] pre-drawn N(0,1): slot s of this op's rows starts at noise + s*noise_slot_stride */
+  int64_t noise_slot_stride;     /* floats between slots; 0 = batch*row (the op covers the whole tape) */
   const float* prior; const float* mask;      /* mask: `row` floats or NULL */
   const float* x_min; const float* x_max;     /* `row` floats or NULL */
   float* xhat_prev;              /* (batch,row) history for the 2M solvers or NULL */
@@ -153,7 +154,11 @@ typedef struct cds_update_op {
 } cds_update_op;
 
 /* cds_op.flags */
-enum { CDS_OPF_ONCE = 1 /* run once per cds_plan_run, before its first iteration, instead of in every iteration */ };
+enum { CDS_OPF_ONCE = 1 /* run once per cds_plan_run, before its first iteration, instead of in every iteration */,
+       CDS_OPF_BRANCH_SHIFT = 8, CDS_OPF_BRANCH_MASK = 0xff00
+       /* bits 8..15: branch index.  Operators of one branch run in program order; different branches are independent
+        * chains (disjoint trajectories) that the engine enqueues on parallel streams / parallel graph branches and joins at
+        * the end of every iteration, so that one chain's kernel boundaries overlap with the other chain's kernels. */ };
 
 typedef struct cds_op {
   int32_t kind;                  /* cds_op_kind */

@@ -183,7 +183,8 @@ def run_update(u, it):
         pr = f(u.w_cfg) * pr + f(u.w_uncond) * _arr(u.pred_uncond, (u.batch, u.row), (u.row, 1))
     xmin = _arr(u.x_min, (u.row,), (1,)) if u.x_min else None
     xmax = _arr(u.x_max, (u.row,), (1,)) if u.x_max else None
-    z = _arr(u.noise + 4 * slot * n, (u.batch, u.row), (u.row, 1)) if slot >= 0 else None
+    slot_stride = u.noise_slot_stride if u.noise_slot_stride > 0 else n
+    z = _arr(u.noise + 4 * slot * slot_stride, (u.batch, u.row), (u.row, 1)) if slot >= 0 else None
     if kind == 5:
         out = k0 * x + k1 * pr
         if u.final_clip:

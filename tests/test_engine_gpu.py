@@ -217,3 +217,30 @@ def test_sampler_bf16_tensor_cores_goldens(golden, name, monkeypatch):
         err = np.abs(x0.cpu().numpy() - golden["samplers"][name + "/x0"])
         assert err.max() < 0.2 and err.mean() < 0.02, (name, graph, float(err.max()), float(err.mean()))
     assert torch.equal(outs[0], outs[1])         # graph replay == direct launches
+
+
+@pytest.mark.parametrize("math", ["fp32", "bf16"])
+def test_parallel_branches_give_the_same_bits(math, monkeypatch):
+    """CDS_BRANCHES splits the batch into independent kernel chains on parallel streams / graph branches: trajectories are
+    independent, so the result must equal the single-chain run bit for bit (graph replay and direct launches)."""
+    monkeypatch.setenv("CDS_MATH", math)
+    T, B = 6, 2048
+    outs = {}
+    for branches, graph in (("1", "1"), ("2", "1"), ("2", "0"), ("4", "1")):
+        monkeypatch.setenv("CDS_BRANCHES", branches)
+        monkeypatch.setenv("CDS_BRANCH_MIN_BATCH", "256")
+        monkeypatch.setenv("CDS_GRAPH", graph)
+        agent, sd, mask = _cfg2_agent(T)
+        g = torch.Generator().manual_seed(1)
+        prior = torch.zeros(B, 32, 14)
+        prior[:, 0, :11] = torch.randn(B, 11, generator=g)
+        torch.manual_seed(5)
+        with torch.no_grad():
+            x, _ = agent.sample(prior.to(DEV), solver="ddpm", n_samples=B, sample_steps=T, temperature=0.5)
+        plan = next(iter(agent._engine_plans.values()))
+        assert plan.n_branches == int(branches)
+        outs[(branches, graph)] = x.cpu()
+    ref = outs[("1", "1")]
+    assert torch.isfinite(ref).all()
+    for k, v in outs.items():
+        assert torch.equal(v, ref), k

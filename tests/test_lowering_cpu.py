@@ -157,3 +157,30 @@ def test_table_caches_follow_the_request(golden):
         for p in agent.model_ema["diffusion"].parameters():
             p.mul_(1.01)
     assert np.abs(run() - a0).max() > 1e-4
+
+
+@pytest.mark.parametrize("name,math", [("disc_dup_ddpm_x0", "fp32"), ("cont_cfg2branch_2M", "fp32"), ("cont_ddim_eps", "bf16")])
+def test_lowered_sampler_two_branches(golden, name, math, monkeypatch):
+    """The batch split into two independent operator chains (cds_op.flags branch bits; parallel streams on the GPU): same
+    results, every branch reads/writes its own slice of x_t / noise / prior / condition."""
+    monkeypatch.setenv("CDS_MATH", math)
+    monkeypatch.setenv("CDS_BRANCHES", "2")
+    monkeypatch.setenv("CDS_BRANCH_MIN_BATCH", "1")
+    from cleandiffuser_b200.engine import cabi
+    spec = cases.sampler_cases()[name]
+    agent, inp, kw = build_agent(spec)
+    tape = NoiseTape(tape_of(golden["samplers"], name))
+    with tape.active(), torch.no_grad():
+        x0, _ = agent.sample(inp["prior"], **kw)
+    plan = next(iter(agent._engine_plans.values()))
+    assert plan.n_branches == 2
+    branches = sorted({(op.flags >> cabi.OPF_BRANCH_SHIFT) & 0xff for op in plan.program.ops})
+    assert branches == [0, 1]
+    upd = [op.u.update for op in plan.program.ops if op.kind == cabi.OP_UPDATE]
+    assert len(upd) == 2 and upd[1].x == upd[0].x + 4 * upd[0].batch * upd[0].row
+    want = golden["samplers"][name + "/x0"]
+    if math == "fp32":
+        np.testing.assert_allclose(x0.numpy(), want, rtol=1e-4, atol=3e-4)
+    else:
+        err = np.abs(x0.numpy() - want)
+        assert err.max() < 0.2 and err.mean() < 0.02, (float(err.max()), float(err.mean()))
