@@ -76,7 +76,7 @@ class ClockSampler:
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -88,6 +88,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi needs ~0.5 s before its first line: block until it is sampling (so that the timed region is covered)."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+        return len(self.rows)
+
     def __exit__(self, *a):
         if self.proc is not None:
             self.proc.terminate()
@@ -96,10 +103,11 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, first=0, last=None):
+        """Rows [first, last) = the samples taken while the measured workload was running."""
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[first:last]:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -254,8 +262,24 @@ def main():
         runtime.STATS["time_loop"] = True
         runtime.STATS["loop_events"] = []
         with ClockSampler(local_rank) as clk:
+            clk.wait_first()
+            step_resident()                       # the sampler's first rows already see the GPU under this load
+            torch.cuda.synchronize()
+            row0 = len(clk.rows)
+            runtime.STATS["loop_events"] = []
             ms = timed(step_resident, args.steps)
+            row1 = len(clk.rows)
+            extended = 0
+            t_ext = time.time()
+            while len(clk.rows) - row0 < 5 and time.time() - t_ext < 3.0:    # short timed regions: keep the same load running
+                step_resident()                                               # (un-timed) until a few samples exist
+                torch.cuda.synchronize()
+                extended += 1
+            clocks = clk.summary(row0, None)
+            clocks["samples_inside_timed_region"] = row1 - row0
+            clocks["untimed_steps_of_the_same_load_sampled_after"] = extended
         runtime.STATS["time_loop"] = False
+        runtime.STATS["loop_events"] = runtime.STATS["loop_events"][:args.steps]
         loop_ms = [a.elapsed_time(b) for a, b in runtime.STATS["loop_events"]]
         loop_ms_mean = sum(loop_ms) / max(len(loop_ms), 1)
         log(f"timed: {ms / args.steps:.1f} ms/step; reverse loop alone {loop_ms_mean:.2f} ms "
@@ -269,7 +293,7 @@ def main():
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     hbm_peak, peak_src = peaks()
 
-    # ---- live per-kernel roofline of the dominant kernel family (fused conv GEMM) -----------------------------
+    # ---- live per-kernel roofline of the dominant kernel family (fused conv GEMMs: 40 of the 41 launches of an iteration) --
     roofline = None
     if rank == 0:
         plan = next(iter(agent._engine_plans.values()))
@@ -282,32 +306,50 @@ def main():
         for _ in range(reps):
             for i, v in enumerate(plan.handle.profile(50, stream, len(ops))):
                 per_op[i] += v / reps
+        in_iter = [not (op.flags & 1) for op in ops]                  # CDS_OPF_ONCE operators are not part of the iteration
         conv_ms, conv_bytes, conv_flops, n_conv = 0.0, 0.0, 0.0, 0
-        for op, t_ms in zip(ops, per_op):
-            if op.kind != 0:
+        for op, t_ms, live in zip(ops, per_op, in_iter):
+            if op.kind != 0 or not live:
                 continue
             c = op.u.conv
             n_conv += 1
             conv_ms += t_ms
+            # SURVEY 8(d) canonical accounting: every fused conv reads its input(s) and writes its output once, fp32
             conv_bytes += 4.0 * c.batch * (c.L_in * c.C_in + c.L_out * c.C_out * c.phases
                                            + (c.L_out * c.res_C if c.res_w else 0) + (c.L_out * c.C_out if c.res else 0))
             conv_flops += 2.0 * c.batch * c.L_out * c.C_out * c.phases * (c.taps * c.C_in + (c.res_C if c.res_w else 0))
-        iter_ms = sum(per_op)
+        iter_ms = sum(t for t, live in zip(per_op, in_iter) if live)
         for i, (op, t_ms) in enumerate(zip(ops, per_op)):
             if op.kind == 0:
                 c = op.u.conv
                 log(f"op {i:2d} conv {'tc ' if c.math == 1 else 'f32'} L {c.L_in:3d}->{c.L_out * c.phases:3d} C {c.C_in:4d}->{c.C_out:4d} "
                     f"k{c.taps} s{c.stride} gn{c.groups} res{'W' if c.res_w else ('I' if c.res else '-')}: {t_ms * 1e3:8.1f} us")
             else:
-                log(f"op {i:2d} kind {op.kind}: {t_ms * 1e3:8.1f} us")
+                log(f"op {i:2d} kind {op.kind}{' (once per call)' if op.flags & 1 else ''}: {t_ms * 1e3:8.1f} us")
         log(f"iteration total {iter_ms * 1e3:.1f} us (direct launches, event-bracketed)")
-        achieved = conv_bytes / (conv_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "conv_gemm (fused Conv1d+GN+Mish+FiLM+residual), all launches of one iteration",
+        share = conv_ms / iter_ms
+        # the timed region replays CUDA graphs (no per-launch events possible inside): the conv kernels' time per iteration is
+        # the event-timed loop time x their share of the iteration (share from the event-bracketed direct launches above;
+        # the ncu launch list under profiles/ gives the same share)
+        loop_iter_ms = loop_ms_mean / S_STEPS
+        conv_ms_graph = loop_iter_ms * share
+        achieved = conv_bytes / (conv_ms_graph * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("conv_dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": "conv_tc_kernel / conv_ps_kernel (fused Conv1d+GroupNorm+Mish+FiLM+residual), all "
+                                              f"{n_conv} conv launches of one reverse iteration",
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "peak_source": peak_src, "traffic": None,
-                    "launches_per_iter": n_conv, "avg_launch_us": conv_ms / max(n_conv, 1) * 1e3,
-                    "alg_bytes_per_iter": conv_bytes, "conv_share_of_iter": conv_ms / iter_ms,
-                    "tflops_effective": conv_flops / (conv_ms * 1e-3) / 1e12,
+                    "peak_source": peak_src, "traffic": traffic,
+                    "how": "algorithmic bytes (SURVEY 8d: fp32 in+out of every fused conv) of one iteration / (event-timed graph-replay "
+                           "loop time per iteration x conv share of the iteration)",
+                    "launches_per_iter": n_conv, "avg_launch_us": conv_ms_graph / max(n_conv, 1) * 1e3,
+                    "alg_bytes_per_launch": conv_bytes / max(n_conv, 1), "alg_bytes_per_iter": conv_bytes,
+                    "conv_share_of_iter": share, "tflops_effective": conv_flops / (conv_ms_graph * 1e-3) / 1e12,
+                    "direct_launch": {"avg_launch_us": conv_ms / max(n_conv, 1) * 1e3,
+                                      "achieved": conv_bytes / (conv_ms * 1e-3) / 1e9},
                     "sample_level": {"alg_bytes_per_traj": ALG_BYTES_PER_TRAJ,
                                      "achieved_GBs": ALG_BYTES_PER_TRAJ * value / world / 1e9,
                                      "frac": ALG_BYTES_PER_TRAJ * value / world / 1e9 / hbm_peak}}
@@ -324,7 +366,7 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if args.math == "fp32" else "bf16 operands / f32 accumulate", "data": "synthetic",
-                "config": config, "clocks": clk.summary(),
+                "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": prior_host.numel() * 4,
                         "d2h_bytes_per_step": B * H * D * 4, "ms_per_step": ms_e2e / args.steps},
                 "loop_ms_per_step": loop_ms_mean, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
