@@ -213,6 +213,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     from cleandiffuser_b200.engine import runtime
