@@ -308,45 +308,6 @@ int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
     // the branches share the machine: one CTA per SM and kernel, so that kernels of different branches co-reside
     for (Step& s : p->steps) if (s.tc && !s.ps) s.tcl.max_ctas_per_sm = 1;
   }
-  // chains: consecutive tensor-core convs of one resolution level (same batch, L, width; stride 1) become ONE persistent
-  // launch -- their dependencies are tile-local (conv_tc.cuh, ConvTcChain).  CDS_CHAIN=1 switches it on.
-  {
-    const char* ce = getenv("CDS_CHAIN");
-    const bool chain_on = ce && ce[0] == '1';
-    auto chainable = [](const Step& s) {
-      if (!s.tc || s.ps || s.skip || (s.op.flags & CDS_OPF_ONCE)) return false;
-      const cds_conv_op& c = s.op.u.conv;
-      const int n = cds::conv_tc_width(c);
-      return c.stride == 1 && c.phases == 1 && c.L_in == c.L_out && (n == 32 || n == 64) && c.in_batch_mod == 0 &&
-             c.res_batch_mod == 0 && c.C_in % 32 == 0 && (!c.res_w || c.res_C % 32 == 0);
-    };
-    for (size_t i = 0; chain_on && i < p->steps.size();) {
-      if (!chainable(p->steps[i])) { ++i; continue; }
-      const cds_conv_op& c0 = p->steps[i].op.u.conv;
-      size_t j = i + 1;
-      while (j < p->steps.size() && j - i < (size_t)cds::kTcMaxChain && chainable(p->steps[j]) &&
-             p->steps[j].branch == p->steps[i].branch && p->steps[j].op.u.conv.batch == c0.batch &&
-             p->steps[j].op.u.conv.L_out == c0.L_out && cds::conv_tc_width(p->steps[j].op.u.conv) == cds::conv_tc_width(c0))
-        ++j;
-      if (j - i >= 2) {
-        bool k64 = true, any_res = false;
-        for (size_t k = i; k < j; ++k) {
-          const cds_conv_op& c = p->steps[k].op.u.conv;
-          if (c.C_in % 64 != 0 || (c.res_w && c.res_C % 64 != 0)) k64 = false;
-          if (c.res_w) any_res = true;
-        }
-        bool ok = true;
-        for (size_t k = i; k < j && ok; ++k) ok = cds::conv_tc_prepare(p->steps[k].op.u.conv, &p->steps[k].tcl, k64 ? 64 : 32, 1);
-        if (!ok) return fail(CDS_ERR_CUDA, "conv chain: cuTensorMapEncodeTiled failed");
-        cds::ConvTcLaunch& head = p->steps[i].tcl;
-        head.has_res = any_res;
-        head.n_extra = (int)(j - i - 1);
-        for (size_t k = i + 1; k < j; ++k) { head.extra[k - i - 1] = p->steps[k].tcl.prm; p->steps[k].skip = true; }
-        if (p->n_branches > 1) head.max_ctas_per_sm = 1;
-      }
-      i = j;
-    }
-  }
   // peephole: [tensor-core narrow output head, fp32 dense out] -> [solver update reading it as its only prediction, last
   // operator of the iteration]: the update moves into the head's epilogue (no prediction round trip, one launch less)
   // OPT-IN (CDS_FUSE_UPDATE=1): measured slower on B200 than the separate streaming kernel (cfg2: 64 us vs 19 + 21 us) --

@@ -53,22 +53,12 @@ struct ConvTcParams {
   cds_update_op upd; int upd_on; int* advance;
   long long* trace;               // debug: per-CTA clock64 timeline (kTraceSlots entries per CTA), normally NULL
 };
-// Up to kTcMaxChain same-resolution convs of one level run as ONE persistent kernel: every CTA owns a fixed set of row tiles and
-// walks the operators one after the other over its own tiles.  A conv at a fixed resolution only needs the rows of its own
-// tile (whole trajectories), so the dependencies are CTA-local: no grid-wide barrier, no kernel boundary (drain + dependency
-// latency + ramp, ~3 us each) between the operators; the ring, the TMEM double buffer and the warp roles just keep going.
-constexpr int kTcMaxChain = 4;
-struct ConvTcChain {
-  int n_ops; int pad_;
-  ConvTcParams op[kTcMaxChain];
-};
 constexpr int kTraceSlots = 64;
 // [0] globaltimer at entry  [1] clock at entry  [2] clock after the prologue barrier  [3] clock at exit  [4] globaltimer at exit
 // [5] tiles done by this CTA;  tile t (t < 14): [8+4t] producer issued its last k-block, [9+4t] MMA saw its first operands,
 // [10+4t] epilogue saw the accumulator, [11+4t] epilogue done
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define CDS_TRACE(slot, val) do { if (p.trace) p.trace[(int64_t)blockIdx.x * kTraceSlots + (slot)] = (val); } while (0)
-#define CDS_TRACE0(slot, val) do { if (p0.trace) p0.trace[(int64_t)blockIdx.x * kTraceSlots + (slot)] = (val); } while (0)
 
 // MUFU approximations with flush-to-zero: ONE instruction each (the non-ftz forms expand into range fix-ups)
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -187,20 +177,19 @@ struct ConvTcCfg {
 };
 
 // W consecutive activations (bf16 or fp32) <-> registers, 8/16-byte vector accesses
-// (plain coherent loads, not ld.global.nc: inside a chain the residual rows were written earlier by this very kernel)
 template <int W>
 __device__ __forceinline__ void load_row(const void* base, int64_t off, int dtype, float (&r)[W]) {
   if (dtype == CDS_BF16) {
     const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + off;
     if constexpr (W == 4) {
-      uint2 u = *reinterpret_cast<const uint2*>(p);
+      uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
       float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
       r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
     } else {
 #pragma unroll
       for (int k = 0; k < W / 8; ++k) {
-        uint4 u = reinterpret_cast<const uint4*>(p)[k];
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + k);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); r[8 * k + 2 * j] = f.x; r[8 * k + 2 * j + 1] = f.y; }
@@ -209,7 +198,7 @@ __device__ __forceinline__ void load_row(const void* base, int64_t off, int dtyp
   } else {
     const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
 #pragma unroll
-    for (int k = 0; k < W / 4; ++k) { float4 f = p[k]; r[4 * k] = f.x; r[4 * k + 1] = f.y; r[4 * k + 2] = f.z; r[4 * k + 3] = f.w; }
+    for (int k = 0; k < W / 4; ++k) { float4 f = __ldg(p + k); r[4 * k] = f.x; r[4 * k + 1] = f.y; r[4 * k + 2] = f.z; r[4 * k + 3] = f.w; }
   }
 }
 template <int W>
@@ -240,9 +229,8 @@ __device__ __forceinline__ void store_row(void* base, int64_t off, int dtype, co
 
 template <int KC, int N, bool HAS_RES, int SPLIT>
 __global__ void __launch_bounds__(kTcThreads, ConvTcCfg<KC, N, HAS_RES, SPLIT>::kMinBlocks)
-conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict__ iter_ptr) {
+conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ iter_ptr) {
   using Cfg = ConvTcCfg<KC, N, HAS_RES, SPLIT>;
-  const ConvTcParams& p0 = chain.op[0];            // geometry shared by the whole chain: batch, L, tiles
   constexpr int kTcStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kTcMaxStages];
@@ -255,37 +243,33 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
   __shared__ __align__(16) float s_col[6][Cfg::kCols];
   // fused solver update (narrow head only): the tile's predictions, re-read with a coalesced element <-> thread mapping
   __shared__ float s_pred[N == 16 ? 128 * 16 : 1];
-  __shared__ uint32_t done_cnt;                    // chains: (operator, tile) items this CTA's epilogue has finished and published
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // operand ring, 1024-byte aligned (swizzle atoms)
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
 
-  const int T = 128 >> p0.log2L;                      // trajectories per tile
-  if (threadIdx.x == 0) { CDS_TRACE0(0, gtimer()); CDS_TRACE0(1, clock64()); }
-  // row tiles owned by this CTA (the same set for every operator of the chain)
-  const int my_tiles = (int)blockIdx.x < p0.num_tiles ? (p0.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int T = 128 >> p.log2L;                       // trajectories per tile
+  if (threadIdx.x == 0) { CDS_TRACE(0, gtimer()); CDS_TRACE(1, clock64()); }
+  const int n_kb_main = p.taps * p.kchunks;
+  const int n_kb = n_kb_main + (HAS_RES ? p.kchunks2 : 0);
 
   if (threadIdx.x == 0) {
-    done_cnt = 0;
     for (int s = 0; s < kTcStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], kTcEpiThreads / 32); }
     ptx::fence_barrier_init();
   }
   if (warp == 8 && lane == 0) {
-    for (int o = 0; o < chain.n_ops; ++o) {
-      ptx::prefetch_tensormap(&chain.op[o].tm_a);
-      ptx::prefetch_tensormap(&chain.op[o].tm_b);
-      if (HAS_RES && chain.op[o].kchunks2 > 0) { ptx::prefetch_tensormap(&chain.op[o].tm_a2); ptx::prefetch_tensormap(&chain.op[o].tm_b2); }
-    }
+    ptx::prefetch_tensormap(&p.tm_a);
+    ptx::prefetch_tensormap(&p.tm_b);
+    if (HAS_RES) { ptx::prefetch_tensormap(&p.tm_a2); ptx::prefetch_tensormap(&p.tm_b2); }
   }
   if (warp == 9) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_holder;
-  if (threadIdx.x == 0) CDS_TRACE0(2, clock64());
+  if (threadIdx.x == 0) CDS_TRACE(2, clock64());
   // programmatic dependent launch: the next kernel of the stream may start its own prologue and weight prefetch now; it
   // blocks in grid_dep_wait() until this grid has completed before it touches anything a predecessor wrote
   if (threadIdx.x == 0) ptx::grid_dep_launch_dependents();
@@ -296,15 +280,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
       // Weights do not depend on the previous kernel: arm the first ring fill and fetch its W tiles BEFORE waiting for the
       // predecessor grid (programmatic dependent launch); the activation tiles of those stages follow after the wait.
       int pre = 0;
-      if (my_tiles > 0) {
-        const ConvTcParams& p = p0;
-        const int n_kb_main = p.taps * p.kchunks, n_kb = n_kb_main + p.kchunks2;
+      if (blockIdx.x < p.num_tiles) {
         const int n_off0 = (blockIdx.x % SPLIT) * N;
         pre = n_kb < kTcStages ? n_kb : kTcStages;
         for (int kb = 0; kb < pre; ++kb) {
           uint8_t* sb = smem_al + kb * Cfg::kStageBytes + Cfg::kABytes;
           ptx::mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
-          if (kb < n_kb_main) {
+          if (!HAS_RES || kb < n_kb_main) {
             const int tap = kb / p.kchunks, ck = kb - tap * p.kchunks;
             ptx::tma_load_2d(sb, &p.tm_b, &full_bar[kb], ck * KC, tap * p.C_out * p.phases + n_off0);
           } else {
@@ -313,19 +295,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
         }
       }
       ptx::grid_dep_wait();
-      int ring = 0;                                   // k-blocks issued so far (smem ring position, across tiles and operators)
-      for (int o = 0; o < chain.n_ops; ++o) {
-      const ConvTcParams& p = chain.op[o];
-      const int n_kb_main = p.taps * p.kchunks, n_kb = n_kb_main + p.kchunks2;     // kchunks2 = 0 without a shortcut conv
-      int t_i = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t_i) {
-      if (o > 0) {
-        // the previous operator's output rows of THIS tile were written by this CTA's epilogue: wait until it has published
-        // them (items complete in (operator, tile) order), then order the generic-proxy writes before the TMA reads
-        const uint32_t need = (uint32_t)((o - 1) * my_tiles + t_i + 1);
-        while (ptx::ld_acquire_cta_shared(&done_cnt) < need) { }
-        ptx::fence_proxy_async_all();
-      }
+      int ring = 0;                                   // k-blocks issued so far (smem ring position, across tiles)
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int b0 = (tile / SPLIT) * T;
       const int n_off = (tile % SPLIT) * N;           // first layer column of this CTA tile
       const int a_b0 = p.in_batch_mod > 0 ? b0 % p.in_batch_mod : b0;
@@ -340,7 +311,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
         }
         uint8_t* sa = smem_al + s * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
-        if (kb < n_kb_main) {
+        if (!HAS_RES || kb < n_kb_main) {
           const int tap = kb / p.kchunks, ck = kb - tap * p.kchunks;
           ptx::tma_load_3d(sa, &p.tm_a, &full_bar[s], ck * KC, tap - p.pad, a_b0);
           if (!w_done) ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KC, tap * p.C_out * p.phases + n_off);
@@ -350,8 +321,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
           if (!w_done) ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], ck * KC, n_off);
         }
       }
-      if (o == 0 && t_i < 14) CDS_TRACE0(8 + 4 * t_i, clock64());
-      }
+      { const int t_i = (tile - blockIdx.x) / gridDim.x; if (t_i < 14) CDS_TRACE(8 + 4 * t_i, clock64()); }
       }
     }
   } else if (warp == 9) {
@@ -359,9 +329,6 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, N);
       int ring = 0, it = 0;
-      for (int o = 0; o < chain.n_ops; ++o) {
-      const ConvTcParams& p = chain.op[o];
-      const int n_kb_main = p.taps * p.kchunks, n_kb = n_kb_main + p.kchunks2;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it % Cfg::kAccBufs;
       const uint32_t use = (uint32_t)(it / Cfg::kAccBufs);            // how often this buffer has been used before
@@ -373,11 +340,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
         const uint32_t ph = (ring / kTcStages) & 1;
         ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after_sync();
-        if (kb == 0 && it < 14) CDS_TRACE0(9 + 4 * it, clock64());
+        if (kb == 0 && it < 14) CDS_TRACE(9 + 4 * it, clock64());
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
         const uint64_t da = ptx::make_kmajor_desc<Cfg::kRowBytes>(sa);
         const uint64_t db = ptx::make_kmajor_desc<Cfg::kRowBytes>(sa + Cfg::kABytes);
-        const bool second = kb >= n_kb_main;
+        const bool second = HAS_RES && kb >= n_kb_main;
         const uint32_t d_addr = acc_base + (second ? (uint32_t)N : 0u);
         const bool first_of_acc = second ? (kb == n_kb_main) : (kb == 0);
 #pragma unroll
@@ -388,7 +355,6 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
         ptx::umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
       }
       ptx::umma_commit(&tmem_full_bar[buf]);      // this tile's accumulators complete
-      }
       }
     }
   } else {
@@ -402,15 +368,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
     const int q = warp & 3;                         // TMEM lane quarter this warp may touch
     const int half = warp >> 2;                     // which slice of the N columns this warp handles
     const bool active = half < EW;                  // warp-uniform (N = 16: only warps 0..3 work)
-    const int m = 32 * q + lane;
-    const int col0 = half * NH;
-    int it = 0;                                     // tiles done so far (TMEM buffer alternation), across operators
-    for (int o = 0; o < chain.n_ops; ++o) {
-    const ConvTcParams& p = chain.op[o];
     const int n_real = p.C_out * p.phases;          // < N only for narrow heads (C_out <= 16)
 
-    // ---- stage the per-column constants (overlaps with the TMA/MMA main loop; every epilogue warp has left the previous
-    // operator's last tile: the per-tile publish barrier below, or this being the first operator)
+    // ---- stage the per-column constants (overlaps with the TMA/MMA main loop)
     {
       const float* bstep = p.bias.step ? p.bias.step + (int64_t)iter * p.bias.step_stride : nullptr;
       const float* sstep = p.scale.step ? p.scale.step + (int64_t)iter * p.scale.step_stride : nullptr;
@@ -440,6 +400,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
 
     UpdRow upd_row = {};
     if (N == 16 && p.upd_on) upd_row = load_upd_row(p.upd, iter);
+    const int m = 32 * q + lane;
+    const int col0 = half * NH;
+    int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
     const int buf = it % Cfg::kAccBufs;
     const uint32_t use = (uint32_t)(it / Cfg::kAccBufs);
@@ -456,7 +419,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
 
     ptx::mbar_wait(&tmem_full_bar[buf], use & 1);
     ptx::tc_fence_after_sync();
-    if (threadIdx.x == 0 && it < 14) CDS_TRACE0(10 + 4 * it, clock64());
+    if (threadIdx.x == 0 && it < 14) CDS_TRACE(10 + 4 * it, clock64());
 
     // ---- 16 finished pre-activation columns (y) -> activation, FiLM, residual(s), store.  n0 = CTA-tile column.
     // FILM: 0 none, 1 additive per-iteration row (staged in smem), 2 anything (scale and/or per-trajectory rows)
@@ -484,7 +447,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
 #pragma unroll
         for (int j = 0; j < 16; ++j) addv[j] += resv[j];
       }
-      if (HAS_RES && p.kchunks2 > 0) {
+      if constexpr (HAS_RES) {
         float r2[16];
         ptx::tmem_ld<16>(t_row + (uint32_t)(N + n0), r2);
         const float4* rb4 = reinterpret_cast<const float4*>(&s_col[5][ng0]);
@@ -647,19 +610,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
       }
       ptx::named_bar_sync(1, kTcEpiThreads);
     }
-    if (chain.n_ops > 1) {
-      // publish this (operator, tile): the rows just stored are the next operator's input for the same tile.  Every thread
-      // makes its global stores visible (device scope) and orders them before later async-proxy (TMA) reads, the epilogue
-      // warps meet, one thread bumps the counter the TMA producer polls.
-      __threadfence();
-      ptx::fence_proxy_async_all();
-      ptx::named_bar_sync(1, kTcEpiThreads);
-      if (threadIdx.x == 0) ptx::red_release_cta_shared_add(&done_cnt, 1u);
-    }
-    if (threadIdx.x == 0 && it < 14) CDS_TRACE0(11 + 4 * it, clock64());
+    if (threadIdx.x == 0 && it < 14) CDS_TRACE(11 + 4 * it, clock64());
     }   // tile loop
-    }   // operator loop
-    if (threadIdx.x == 0) CDS_TRACE0(5, (long long)it);
+    if (threadIdx.x == 0) CDS_TRACE(5, (long long)it);
   }
 
   __syncthreads();
@@ -667,8 +620,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcChain chain, const int* __restrict_
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
-  if (N == 16 && p0.upd_on && p0.advance) advance_iteration_when_last(p0.advance, iter_ptr ? *iter_ptr : 0);
-  if (threadIdx.x == 0) { CDS_TRACE0(3, clock64()); CDS_TRACE0(4, gtimer()); }
+  if (N == 16 && p.upd_on && p.advance) advance_iteration_when_last(p.advance, iter_ptr ? *iter_ptr : 0);
+  if (threadIdx.x == 0) { CDS_TRACE(3, clock64()); CDS_TRACE(4, gtimer()); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -750,8 +703,6 @@ struct ConvTcLaunch {
   ConvTcParams prm;
   int kc = 0, n = 0, split = 1;   // n = CTA tile width, split*n = layer width
   int max_ctas_per_sm = 0;        // > 0: use at most this many CTAs per SM (plans with parallel branches share the SMs)
-  int n_extra = 0;                // operators chained behind this one in the same launch (ConvTcChain)
-  ConvTcParams extra[kTcMaxChain - 1];
   bool has_res = false;
   dim3 grid;
 };
@@ -766,18 +717,17 @@ inline int conv_tc_pick_split(const cds_conv_op& c, int n_total, int m_tiles) {
   return m_tiles < 296 ? 2 : 1;
 }
 
-inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out, int force_kc = 0, int force_split = 0) {
+inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
   ConvTcLaunch& L = *out;
   memset(&L.prm, 0, sizeof(L.prm));
-  L.n_extra = 0;
-  const int kc = force_kc > 0 ? force_kc : conv_tc_pick_kc(c);
+  const int kc = conv_tc_pick_kc(c);
   ConvTcParams& p = L.prm;
   const int Lp = c.L_out, T = 128 / Lp;
   const int64_t rows = (int64_t)c.batch * Lp;
   const int m_tiles = (int)((rows + 127) / 128);
   const int n_total = conv_tc_width(c);
   L.kc = kc; L.has_res = c.res_w != nullptr;
-  L.split = force_split > 0 ? force_split : conv_tc_pick_split(c, n_total, m_tiles);
+  L.split = conv_tc_pick_split(c, n_total, m_tiles);
   L.n = n_total / L.split;
   const uint64_t in_b = c.in_batch_mod > 0 ? (uint64_t)c.in_batch_mod : (uint64_t)c.batch;
   {
@@ -863,11 +813,8 @@ cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStr
   unsigned cap = (unsigned)resident;
   if (L.max_ctas_per_sm > 0 && (unsigned)(L.max_ctas_per_sm * sm_count) < cap) cap = (unsigned)(L.max_ctas_per_sm * sm_count);
   dim3 grid(L.grid.x < cap ? L.grid.x : cap);
-  ConvTcChain prm;
-  prm.n_ops = 1 + L.n_extra; prm.pad_ = 0;
-  prm.op[0] = L.prm;
-  for (int k = 0; k < L.n_extra; ++k) prm.op[k + 1] = L.extra[k];
-  prm.op[0].trace = conv_tc_trace_hook((int)grid.x);
+  ConvTcParams prm = L.prm;
+  prm.trace = conv_tc_trace_hook((int)grid.x);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
   cudaLaunchAttribute at[1];

@@ -153,18 +153,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// generic-proxy writes (st.global / st.shared) -> later async-proxy accesses (TMA): all state spaces
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// CTA-scope release / acquire on a shared-memory word (epilogue -> TMA producer hand-off inside one CTA)
-__device__ __forceinline__ void red_release_cta_shared_add(uint32_t* addr, uint32_t v) {
-  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(addr)), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_cta_shared(const uint32_t* addr) {
-  uint32_t v;
-  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(addr)) : "memory");
-  return v;
-}
-
 // named barrier among a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
