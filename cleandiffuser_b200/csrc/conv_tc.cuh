@@ -403,7 +403,129 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     const int m = 32 * q + lane;
     const int col0 = half * NH;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+
+    // ---- fast lane: the UNet block conv (GroupNorm + Mish, optional additive time row, optional identity residual / shortcut
+    // accumulator, bf16 in and out, every column real).  The narrow tiles run close to the ISSUE limit (4 epilogue warps per
+    // scheduler at ~0.2 IPC each), so instructions per tile are what counts: the option dispatch happens ONCE per kernel (the
+    // tile loop lives inside the specialisation), addresses are strength-reduced to one multiply-add per tile, dtypes are fixed.
+    const bool fast_ok = N >= 32 && has_gn && p.act == CDS_ACT_MISH && film != 2 && p.phases == 1 && io_vec &&
+                         p.out_dtype == CDS_BF16 && (!add_res || p.res_dtype == CDS_BF16) && p.res_batch_mod == 0;
+    auto fast_tiles = [&](auto film_tag, auto res_tag) {
+      constexpr bool SHIFT = decltype(film_tag)::value == 1;
+      constexpr bool RES = decltype(res_tag)::value;
+      constexpr int CPG = Cfg::kCols / 8;
+      constexpr int WC = CPG > 16 ? CPG : 16;
+      constexpr int GPC = WC / CPG;
+      const int T_ = 128 >> p.log2L;
+      const int tb = m >> p.log2L, l = m & (p.L - 1);              // trajectory inside the tile / position: tile-invariant
+      const float inv_cnt = 1.f / (float)(p.L * CPG);
+      const float eps = p.gn_eps;
+      const int L_ = p.L, log2L_ = p.log2L, batch_ = p.batch;
+      __nv_bfloat16* const out_l = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)l * p.out_lstride;
+      const __nv_bfloat16* const res_l = RES ? reinterpret_cast<const __nv_bfloat16*>(p.res) + (int64_t)l * p.res_lstride : nullptr;
+      const int64_t out_bs = p.out_bstride, res_bs = p.res_bstride;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it % Cfg::kAccBufs;
+        const uint32_t use = (uint32_t)(it / Cfg::kAccBufs);
+        const int n_off = (tile % SPLIT) * N;
+        const int b = (tile / SPLIT) * T_ + tb;
+        const bool valid = b < batch_;
+        const uint32_t t_row = t_lane + (uint32_t)(buf * Cfg::kColsPerTile);
+        __nv_bfloat16* const out_row = out_l + (int64_t)b * out_bs + n_off;
+        const __nv_bfloat16* const res_row_p = RES ? res_l + (int64_t)b * res_bs + n_off : nullptr;
+        ptx::mbar_wait(&tmem_full_bar[buf], use & 1);
+        ptx::tc_fence_after_sync();
+        if (threadIdx.x == 0 && it < 14) CDS_TRACE(10 + 4 * it, clock64());
+#pragma unroll 1
+        for (int ch = 0; ch < NH / WC; ++ch) {
+          const int n0 = col0 + ch * WC;                            // CTA-tile column
+          const float* const cb = &s_col[0][n_off + n0];            // staged constants of these columns (row stride kCols)
+          float v[WC];
+          ptx::tmem_ld<WC>(t_row + (uint32_t)n0, v);
+          float s1[GPC], s2[GPC], ga[GPC], gc[GPC];
+#pragma unroll
+          for (int g = 0; g < GPC; ++g) { s1[g] = 0.f; s2[g] = 0.f; }
+#pragma unroll
+          for (int k = 0; k < WC / 4; ++k) {
+            const float4 bb = reinterpret_cast<const float4*>(cb)[k];
+            const int g = (4 * k) / CPG;
+            const float x0 = (v[4 * k] += bb.x), x1 = (v[4 * k + 1] += bb.y), x2 = (v[4 * k + 2] += bb.z), x3 = (v[4 * k + 3] += bb.w);
+            s1[g] += (x0 + x1) + (x2 + x3);
+            s2[g] = fmaf(x0, x0, s2[g]); s2[g] = fmaf(x1, x1, s2[g]); s2[g] = fmaf(x2, x2, s2[g]); s2[g] = fmaf(x3, x3, s2[g]);
+          }
+          gn_coeffs<GPC>(s1, s2, L_, log2L_, lane, inv_cnt, eps, ga, gc);
+#pragma unroll
+          for (int h = 0; h < WC / 16; ++h) {
+            float addv[16];
+            if constexpr (SHIFT) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 sft = reinterpret_cast<const float4*>(cb + 4 * Cfg::kCols + 16 * h)[k];
+                addv[4 * k] = sft.x; addv[4 * k + 1] = sft.y; addv[4 * k + 2] = sft.z; addv[4 * k + 3] = sft.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) addv[j] = 0.f;
+            }
+            if constexpr (RES) {
+              uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
+              if (valid) { const uint4* rp = reinterpret_cast<const uint4*>(res_row_p + n0 + 16 * h); u0 = rp[0]; u1 = rp[1]; }
+              const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {                           // bf16 pair -> two fp32: shift / mask, no cvt
+                addv[2 * j] += __uint_as_float(w[j] << 16);
+                addv[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+              }
+            }
+            if constexpr (HAS_RES) {
+              float r2[16];
+              ptx::tmem_ld<16>(t_row + (uint32_t)(N + n0 + 16 * h), r2);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 rb = reinterpret_cast<const float4*>(cb + 5 * Cfg::kCols + 16 * h)[k];
+                addv[4 * k] += r2[4 * k] + rb.x; addv[4 * k + 1] += r2[4 * k + 1] + rb.y;
+                addv[4 * k + 2] += r2[4 * k + 2] + rb.z; addv[4 * k + 3] += r2[4 * k + 3] + rb.w;
+              }
+            }
+            uint32_t packed[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 gm = reinterpret_cast<const float4*>(cb + 1 * Cfg::kCols + 16 * h)[k];
+              const float4 be = reinterpret_cast<const float4*>(cb + 2 * Cfg::kCols + 16 * h)[k];
+              const int g = (16 * h + 4 * k) / CPG;
+              const float o0 = mish_fma(fmaf(fmaf(v[16 * h + 4 * k + 0], ga[g], gc[g]), gm.x, be.x), addv[4 * k + 0]);
+              const float o1 = mish_fma(fmaf(fmaf(v[16 * h + 4 * k + 1], ga[g], gc[g]), gm.y, be.y), addv[4 * k + 1]);
+              const float o2 = mish_fma(fmaf(fmaf(v[16 * h + 4 * k + 2], ga[g], gc[g]), gm.z, be.z), addv[4 * k + 2]);
+              const float o3 = mish_fma(fmaf(fmaf(v[16 * h + 4 * k + 3], ga[g], gc[g]), gm.w, be.w), addv[4 * k + 3]);
+              __nv_bfloat162 p01 = __floats2bfloat162_rn(o0, o1), p23 = __floats2bfloat162_rn(o2, o3);
+              packed[2 * k] = *reinterpret_cast<uint32_t*>(&p01);
+              packed[2 * k + 1] = *reinterpret_cast<uint32_t*>(&p23);
+            }
+            if (valid) {
+              uint4* op = reinterpret_cast<uint4*>(out_row + n0 + 16 * h);
+              op[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+              op[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+          }
+        }
+        // hand the accumulator buffer back to the MMA warp (one arrival per epilogue warp)
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+        if (threadIdx.x == 0 && it < 14) CDS_TRACE(11 + 4 * it, clock64());
+      }
+    };
+    if constexpr (N >= 32) {
+      if (fast_ok) {
+        using T1 = std::integral_constant<int, 1>;
+        using T0 = std::integral_constant<int, 0>;
+        if (film == 1) { if (add_res) fast_tiles(T1{}, std::true_type{}); else fast_tiles(T1{}, std::false_type{}); }
+        else { if (add_res) fast_tiles(T0{}, std::true_type{}); else fast_tiles(T0{}, std::false_type{}); }
+      }
+    }
+    // generic lane (everything else; a no-op after the fast lane: `it` then already counts all of this CTA's tiles)
+    for (int tile = blockIdx.x + it * (int)gridDim.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
     const int buf = it % Cfg::kAccBufs;
     const uint32_t use = (uint32_t)(it / Cfg::kAccBufs);
     const int64_t row = (int64_t)(tile / SPLIT) * 128 + m;
