@@ -12,7 +12,7 @@ timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpur
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "[bench reference] exit $?"; head -c 400 gpurun_out/bench_reference.json; echo
 if [ -z "$SKIP_NCU" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
-     -s ${NCU_SKIP:-250} -c ${NCU_COUNT:-130} --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+     -s ${NCU_SKIP:-1000} -c ${NCU_COUNT:-130} --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   echo "[ncu launch list] exit $?"
   NCU_KERNEL='conv_(tc|ps)_kernel' NCU_SPECS="${NCU_SPECS:-40:1:first,57:1:ps}" bash scripts/ncu_tc.sh > gpurun_out/ncu_full.log 2>&1; echo "[ncu full] exit $?"
   rm -f gpurun_out/*.source.csv
