@@ -308,30 +308,6 @@ int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
     // the branches share the machine: one CTA per SM and kernel, so that kernels of different branches co-reside
     for (Step& s : p->steps) if (s.tc && !s.ps) s.tcl.max_ctas_per_sm = 1;
   }
-  // peephole: [tensor-core narrow output head, fp32 dense out] -> [solver update reading it as its only prediction, last
-  // operator of the iteration]: the update moves into the head's epilogue (no prediction round trip, one launch less)
-  // OPT-IN (CDS_FUSE_UPDATE=1): measured slower on B200 than the separate streaming kernel (cfg2: 64 us vs 19 + 21 us) --
-  // the update's IEEE divisions serialise behind the head's tile loop on 296 CTAs instead of filling the machine.
-  const char* fuse_env = getenv("CDS_FUSE_UPDATE");
-  if (fuse_env && fuse_env[0] == '1' && p->n_branches == 1) {
-    int last = -1, prev = -1;
-    for (int i = 0; i < (int)p->steps.size(); ++i)
-      if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) { prev = last; last = i; }
-    if (last >= 0 && prev >= 0 && p->steps[last].op.kind == CDS_OP_UPDATE && p->steps[prev].op.kind == CDS_OP_CONV &&
-        p->steps[prev].tc && !p->steps[prev].ps && p->steps[prev].tcl.n == 16) {
-      const cds_update_op& u = p->steps[last].op.u.update;
-      const cds_conv_op& c = p->steps[prev].op.u.conv;
-      const bool dense = c.out_dtype == CDS_F32 && c.out_lstride == c.C_out && c.out_bstride == (int64_t)c.L_out * c.C_out;
-      if (dense && u.pred == c.out && !u.pred_uncond && (int64_t)u.batch * u.row == (int64_t)c.batch * c.L_out * c.C_out &&
-          u.row == c.L_out * c.C_out && (!u.x_cast || u.cast_C_in == c.C_out) && !c.res &&
-          c.phases == 1 && c.act == CDS_ACT_NONE && !c.scale.step && !c.scale.sample && !c.shift.step && !c.shift.sample &&
-          !c.bias.sample) {
-        cds::ConvTcParams& prm = p->steps[prev].tcl.prm;
-        prm.upd = u; prm.upd_on = 1; prm.advance = p->d_iter;
-        p->steps[last].skip = true;
-      }
-    }
-  }
   p->finalized = true;
   return CDS_OK;
 }

@@ -25,7 +25,6 @@
 #include <type_traits>
 
 #include "common.cuh"
-#include "elementwise.cuh"
 #include "ptx_sm100.cuh"
 
 namespace cds {
@@ -48,9 +47,6 @@ struct ConvTcParams {
   const void* res; int64_t res_bstride; int res_lstride; int res_batch_mod; int res_dtype;
   const float* res_bias;
   void* out; int64_t out_bstride; int out_lstride; int out_dtype;
-  // solver update fused into the epilogue of the network's narrow output head (upd_on): the prediction never goes to
-  // HBM, x_t is updated in place by the thread that holds the accumulator; `advance` as in solver_update_kernel
-  cds_update_op upd; int upd_on; int* advance;
   long long* trace;               // debug: per-CTA clock64 timeline (kTraceSlots entries per CTA), normally NULL
 };
 constexpr int kTraceSlots = 64;
@@ -241,8 +237,6 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   // per-column constants of the epilogue, staged once per CTA while the main loop runs:
   // 0 bias  1 GN gamma  2 GN beta  3 FiLM scale  4 FiLM shift  5 shortcut bias   (iteration-indexed "step" parts)
   __shared__ __align__(16) float s_col[6][Cfg::kCols];
-  // fused solver update (narrow head only): the tile's predictions, re-read with a coalesced element <-> thread mapping
-  __shared__ float s_pred[N == 16 ? 128 * 16 : 1];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // operand ring, 1024-byte aligned (swizzle atoms)
@@ -398,8 +392,6 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     const bool add_res = p.res != nullptr;
     const int film = (smp || has_scale) ? 2 : (has_shift ? 1 : 0);
 
-    UpdRow upd_row = {};
-    if (N == 16 && p.upd_on) upd_row = load_upd_row(p.upd, iter);
     const int m = 32 * q + lane;
     const int col0 = half * NH;
     int it = 0;
@@ -516,7 +508,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         if (threadIdx.x == 0 && it < 14) CDS_TRACE(11 + 4 * it, clock64());
       }
     };
-    if constexpr (N >= 32) {
+    if constexpr (N >= 32 && Cfg::kCols <= 256) {
       if (fast_ok) {
         using T1 = std::integral_constant<int, 1>;
         using T0 = std::integral_constant<int, 0>;
@@ -608,14 +600,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
           else o[j] = tc_act<ACT>(p.act, yv[YO + j]) + addv[j];
         }
       }
-      if (!valid && !(N == 16 && p.upd_on)) return;
+      if (!valid) return;
       const int64_t oo = (int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + c0;
       if (io_vec) {
         store_row<16>(p.out, oo, p.out_dtype, o);
-      } else if (N == 16 && p.upd_on) {
-        // the head's prediction feeds the solver update (below, after the tile's rows are all staged)
-#pragma unroll
-        for (int j = 0; j < 16; ++j) s_pred[(N == 16 ? m : 0) * 16 + j] = o[j];
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -645,7 +633,47 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     // the whole column slice of this thread for one compile-time (GN, ACT, FILM) combination
     auto run = [&](auto gn_tag, auto act_tag, auto film_tag) {
       constexpr bool GN = decltype(gn_tag)::value;
-      if constexpr (GN && N >= 32) {
+      if constexpr (GN && N >= 32 && (Cfg::kCols / 8) > 32) {
+        // wide layers (C_out = 512 / 1024: ChiUNet1d): a GroupNorm group is 64 / 128 columns -- too many to hold in registers,
+        // so the group is read from TMEM twice: statistics first, then normalise + activation + store, 32 columns at a time
+        constexpr int CPG = Cfg::kCols / 8;
+        constexpr int GPT = NH / CPG;                 // whole groups per thread
+        static_assert(NH % CPG == 0 && GPT >= 1, "a thread's column slice must hold whole GroupNorm groups");
+        const float inv_cnt = 1.f / (float)(p.L * CPG);
+#pragma unroll 1
+        for (int g = 0; g < GPT; ++g) {
+          float s1[1] = {0.f}, s2[1] = {0.f}, ga[1], gc[1];
+#pragma unroll 1
+          for (int ch = 0; ch < CPG / 32; ++ch) {
+            const int n0 = col0 + g * CPG + ch * 32;
+            float v[32];
+            ptx::tmem_ld<32>(t_row + (uint32_t)n0, v);
+            add_bias(std::integral_constant<int, 32>{}, v, n0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s1[0] += v[j]; s2[0] = fmaf(v[j], v[j], s2[0]); }
+          }
+          gn_coeffs<1>(s1, s2, p.L, p.log2L, lane, inv_cnt, p.gn_eps, ga, gc);
+#pragma unroll 1
+          for (int ch = 0; ch < CPG / 32; ++ch) {
+            const int n0 = col0 + g * CPG + ch * 32;
+            float v[32];
+            ptx::tmem_ld<32>(t_row + (uint32_t)n0, v);
+            add_bias(std::integral_constant<int, 32>{}, v, n0);
+            const float4* ga4 = reinterpret_cast<const float4*>(&s_col[1][n_off + n0]);
+            const float4* be4 = reinterpret_cast<const float4*>(&s_col[2][n_off + n0]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 gm = ga4[k], be = be4[k];
+              v[4 * k + 0] = fmaf(fmaf(v[4 * k + 0], ga[0], gc[0]), gm.x, be.x);
+              v[4 * k + 1] = fmaf(fmaf(v[4 * k + 1], ga[0], gc[0]), gm.y, be.y);
+              v[4 * k + 2] = fmaf(fmaf(v[4 * k + 2], ga[0], gc[0]), gm.z, be.z);
+              v[4 * k + 3] = fmaf(fmaf(v[4 * k + 3], ga[0], gc[0]), gm.w, be.w);
+            }
+            post16(act_tag, film_tag, v, std::integral_constant<int, 0>{}, n0);
+            post16(act_tag, film_tag, v, std::integral_constant<int, 16>{}, n0 + 16);
+          }
+        }
+      } else if constexpr (GN && N >= 32) {
         // GroupNorm (8 groups over the layer's kCols columns).  A chunk of WC = max(16, CPG) columns is read from TMEM
         // once and holds GPC = WC / CPG whole groups: per-thread sums over the group's columns, all-reduce over the L
         // lanes (= positions) of the trajectory, then y = ((v - mean) * rstd) * gamma + beta as two FMAs per element.
@@ -718,20 +746,6 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     ptx::tc_fence_before_sync();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
-    if (N == 16 && p.upd_on) {
-      // fused reverse-process update of the tile's 128 rows x C_out elements (contiguous in x_t): all 256 epilogue threads,
-      // consecutive threads <-> consecutive elements
-      ptx::named_bar_sync(1, kTcEpiThreads);
-      const int64_t row0 = (int64_t)tile * 128;                       // SPLIT == 1 for the narrow head
-      const int64_t rows_left = (int64_t)p.batch * p.L - row0;
-      const int cnt = (int)(rows_left < 128 ? rows_left : 128) * p.C_out;
-      const int traj = p.L * p.C_out;                                 // tiles start on trajectory boundaries (128 % L == 0)
-      for (int k = threadIdx.x; k < cnt; k += kTcEpiThreads) {
-        const int r = k / p.C_out, j = k - r * p.C_out;
-        solver_update_element(p.upd, upd_row, row0 * p.C_out + k, k % traj, (row0 + r) * p.upd.cast_C_out + j, s_pred[r * 16 + j]);
-      }
-      ptx::named_bar_sync(1, kTcEpiThreads);
-    }
     if (threadIdx.x == 0 && it < 14) CDS_TRACE(11 + 4 * it, clock64());
     }   // tile loop
     if (threadIdx.x == 0) CDS_TRACE(5, (long long)it);
@@ -742,7 +756,6 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
-  if (N == 16 && p.upd_on && p.advance) advance_iteration_when_last(p.advance, iter_ptr ? *iter_ptr : 0);
   if (threadIdx.x == 0) { CDS_TRACE(3, clock64()); CDS_TRACE(4, gtimer()); }
 }
 
@@ -791,6 +804,7 @@ inline int conv_tc_pick_kc(const cds_conv_op& c) {
 inline int conv_tc_width(const cds_conv_op& c) {
   int n = c.C_out * c.phases;
   if (n == 32 || n == 64 || n == 128 || n == 256) return (c.phases == 1 || c.C_out % 16 == 0) ? n : 0;
+  if ((n == 512 || n == 1024) && c.phases == 1) return n;      // wide layers: 2 / 4 CTAs of 256 columns (2-4 whole GroupNorm groups each)
   if (n <= 16 && c.phases == 1 && c.taps == 1 && c.groups == 0 && !c.res_w && !c.res) return 16;
   return 0;
 }
@@ -804,6 +818,7 @@ inline bool conv_tc_eligible(const cds_conv_op& c) {
   if (L > 32 || (L & (L - 1)) != 0) return false;
   if (c.stride == 1 ? (c.L_in != L) : (c.L_in != 2 * L || c.phases != 1 || c.res_w || c.res)) return false;
   if (conv_tc_width(c) == 0) return false;
+  if (conv_tc_width(c) > 256 && conv_tc_pick_kc(c) != 64) return false;       // wide variants are instantiated for KC = 64 only
   if (c.C_in % 32 != 0) return false;
   if (c.groups != 0 && (c.groups != 8 || c.phases != 1 || c.C_out < 32)) return false;
   if (c.phases == 2 && (c.res || c.res_w)) return false;
@@ -832,6 +847,7 @@ struct ConvTcLaunch {
 // Share a layer's columns between two CTAs?  Yes for the wide layers (C_out >= 128: halves the per-CTA epilogue and main
 // loop and lets two CTAs share an SM) and for C_out = 64 when there are too few row tiles to fill the machine.
 inline int conv_tc_pick_split(const cds_conv_op& c, int n_total, int m_tiles) {
+  if (n_total > 256) return n_total / 256;
   if (c.phases != 1 || n_total < 64) return 1;
   if (n_total >= 128) return 2;
   const char* e = getenv("CDS_TC_SPLIT64");
@@ -955,6 +971,7 @@ cudaError_t conv_tc_preload_t() {
 // every (KC, N, SPLIT) the dispatcher can pick (each with and without the shortcut accumulator); X(kc, n, split)
 #define CDS_TC_VARIANTS(X)                                                                              \
   X(64, 16, 1) X(64, 32, 1) X(64, 64, 1) X(64, 128, 1) X(64, 256, 1) X(64, 32, 2) X(64, 64, 2) X(64, 128, 2) \
+  X(64, 256, 2) X(64, 256, 4)                                                                            \
   X(32, 16, 1) X(32, 32, 1) X(32, 64, 1) X(32, 128, 1) X(32, 256, 1) X(32, 32, 2) X(32, 64, 2) X(32, 128, 2)
 
 #ifndef CDS_TC_INSTANTIATE

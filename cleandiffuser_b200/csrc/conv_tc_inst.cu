@@ -15,9 +15,9 @@ namespace cds {
   template cudaError_t conv_tc_preload_t<KC_, N_, true, S_>();
 
 #if CDS_TC_PART == 0
-CDS_TC_INST(64, 16, 1) CDS_TC_INST(32, 16, 1)
+CDS_TC_INST(64, 16, 1) CDS_TC_INST(32, 16, 1) CDS_TC_INST(64, 256, 2)
 #elif CDS_TC_PART == 1
-CDS_TC_INST(64, 32, 1) CDS_TC_INST(32, 32, 1)
+CDS_TC_INST(64, 32, 1) CDS_TC_INST(32, 32, 1) CDS_TC_INST(64, 256, 4)
 #elif CDS_TC_PART == 2
 CDS_TC_INST(64, 64, 1) CDS_TC_INST(32, 64, 1)
 #elif CDS_TC_PART == 3

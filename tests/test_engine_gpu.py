@@ -244,3 +244,29 @@ def test_parallel_branches_give_the_same_bits(math, monkeypatch):
     assert torch.isfinite(ref).all()
     for k, v in outs.items():
         assert torch.equal(v, ref), k
+
+
+def test_chiunet_full_size_on_tensor_cores(monkeypatch):
+    """cfg3's backbone exactly as the DP pipelines build it (model_dim 256 -> 256/512/1024 channels, 68.9 M parameters): every conv,
+    the C_out = 512 / 1024 ones included (2 / 4 CTAs of 256 columns, two-pass GroupNorm), runs on tcgen05; checked against the
+    module's own fp32 forward on the GPU (TF32 off), bf16 tolerance."""
+    monkeypatch.setenv("CDS_MATH", "bf16")
+    from cleandiffuser_b200.engine.lower import Program, View, lower_denoiser
+    from cleandiffuser_b200.nn_diffusion import ChiUNet1d
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = load_synth(ChiUNet1d(7, 20, 2, model_dim=256, emb_dim=256, kernel_size=5, dim_mult=[1, 2, 2]), seed=3).eval().to(DEV)
+    g = torch.Generator().manual_seed(4)
+    B = 160                                                         # 2.5 / 5 / 20 row tiles at L = 4 / 8 / 16 (ragged last tile)
+    x, cond = torch.randn(B, 16, 7, generator=g).to(DEV), torch.randn(B, 40, generator=g).to(DEV)
+    t = torch.tensor([17], device=DEV)
+    with torch.no_grad():
+        want = net(x, t.expand(B), cond)
+    y = runtime.engine_forward(net, x, t, cond)
+    err = (y - want).abs()
+    assert torch.isfinite(y).all()
+    assert err.max().item() < 0.25 and err.mean().item() < 0.02, (err.max().item(), err.mean().item())
+    p = Program(torch.device(DEV), B, 1, cabi.MATH_BF16_TC)
+    lower_denoiser(p, net, View(p.buf(B, 16, 7), 16, 7), (16, 7), True, 0)
+    convs = [op.u.conv for op in p.ops if op.kind == cabi.OP_CONV and op.u.conv.taps > 1]
+    assert len(convs) >= 28 and all(c.math == cabi.MATH_BF16_TC for c in convs), [(c.C_in, c.C_out, c.math) for c in convs]

@@ -184,3 +184,26 @@ def test_lowered_sampler_two_branches(golden, name, math, monkeypatch):
     else:
         err = np.abs(x0.numpy() - want)
         assert err.max() < 0.2 and err.mean() < 0.02, (float(err.max()), float(err.mean()))
+
+
+def test_wide_chiunet_layers_lower_to_tensor_core_ops(monkeypatch):
+    """ChiUNet1d with C_out = 512 and 1024 layers (cumulative dim_mult, as at the pipelines' model_dim 256): the wide layers are
+    tensor-core operators too (2-4 CTAs of 256 columns per row tile), and the lowered bf16 program agrees with the module."""
+    monkeypatch.setenv("CDS_MATH", "bf16")
+    from cleandiffuser_b200.engine import cabi
+    from cleandiffuser_b200.nn_diffusion import ChiUNet1d
+    from cleandiffuser_b200.testing import load_synth
+    net = load_synth(ChiUNet1d(7, 20, 2, model_dim=128, emb_dim=64, kernel_size=5, dim_mult=[1, 2, 2]), seed=3).eval()
+    g = torch.Generator().manual_seed(4)
+    x, cond = torch.randn(2, 16, 7, generator=g), torch.randn(2, 40, generator=g)
+    t = torch.tensor([17])
+    with torch.no_grad():
+        want = net(x, t.expand(2), cond).numpy()
+    y = runtime.engine_forward(net, x, t, cond).numpy()
+    err = np.abs(y - want)
+    assert err.max() < 0.1 and err.mean() < 0.02, (float(err.max()), float(err.mean()))
+    from cleandiffuser_b200.engine.lower import Program, View, lower_denoiser
+    p = Program(torch.device("cpu"), 2, 1, cabi.MATH_BF16_TC)
+    lower_denoiser(p, net, View(p.buf(2, 16, 7), 16, 7), (16, 7), True, 0)
+    wide = [op.u.conv for op in p.ops if op.kind == cabi.OP_CONV and op.u.conv.C_out == 512]
+    assert len(wide) >= 6 and all(c.math == cabi.MATH_BF16_TC for c in wide)
