@@ -3,6 +3,8 @@
 // row and runs an online softmax over the keys, so the L x L score matrix never exists in memory.
 // Algorithmic HBM bytes per (trajectory, head): 4*L*hd*4 (q, k, v read; out written).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace cds {
@@ -39,9 +41,16 @@ __global__ void __launch_bounds__(128) attention_f32_kernel(const cds_attn_op p)
       mx = nm;
     }
     float inv = 1.f / den;
-    float* dst = p.out + ((int64_t)b * p.L + i) * p.C + h * HD;
+    const int64_t o_off = ((int64_t)b * p.L + i) * p.C + h * HD;
+    if (p.out_dtype == CDS_BF16) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + o_off;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) dst[d] = o[d] * inv;
+      for (int d = 0; d < HD; ++d) dst[d] = __float2bfloat16_rn(o[d] * inv);
+    } else {
+      float* dst = reinterpret_cast<float*>(p.out) + o_off;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) dst[d] = o[d] * inv;
+    }
   }
 }
 

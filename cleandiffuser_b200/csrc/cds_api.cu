@@ -80,6 +80,7 @@ int validate(const cds_op& op, Step* out) {
         return CDS_OK;
       }
       if (c.math != CDS_MATH_FP32) return fail(CDS_ERR_UNSUPPORTED, "conv: math mode %d unknown", c.math);
+      if (c.sample_row_div > 1) return fail(CDS_ERR_UNSUPPORTED, "conv: sample_row_div needs the tensor-core kernel");
       out->conv_bn = cds::conv_simt_pick_bn(c);
       if (out->conv_bn == 0)
         return fail(CDS_ERR_UNSUPPORTED, "conv: GroupNorm tile does not fit (L_out=%d C_out=%d groups=%d)", c.L_out,

@@ -41,6 +41,8 @@ struct ConvTcParams {
   int phases;                     // 2: columns [0,C_out) / [C_out,2C_out) are output positions 2l / 2l+1 (transposed conv)
   int kchunks, kchunks2;          // channel chunks of the main conv / of the shortcut conv
   int in_batch_mod;
+  int n_col_tiles;                // SPLIT == 1 kernels, no GroupNorm: the layer's columns as this many N-wide tiles (runtime)
+  int sample_div;                 // per-trajectory vectors are indexed by (row's batch index) / sample_div   (>= 1)
   cds_vec bias, scale, shift;
   int groups; const float* gn_gamma; const float* gn_beta; float gn_eps;
   int act;
@@ -275,7 +277,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       // predecessor grid (programmatic dependent launch); the activation tiles of those stages follow after the wait.
       int pre = 0;
       if (blockIdx.x < p.num_tiles) {
-        const int n_off0 = (blockIdx.x % SPLIT) * N;
+        const int n_off0 = (int)(blockIdx.x % (SPLIT > 1 ? SPLIT : p.n_col_tiles)) * N;
         pre = n_kb < kTcStages ? n_kb : kTcStages;
         for (int kb = 0; kb < pre; ++kb) {
           uint8_t* sb = smem_al + kb * Cfg::kStageBytes + Cfg::kABytes;
@@ -291,8 +293,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       ptx::grid_dep_wait();
       int ring = 0;                                   // k-blocks issued so far (smem ring position, across tiles)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int b0 = (tile / SPLIT) * T;
-      const int n_off = (tile % SPLIT) * N;           // first layer column of this CTA tile
+      const int nct = SPLIT > 1 ? SPLIT : p.n_col_tiles;
+      const int b0 = (tile / nct) * T;
+      const int n_off = (tile % nct) * N;             // first layer column of this CTA tile
       const int a_b0 = p.in_batch_mod > 0 ? b0 % p.in_batch_mod : b0;
       const int r_b0 = p.res_batch_mod > 0 ? b0 % p.res_batch_mod : b0;
       for (int kb = 0; kb < n_kb; ++kb, ++ring) {
@@ -364,15 +367,15 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     const bool active = half < EW;                  // warp-uniform (N = 16: only warps 0..3 work)
     const int n_real = p.C_out * p.phases;          // < N only for narrow heads (C_out <= 16)
 
-    // ---- stage the per-column constants (overlaps with the TMA/MMA main loop)
-    {
+    // ---- stage the per-column constants (overlaps with the TMA/MMA main loop): columns [first, first + kCols) of the layer
+    auto stage_cols = [&](int first) {
       const float* bstep = p.bias.step ? p.bias.step + (int64_t)iter * p.bias.step_stride : nullptr;
       const float* sstep = p.scale.step ? p.scale.step + (int64_t)iter * p.scale.step_stride : nullptr;
       const float* hstep = p.shift.step ? p.shift.step + (int64_t)iter * p.shift.step_stride : nullptr;
       const bool scale_any = p.scale.step || p.scale.sample;
       for (int n = threadIdx.x; n < Cfg::kCols; n += kTcEpiThreads) {
-        const bool real = n < n_real;
-        const int c = real ? n % p.C_out : 0;
+        const bool real = first + n < n_real;
+        const int c = real ? (first + n) % p.C_out : 0;
         s_col[0][n] = (real && bstep) ? __ldg(bstep + c) : 0.f;
         s_col[1][n] = (real && p.groups > 0) ? __ldg(p.gn_gamma + c) : 1.f;
         s_col[2][n] = (real && p.groups > 0) ? __ldg(p.gn_beta + c) : 0.f;
@@ -380,15 +383,16 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         s_col[4][n] = (real && hstep) ? __ldg(hstep + c) : 0.f;
         s_col[5][n] = (real && HAS_RES && p.res_bias) ? __ldg(p.res_bias + c) : 0.f;
       }
-      ptx::named_bar_sync(1, kTcEpiThreads);
-    }
+    };
+    stage_cols(0);
+    ptx::named_bar_sync(1, kTcEpiThreads);
 
     // CTA-uniform option flags
     const bool has_gn = p.groups > 0;
     const bool smp = p.bias.sample || p.scale.sample || p.shift.sample;
     const bool has_scale = p.scale.step || p.scale.sample;
     const bool has_shift = p.shift.step || p.shift.sample;
-    const bool io_vec = n_real == Cfg::kCols;
+    const bool io_vec = n_real == Cfg::kCols * (SPLIT > 1 ? 1 : p.n_col_tiles);     // every column of every tile is a real channel
     const bool add_res = p.res != nullptr;
     const int film = (smp || has_scale) ? 2 : (has_shift ? 1 : 0);
 
@@ -400,7 +404,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     // accumulator, bf16 in and out, every column real).  The narrow tiles run close to the ISSUE limit (4 epilogue warps per
     // scheduler at ~0.2 IPC each), so instructions per tile are what counts: the option dispatch happens ONCE per kernel (the
     // tile loop lives inside the specialisation), addresses are strength-reduced to one multiply-add per tile, dtypes are fixed.
-    const bool fast_ok = N >= 32 && has_gn && p.act == CDS_ACT_MISH && film != 2 && p.phases == 1 && io_vec &&
+    const bool fast_ok = N >= 32 && p.n_col_tiles <= 1 && has_gn && p.act == CDS_ACT_MISH && film != 2 && p.phases == 1 && io_vec &&
                          p.out_dtype == CDS_BF16 && (!add_res || p.res_dtype == CDS_BF16) && p.res_batch_mod == 0;
     auto fast_tiles = [&](auto film_tag, auto res_tag) {
       constexpr bool SHIFT = decltype(film_tag)::value == 1;
@@ -520,14 +524,24 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     for (int tile = blockIdx.x + it * (int)gridDim.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
     const int buf = it % Cfg::kAccBufs;
     const uint32_t use = (uint32_t)(it / Cfg::kAccBufs);
-    const int64_t row = (int64_t)(tile / SPLIT) * 128 + m;
-    const int n_off = (tile % SPLIT) * N;
+    const int nct = SPLIT > 1 ? SPLIT : p.n_col_tiles;
+    const int64_t row = (int64_t)(tile / nct) * 128 + m;
+    const int n_off = (tile % nct) * N;
+    // s_col holds the kCols = N*SPLIT columns of the layer; with runtime column tiles (SPLIT == 1, n_col_tiles > 1) it holds the
+    // N columns of the CURRENT tile and is re-staged whenever the column tile changes
+    const int sc_off = SPLIT > 1 ? n_off : 0;
+    if (SPLIT == 1 && p.n_col_tiles > 1) {
+      ptx::named_bar_sync(1, kTcEpiThreads);        // everybody has left the previous tile's constants
+      stage_cols(n_off);
+      ptx::named_bar_sync(1, kTcEpiThreads);
+    }
     const bool valid = active && row < (int64_t)p.batch * p.L;
     const int b = (int)(row >> p.log2L), l = (int)(row & (p.L - 1));
     const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * Cfg::kColsPerTile);
-    const float* bias_smp = p.bias.sample ? p.bias.sample + (int64_t)b * p.bias.sample_stride : nullptr;
-    const float* scale_smp = p.scale.sample ? p.scale.sample + (int64_t)b * p.scale.sample_stride : nullptr;
-    const float* shift_smp = p.shift.sample ? p.shift.sample + (int64_t)b * p.shift.sample_stride : nullptr;
+    const int bs = p.sample_div > 1 ? b / p.sample_div : b;        // owner of the per-trajectory vectors (flattened token rows)
+    const float* bias_smp = p.bias.sample ? p.bias.sample + (int64_t)bs * p.bias.sample_stride : nullptr;
+    const float* scale_smp = p.scale.sample ? p.scale.sample + (int64_t)bs * p.scale.sample_stride : nullptr;
+    const float* shift_smp = p.shift.sample ? p.shift.sample + (int64_t)bs * p.shift.sample_stride : nullptr;
     const int rb = p.res_batch_mod > 0 ? b % p.res_batch_mod : b;
     const int64_t res_row = (int64_t)rb * p.res_bstride + (int64_t)l * p.res_lstride;
 
@@ -542,11 +556,12 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       constexpr int FILM = decltype(film_tag)::value;
       constexpr int YO = decltype(off_tag)::value;                 // offset of these 16 columns inside yv[]
       const int ng0 = n_off + n0;                                 // layer column of the chunk's first element
+      const int sg0 = sc_off + n0;                                // ... and where its constants sit in s_col
       const int phase = (p.phases == 1 || ng0 < p.C_out) ? 0 : 1;
       const int c0 = ng0 - phase * p.C_out;                       // its channel
       float addv[16];                                             // everything that is ADDED after the activation
       if constexpr (FILM == 1) {
-        const float4* sh4 = reinterpret_cast<const float4*>(&s_col[4][ng0]);
+        const float4* sh4 = reinterpret_cast<const float4*>(&s_col[4][sg0]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) { const float4 s = sh4[k]; addv[4 * k] = s.x; addv[4 * k + 1] = s.y; addv[4 * k + 2] = s.z; addv[4 * k + 3] = s.w; }
       } else {
@@ -564,7 +579,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       if constexpr (HAS_RES) {
         float r2[16];
         ptx::tmem_ld<16>(t_row + (uint32_t)(N + n0), r2);
-        const float4* rb4 = reinterpret_cast<const float4*>(&s_col[5][ng0]);
+        const float4* rb4 = reinterpret_cast<const float4*>(&s_col[5][sg0]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float4 s = rb4[k];
@@ -575,8 +590,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       float o[16];
       if constexpr (FILM == 2) {
         float sc[16], sh[16];
-        const float4* sc4 = reinterpret_cast<const float4*>(&s_col[3][ng0]);
-        const float4* sh4 = reinterpret_cast<const float4*>(&s_col[4][ng0]);
+        const float4* sc4 = reinterpret_cast<const float4*>(&s_col[3][sg0]);
+        const float4* sh4 = reinterpret_cast<const float4*>(&s_col[4][sg0]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float4 a = sc4[k], d = sh4[k];
@@ -618,7 +633,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     // v[j] += bias(column) for WC columns starting at CTA-tile column n0 (float4 reads of the staged constants)
     auto add_bias = [&](auto wc_tag, auto& v, int n0) {
       constexpr int WC = decltype(wc_tag)::value;
-      const float4* b4 = reinterpret_cast<const float4*>(&s_col[0][n_off + n0]);
+      const float4* b4 = reinterpret_cast<const float4*>(&s_col[0][sc_off + n0]);
 #pragma unroll
       for (int k = 0; k < WC / 4; ++k) {
         const float4 bb = b4[k];
@@ -805,6 +820,11 @@ inline int conv_tc_width(const cds_conv_op& c) {
   int n = c.C_out * c.phases;
   if (n == 32 || n == 64 || n == 128 || n == 256) return (c.phases == 1 || c.C_out % 16 == 0) ? n : 0;
   if ((n == 512 || n == 1024) && c.phases == 1) return n;      // wide layers: 2 / 4 CTAs of 256 columns (2-4 whole GroupNorm groups each)
+  // un-normalised layers of any width that is a multiple of 64 (DiT1d's 320 / 960 / 1280-wide Linear layers): runtime column tiles
+  if (n > 64 && n % 64 == 0 && c.groups == 0) {
+    const int tn = n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64);       // a column tile must not straddle the two phases
+    if (c.phases == 1 || c.C_out % tn == 0) return n;
+  }
   if (n <= 16 && c.phases == 1 && c.taps == 1 && c.groups == 0 && !c.res_w && !c.res) return 16;
   return 0;
 }
@@ -818,7 +838,8 @@ inline bool conv_tc_eligible(const cds_conv_op& c) {
   if (L > 32 || (L & (L - 1)) != 0) return false;
   if (c.stride == 1 ? (c.L_in != L) : (c.L_in != 2 * L || c.phases != 1 || c.res_w || c.res)) return false;
   if (conv_tc_width(c) == 0) return false;
-  if (conv_tc_width(c) > 256 && conv_tc_pick_kc(c) != 64) return false;       // wide variants are instantiated for KC = 64 only
+  if (conv_tc_width(c) > 256 && c.groups != 0 && conv_tc_pick_kc(c) != 64) return false;   // wide GN variants: KC = 64 only
+  if (c.sample_row_div > 1 && c.L_out != 1) return false;
   if (c.C_in % 32 != 0) return false;
   if (c.groups != 0 && (c.groups != 8 || c.phases != 1 || c.C_out < 32)) return false;
   if (c.phases == 2 && (c.res || c.res_w)) return false;
@@ -865,8 +886,17 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
   const int m_tiles = (int)((rows + 127) / 128);
   const int n_total = conv_tc_width(c);
   L.kc = kc; L.has_res = c.res_w != nullptr;
-  L.split = conv_tc_pick_split(c, n_total, m_tiles);
-  L.n = n_total / L.split;
+  int col_tiles = 1;                                  // runtime column tiles (SPLIT == 1 kernels)
+  const bool fixed = n_total == 16 || n_total == 32 || n_total == 64 || n_total == 128 || n_total == 256 ||
+                     ((n_total == 512 || n_total == 1024) && c.groups != 0);
+  if (fixed) {
+    L.split = conv_tc_pick_split(c, n_total, m_tiles);
+    L.n = n_total / L.split;
+  } else {
+    L.split = 1;
+    L.n = n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64);
+    col_tiles = n_total / L.n;
+  }
   const uint64_t in_b = c.in_batch_mod > 0 ? (uint64_t)c.in_batch_mod : (uint64_t)c.batch;
   {
     uint64_t dims[3] = {(uint64_t)c.C_in, (uint64_t)c.L_in, in_b};
@@ -903,7 +933,9 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
   p.res = c.res; p.res_bstride = c.res_bstride; p.res_lstride = c.res_lstride; p.res_batch_mod = c.res_batch_mod;
   p.res_dtype = c.res_dtype; p.res_bias = c.res_bias;
   p.out = c.out; p.out_bstride = c.out_bstride; p.out_lstride = c.out_lstride; p.out_dtype = c.out_dtype;
-  p.num_tiles = m_tiles * L.split;
+  p.n_col_tiles = col_tiles;
+  p.sample_div = c.sample_row_div > 1 ? c.sample_row_div : 1;
+  p.num_tiles = m_tiles * (L.split > 1 ? L.split : col_tiles);
   L.grid = dim3((unsigned)p.num_tiles);      // clipped to the resident-CTA capacity at launch (persistent CTAs)
   return true;
 }

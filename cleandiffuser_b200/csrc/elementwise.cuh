@@ -189,8 +189,13 @@ static __global__ void __launch_bounds__(256) ln_modulate_kernel(const cds_lnmod
     const int b = (int)(r / p.L);
     const float* sh = p.shift + (int64_t)b * p.mod_bstride;
     const float* sc = p.scale + (int64_t)b * p.mod_bstride;
-    float* dst = p.out + r * p.C;
-    for (int c = lane; c < p.C; c += 32) dst[c] = fmaf((src[c] - mean) * rstd, 1.f + sc[c], sh[c]);
+    if (p.out_dtype == CDS_BF16) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + r * p.C;
+      for (int c = lane; c < p.C; c += 32) dst[c] = __float2bfloat16_rn(fmaf((src[c] - mean) * rstd, 1.f + sc[c], sh[c]));
+    } else {
+      float* dst = reinterpret_cast<float*>(p.out) + r * p.C;
+      for (int c = lane; c < p.C; c += 32) dst[c] = fmaf((src[c] - mean) * rstd, 1.f + sc[c], sh[c]);
+    }
   }
 }
 

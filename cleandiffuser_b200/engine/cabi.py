@@ -10,7 +10,7 @@ import os
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "libcds.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 OPF_BRANCH_SHIFT = 8   # cds_op.flags bits 8..15: branch index (independent chains run on parallel streams)
 OPF_ONCE = 1          # cds_op.flags: run once per plan run (before its first iteration), not in every iteration
 OP_CONV, OP_UPDATE, OP_LNMOD, OP_ATTN, OP_PREP, OP_CAST = range(6)
@@ -43,17 +43,19 @@ class ConvOp(C.Structure):
         ("out", _f32p), ("out_bstride", C.c_int64), ("out_lstride", C.c_int32),
         ("math", C.c_int32),
         ("in_dtype", C.c_int32), ("out_dtype", C.c_int32), ("res_dtype", C.c_int32), ("res_in_dtype", C.c_int32),
+        ("sample_row_div", C.c_int32),
     ]
 
 
 class LnModOp(C.Structure):
     _fields_ = [("batch", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("eps", C.c_float),
-                ("in_", _f32p), ("out", _f32p), ("shift", _f32p), ("scale", _f32p), ("mod_bstride", C.c_int64)]
+                ("in_", _f32p), ("out", C.c_void_p), ("shift", _f32p), ("scale", _f32p), ("mod_bstride", C.c_int64),
+                ("out_dtype", C.c_int32)]
 
 
 class AttnOp(C.Structure):
     _fields_ = [("batch", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32),
-                ("qkv", _f32p), ("out", _f32p)]
+                ("qkv", _f32p), ("out", C.c_void_p), ("out_dtype", C.c_int32)]
 
 
 class PrepOp(C.Structure):

@@ -166,7 +166,7 @@ class Program:
     def conv(self, x: View, w: WSpec, out: View, *, taps=1, stride=1, pad=0, phases=1, L_out=None,
              bias: Optional[cabi.Vec] = None, gn: Optional[GroupNorm1d] = None, act=cabi.ACT_NONE,
              scale: Optional[cabi.Vec] = None, shift: Optional[cabi.Vec] = None, res: Optional[View] = None,
-             res_conv=None, in_batch_mod=0, res_batch_mod=0, rows=None):
+             res_conv=None, in_batch_mod=0, res_batch_mod=0, rows=None, sample_row_div=0):
         """Emit one CDS_OP_CONV.  ``res_conv`` = (View, WSpec of the 1x1 weight, bias tensor maker)."""
         op = cabi.Op()
         op.kind = cabi.OP_CONV
@@ -176,6 +176,7 @@ class Program:
         c.C_in, c.C_out = x.C, out.C
         c.taps, c.stride, c.pad, c.phases = int(taps), int(stride), int(pad), int(phases)
         c.in_batch_mod = int(in_batch_mod)
+        c.sample_row_div = int(sample_row_div)
         c.in_, c.in_bstride, c.in_lstride, c.in_dtype = x.ptr, x.bstride, x.lstride, x.dtype
         if bias is not None:
             c.bias = bias
@@ -215,6 +216,33 @@ class Program:
         self.ops.append(op)
         return out
 
+    def token_linear(self, x: View, w: WSpec, out: View, **kw):
+        """Linear layer over a dense token stream (rows, L, C): on tensor-core programs the tokens are flattened to rows*L
+        length-1 sequences (any L, e.g. DiT1d's 100), per-trajectory vectors follow through ``sample_row_div = L`` and a
+        residual stream is flattened alongside; if the flattened operator is not tensor-core material it is emitted as is."""
+        L = x.L
+        dense = (x.lstride == x.C and x.bstride == L * x.C and out.lstride == out.C and out.bstride == L * out.C)
+        res = kw.get("res")
+        if res is not None:
+            dense = dense and res.lstride == res.C and res.bstride == L * res.C
+        if self.math == cabi.MATH_BF16_TC and dense and x.t.dtype == torch.bfloat16 and w.nk is not None and kw.get("res_conv") is None:
+            flat = lambda v: View(v.t, 1, v.C, v.offset, v.C, v.C)
+            probe = cabi.Op()
+            c = probe.u.conv
+            c.batch, c.L_in, c.L_out, c.C_in, c.C_out, c.taps, c.stride, c.pad, c.phases = self.rows * L, 1, 1, x.C, out.C, 1, 1, 0, 1
+            c.in_, c.in_bstride, c.in_lstride, c.in_dtype = x.ptr, x.C, x.C, x.dtype
+            c.out, c.out_bstride, c.out_lstride, c.out_dtype = out.ptr, out.C, out.C, out.dtype
+            c.act = kw.get("act", cabi.ACT_NONE)
+            c.sample_row_div = L
+            if res is not None:
+                c.res, c.res_bstride, c.res_lstride, c.res_dtype = res.ptr, res.C, res.C, res.dtype
+            if cabi.load().cds_conv_tc_supported(C.byref(c)):
+                kw2 = dict(kw)
+                if res is not None:
+                    kw2["res"] = flat(res)
+                return self.conv(flat(x), w, flat(out), rows=self.rows * L, sample_row_div=L, **kw2)
+        return self.conv(x, w, out, **kw)
+
     def cast_pad(self, x: View, width: int) -> View:
         """fp32 dense (rows, L, C) -> bf16 dense (rows, L, width) with zero channels appended."""
         assert x.t.dtype == torch.float32 and x.lstride == x.C and x.bstride == x.L * x.C
@@ -232,7 +260,7 @@ class Program:
         op.kind = cabi.OP_LNMOD
         m = op.u.lnmod
         m.batch, m.L, m.C, m.eps = self.rows, x.L, x.C, eps
-        m.in_, m.out = x.ptr, out.ptr
+        m.in_, m.out, m.out_dtype = x.ptr, out.ptr, out.dtype
         m.shift, m.scale = mod.data_ptr() + 4 * int(shift_col), mod.data_ptr() + 4 * int(scale_col)
         m.mod_bstride = mod.stride(0)
         self.ops.append(op)
@@ -242,7 +270,7 @@ class Program:
         op.kind = cabi.OP_ATTN
         a = op.u.attn
         a.batch, a.L, a.C, a.heads = self.rows, out.L, out.C, int(heads)
-        a.qkv, a.out = qkv.ptr, out.ptr
+        a.qkv, a.out, a.out_dtype = qkv.ptr, out.ptr, out.dtype
         self.ops.append(op)
 
 
@@ -498,25 +526,28 @@ def lower_dit(p: Program, net: DiT1d, x: View, horizon: int, has_cond: bool, in_
     mod2d = mod.t.view(R, total)
 
     # ---- tokens
-    f32 = torch.float32          # the LayerNorm / attention operators are fp32: keep the token stream fp32 for now
-    X, Y, ATT = p.act(L, d, f32), p.act(L, d, f32), p.act(L, d, f32)
-    QKV, HID = p.act(L, 3 * d, f32), p.act(L, 4 * d, f32)
+    # residual stream X and the attention operands QKV stay fp32; what feeds a Linear layer (the modulated tokens Y, the
+    # attention output, the MLP hidden) has the program's activation dtype: bf16 on tensor-core programs, where those Linear
+    # layers (97 % of DiT1d's FLOPs outside attention) run on tcgen05 over the flattened token stream
+    f32 = torch.float32
+    X, QKV = p.act(L, d, f32), p.act(L, 3 * d, f32)
+    Y, ATT, HID = p.act(L, d), p.act(L, d), p.act(L, 4 * d)
     p.conv(x, w_linear(net.x_proj.weight), X, bias=_const_vec(p.packed(lambda: net.x_proj.bias)),
            res=View(pos, L, d, bstride=0), in_batch_mod=in_batch_mod)
     for i, blk in enumerate(net.blocks):
         o = 6 * d * i       # chunk order: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
         p.lnmod(X, Y, mod2d, o, o + d, blk.norm1.eps)
         at = blk.attn
-        p.conv(Y, w_linear(at.in_proj_weight), QKV, bias=_const_vec(p.packed(lambda a=at: a.in_proj_bias)))
+        p.token_linear(Y, w_linear(at.in_proj_weight), QKV, bias=_const_vec(p.packed(lambda a=at: a.in_proj_bias)))
         p.attn(QKV, ATT, heads)
         # reference quirk (dit.py:33-34): the residual wraps the MODULATED tokens Y, not the block input
-        p.conv(ATT, w_linear(at.out_proj.weight), X, bias=_const_vec(p.packed(lambda a=at: a.out_proj.bias)),
-               scale=_vec(sample=mod2d, col=o + 2 * d), res=Y)
+        p.token_linear(ATT, w_linear(at.out_proj.weight), X, bias=_const_vec(p.packed(lambda a=at: a.out_proj.bias)),
+                       scale=_vec(sample=mod2d, col=o + 2 * d), res=Y)
         p.lnmod(X, Y, mod2d, o + 3 * d, o + 4 * d, blk.norm2.eps)
-        p.conv(Y, w_linear(blk.mlp[0].weight), HID, bias=_const_vec(p.packed(lambda b=blk: b.mlp[0].bias)),
-               act=cabi.ACT_GELU_TANH)
-        p.conv(HID, w_linear(blk.mlp[3].weight), X, bias=_const_vec(p.packed(lambda b=blk: b.mlp[3].bias)),
-               scale=_vec(sample=mod2d, col=o + 5 * d), res=X)
+        p.token_linear(Y, w_linear(blk.mlp[0].weight), HID, bias=_const_vec(p.packed(lambda b=blk: b.mlp[0].bias)),
+                       act=cabi.ACT_GELU_TANH)
+        p.token_linear(HID, w_linear(blk.mlp[3].weight), X, bias=_const_vec(p.packed(lambda b=blk: b.mlp[3].bias)),
+                       scale=_vec(sample=mod2d, col=o + 5 * d), res=X)
     o = 6 * d * depth
     fl = net.final_layer
     p.lnmod(X, Y, mod2d, o, o + d, fl.norm_final.eps)

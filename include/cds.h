@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CDS_ABI_VERSION 3
+#define CDS_ABI_VERSION 4
 
 typedef enum cds_status {
   CDS_OK = 0,
@@ -103,19 +103,24 @@ typedef struct cds_conv_op {
   void* out; int64_t out_bstride; int32_t out_lstride;
   int32_t math;                    /* cds_math: which kernel family / weight layout */
   int32_t in_dtype, out_dtype, res_dtype, res_in_dtype;   /* cds_dtype of the activation tensors */
+  /* > 1: the `sample` parts of bias / scale / shift belong to row-batch index b / sample_row_div (Linear layers over a token
+   * stream flattened to batch*L rows of length-1 "sequences": one vector per trajectory = per L tokens).  Tensor-core path only. */
+  int32_t sample_row_div;
 } cds_conv_op;
 
 /* out(b,l,:) = LayerNorm(in(b,l,:), eps, no affine) * (1 + scale(b,:)) + shift(b,:) */
 typedef struct cds_lnmod_op {
   int32_t batch, L, C; float eps;
-  const float* in; float* out;                  /* dense (batch, L, C) */
+  const float* in; void* out;                   /* dense (batch, L, C); in fp32, out of out_dtype */
   const float* shift; const float* scale; int64_t mod_bstride;   /* per-trajectory vectors */
+  int32_t out_dtype;                            /* cds_dtype: bf16 feeds the tensor-core Linear that follows */
 } cds_lnmod_op;
 
 /* qkv dense (batch, L, 3*C) with [q | k | v] column blocks, heads split C evenly; out dense (batch, L, C) */
 typedef struct cds_attn_op {
   int32_t batch, L, C, heads;
-  const float* qkv; float* out;
+  const float* qkv; void* out;
+  int32_t out_dtype;                            /* cds_dtype of out */
 } cds_attn_op;
 
 /* dense fp32 (batch, L, C_in) -> dense bf16 (batch, L, C_out), channels [C_in, C_out) zero: gives x_t the 32-channel

@@ -40,6 +40,24 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
+def per_op(agent, tag):
+    """cds_plan_profile of the agent's (only) plan: device time of every operator of one iteration, to stderr."""
+    plan = next(iter(agent._engine_plans.values()))
+    ops = plan.program.ops
+    st = torch.cuda.current_stream().cuda_stream
+    plan.handle.profile(1, st, len(ops))
+    t = plan.handle.profile(1, st, len(ops))
+    kinds = {0: "conv", 1: "update", 2: "lnmod", 3: "attn", 4: "prep", 5: "cast"}
+    tot = sum(t)
+    for i, (op, ms) in enumerate(zip(ops, t)):
+        d = ""
+        if op.kind == 0:
+            c = op.u.conv
+            d = f"{'tc ' if c.math == 1 else 'f32'} rows {c.batch} L {c.L_in}->{c.L_out} C {c.C_in}->{c.C_out} k{c.taps}"
+        print(f"[{tag}] op {i:2d} {kinds[op.kind]:6s} {d:48s} {ms * 1e3:9.1f} us ({ms / tot * 100:4.1f} %)", file=sys.stderr)
+    print(f"[{tag}] iteration total {tot * 1e3:.1f} us", file=sys.stderr)
+
+
 def report(name, batch, ms, gflop_per_traj, note):
     v = batch / (ms * 1e-3)
     print(json.dumps({"config": name, "math": args.math, "batch": batch, "ms_per_sample_call": ms, "trajectories_per_s": v,
@@ -57,6 +75,7 @@ with torch.no_grad():
                                      x_max=torch.ones(1, 16, 7), x_min=-torch.ones(1, 16, 7), device=DEV)
         prior, cond = torch.zeros(B, 16, 7, device=DEV), torch.randn(B, 40, generator=g).to(DEV)
         ms = timed(lambda: agent.sample(prior, solver="ddim", n_samples=B, sample_steps=50, condition_cfg=cond, w_cfg=1.0), args.reps)
+        per_op(agent, "cfg3")
         report("cfg3 ChiUNet1d DDIM 50 w_cfg=1", B, ms, 29.85, "SURVEY 8d: 29.85 GFLOP / trajectory")
         del agent, net
     if "cfg5" in args.cfgs:
@@ -83,5 +102,6 @@ with torch.no_grad():
         ms = timed(lambda: agent.sample(prior, solver="ode_dpmsolver++_2M", n_samples=B, sample_steps=20,
                                         sample_step_schedule="uniform_continuous", temperature=0.5, condition_cfg=cond, w_cfg=6.0),
                    args.reps)
+        per_op(agent, "cfg4")
         report("cfg4 DiT1d DPM-Solver++2M 20 steps, 2 CFG branches (2048 = 16384 / 8 GPUs)", B, ms, 20.96,
-               "SURVEY 8d: 20.96 GFLOP / trajectory; DiT runs on the fp32 CUDA-core kernels in every math mode")
+               "SURVEY 8d: 20.96 GFLOP / trajectory; Linear layers on tcgen05 (bf16), attention / LayerNorm on CUDA cores (fp32)")

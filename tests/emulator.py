@@ -48,14 +48,15 @@ def _store(ptr, shape, strides, dtype, values):
     np.lib.stride_tricks.as_strided(flat, shape=shape, strides=[2 * s for s in strides])[...] = _f32_to_bf16(values)
 
 
-def _vec(v, it, rows, n):
+def _vec(v, it, rows, n, row_div=1):
     out = np.zeros((rows, n), dtype=np.float32)
     present = False
     if v.step:
         out += _arr(v.step + 4 * it * v.step_stride, (n,), (1,))[None]
         present = True
     if v.sample:
-        out += _arr(v.sample, (rows, n), (v.sample_stride, 1))
+        owners = (rows + row_div - 1) // row_div                   # one vector per `row_div` rows (flattened token rows)
+        out += _arr(v.sample, (owners, n), (v.sample_stride, 1))[np.arange(rows) // row_div]
         present = True
     return out if present else None
 
@@ -97,7 +98,8 @@ def run_conv(c, it):
                 acc[:, l, :] += xin[:, pos, :].astype(np.float64) @ w[tap].astype(np.float64)
     y = acc.astype(np.float32)
     chan = np.arange(N) % c.C_out
-    bias = _vec(c.bias, it, B, c.C_out)
+    div = c.sample_row_div if c.sample_row_div > 1 else 1
+    bias = _vec(c.bias, it, B, c.C_out, div)
     if bias is not None:
         y = y + bias[:, None, chan]
     if c.groups > 0:
@@ -109,7 +111,7 @@ def run_conv(c, it):
         y = g.reshape(B, c.L_out, c.C_out).astype(np.float32)
         y = y * _arr(c.gn_gamma, (c.C_out,), (1,)) + _arr(c.gn_beta, (c.C_out,), (1,))
     y = _act(c.act, y.astype(np.float32)).astype(np.float32)
-    scale, shift = _vec(c.scale, it, B, c.C_out), _vec(c.shift, it, B, c.C_out)
+    scale, shift = _vec(c.scale, it, B, c.C_out, div), _vec(c.shift, it, B, c.C_out, div)
     if scale is not None:
         y = y * scale[:, None, chan]
     if shift is not None:
@@ -136,7 +138,7 @@ def run_lnmod(m):
     n = (x - mu) / np.sqrt(var + m.eps)
     sh = _arr(m.shift, (m.batch, m.C), (m.mod_bstride, 1))[:, None]
     sc = _arr(m.scale, (m.batch, m.C), (m.mod_bstride, 1))[:, None]
-    _arr(m.out, (m.batch, m.L, m.C), (m.L * m.C, m.C, 1))[...] = (n * (1 + sc) + sh).astype(np.float32)
+    _store(m.out, (m.batch, m.L, m.C), (m.L * m.C, m.C, 1), m.out_dtype, (n * (1 + sc) + sh).astype(np.float32))
 
 
 def run_attn(a):
@@ -147,7 +149,7 @@ def run_attn(a):
     s = np.exp(s - s.max(-1, keepdims=True))
     s /= s.sum(-1, keepdims=True)
     o = (s @ v).transpose(0, 2, 1, 3).reshape(a.batch, a.L, a.C)
-    _arr(a.out, (a.batch, a.L, a.C), (a.L * a.C, a.C, 1))[...] = o.astype(np.float32)
+    _store(a.out, (a.batch, a.L, a.C), (a.L * a.C, a.C, 1), a.out_dtype, o.astype(np.float32))
 
 
 def run_cast(k):

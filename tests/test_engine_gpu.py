@@ -152,7 +152,7 @@ def test_smoke_entry():
 # tensor-core programs (CDS_MATH=bf16): bf16 operands / activations, fp32 TMEM accumulation and fp32 GN/Mish epilogue.
 # Stated tolerance vs the fp32 reference (measured by emulation: ~8e-3 relative per forward, no
 # compounding over the reverse steps): max-abs 2e-1, mean-abs 2e-2 on O(1) outputs.
-BF16_NETS = ["janner_cfg2", "janner_kitchen_cond", "chi_small", "chi_cm_fourier"]
+BF16_NETS = ["janner_cfg2", "janner_kitchen_cond", "chi_small", "chi_cm_fourier", "dit_small", "dit_pos_uncond"]
 
 
 @pytest.mark.parametrize("name", BF16_NETS)

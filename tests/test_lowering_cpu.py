@@ -80,7 +80,7 @@ def test_lowered_consistency(golden, steps):
 # bf16 tensor-core programs: same lowering, bf16 activations/weights in the interpreter.  Tolerances are the
 # SURVEY 8(c) bf16 figures (single forward ~8e-3 relative); this pins the bf16 *lowering* (dtypes, [tap][Cout][Cin]
 # weight packing, which ops go to which kernel family), the kernels themselves are checked on the GPU.
-BF16_NETS = ["janner_cfg2", "janner_kitchen_cond", "chi_small", "chi_cm_fourier"]
+BF16_NETS = ["janner_cfg2", "janner_kitchen_cond", "chi_small", "chi_cm_fourier", "dit_small", "dit_pos_uncond"]
 
 
 @pytest.mark.parametrize("name", BF16_NETS)
@@ -207,3 +207,29 @@ def test_wide_chiunet_layers_lower_to_tensor_core_ops(monkeypatch):
     lower_denoiser(p, net, View(p.buf(2, 16, 7), 16, 7), (16, 7), True, 0)
     wide = [op.u.conv for op in p.ops if op.kind == cabi.OP_CONV and op.u.conv.C_out == 512]
     assert len(wide) >= 6 and all(c.math == cabi.MATH_BF16_TC for c in wide)
+
+
+def test_dit_linear_layers_lower_to_flattened_tensor_core_ops(monkeypatch):
+    """DiT1d on a tensor-core program: QKV / out-proj / MLP Linear layers become tensor-core operators over the token stream
+    flattened to rows*L length-1 sequences (L = 100 is not a tile-friendly length), per-trajectory gates follow through
+    sample_row_div, LayerNorm+modulate and attention hand bf16 to the Linear that follows."""
+    monkeypatch.setenv("CDS_MATH", "bf16")
+    from cleandiffuser_b200.engine import cabi
+    from cleandiffuser_b200.engine.lower import Program, View, lower_denoiser
+    from cleandiffuser_b200.nn_diffusion import DiT1d
+    from cleandiffuser_b200.testing import load_synth
+    net = load_synth(DiT1d(29, emb_dim=128, d_model=320, n_heads=10, depth=2, timestep_emb_type="fourier"), seed=0).eval()
+    B, L = 3, 100
+    p = Program(torch.device("cpu"), B, 1, cabi.MATH_BF16_TC)
+    lower_denoiser(p, net, View(p.buf(B, L, 29), L, 29), (L, 29), True, 0)
+    tc = [op.u.conv for op in p.ops if op.kind == cabi.OP_CONV and op.u.conv.math == cabi.MATH_BF16_TC]
+    assert sorted((c.C_in, c.C_out) for c in tc) == sorted([(320, 960), (320, 320), (320, 1280), (1280, 320)] * 2)
+    assert all(c.batch == B * L and c.L_in == 1 and c.sample_row_div == L for c in tc)
+    assert all(op.u.lnmod.out_dtype == cabi.BF16 for op in p.ops if op.kind == cabi.OP_LNMOD)
+    assert all(op.u.attn.out_dtype == cabi.BF16 for op in p.ops if op.kind == cabi.OP_ATTN)
+    g = torch.Generator().manual_seed(2)
+    x, cond, t = torch.randn(B, L, 29, generator=g), torch.randn(B, 128, generator=g), torch.tensor([0.37])
+    with torch.no_grad():
+        want = net(x, t.expand(B), cond).numpy()
+    err = np.abs(runtime.engine_forward(net, x, t, cond).numpy() - want)
+    assert err.max() < 0.12 and err.mean() < 0.02, (float(err.max()), float(err.mean()))
