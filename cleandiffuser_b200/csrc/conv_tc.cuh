@@ -825,7 +825,8 @@ inline int conv_tc_width(const cds_conv_op& c) {
     const int tn = n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64);       // a column tile must not straddle the two phases
     if (c.phases == 1 || c.C_out % tn == 0) return n;
   }
-  if (n <= 16 && c.phases == 1 && c.taps == 1 && c.groups == 0 && !c.res_w && !c.res) return 16;
+  // narrow output heads (C_out <= 32, e.g. 14 / 29 state dims): N = 16 / 32 with the missing weight rows zero-filled by the TMA unit
+  if (n <= 32 && n != 32 && c.phases == 1 && c.taps == 1 && c.groups == 0 && !c.res_w && !c.res) return n <= 16 ? 16 : 32;
   return 0;
 }
 
@@ -845,7 +846,7 @@ inline bool conv_tc_eligible(const cds_conv_op& c) {
   if (c.phases == 2 && (c.res || c.res_w)) return false;
   int T = 128 / L;
   if (c.in_batch_mod > 0 && c.in_batch_mod % T != 0) return false;
-  if (c.res_batch_mod > 0 && c.res_batch_mod % T != 0) return false;
+  if (c.res_batch_mod > 0 && c.res_w && c.res_batch_mod % T != 0) return false;   // (the identity residual is read row by row)
   if (c.res_w && (c.res_in_dtype != 1 || c.res_C % 32 != 0)) return false;
   if ((c.in_lstride % 8) || (c.in_bstride % 8) || ((uintptr_t)c.in % 16)) return false;
   if (c.C_out % 16 == 0) {                           // vector stores

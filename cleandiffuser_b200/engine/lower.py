@@ -223,8 +223,12 @@ class Program:
         L = x.L
         dense = (x.lstride == x.C and x.bstride == L * x.C and out.lstride == out.C and out.bstride == L * out.C)
         res = kw.get("res")
+        res_period = 0                       # > 0: the residual repeats every L rows (a (L, C) table broadcast over the batch)
         if res is not None:
-            dense = dense and res.lstride == res.C and res.bstride == L * res.C
+            if res.bstride == 0 and res.lstride == res.C:
+                res_period = L
+            else:
+                dense = dense and res.lstride == res.C and res.bstride == L * res.C
         if self.math == cabi.MATH_BF16_TC and dense and x.t.dtype == torch.bfloat16 and w.nk is not None and kw.get("res_conv") is None:
             flat = lambda v: View(v.t, 1, v.C, v.offset, v.C, v.C)
             probe = cabi.Op()
@@ -234,19 +238,24 @@ class Program:
             c.out, c.out_bstride, c.out_lstride, c.out_dtype = out.ptr, out.C, out.C, out.dtype
             c.act = kw.get("act", cabi.ACT_NONE)
             c.sample_row_div = L
+            c.in_batch_mod = int(kw.get("in_batch_mod", 0)) * L
             if res is not None:
                 c.res, c.res_bstride, c.res_lstride, c.res_dtype = res.ptr, res.C, res.C, res.dtype
+                c.res_batch_mod = res_period
             if cabi.load().cds_conv_tc_supported(C.byref(c)):
                 kw2 = dict(kw)
+                kw2["in_batch_mod"] = c.in_batch_mod
                 if res is not None:
                     kw2["res"] = flat(res)
+                    kw2["res_batch_mod"] = res_period
                 return self.conv(flat(x), w, flat(out), rows=self.rows * L, sample_row_div=L, **kw2)
         return self.conv(x, w, out, **kw)
 
-    def cast_pad(self, x: View, width: int) -> View:
-        """fp32 dense (rows, L, C) -> bf16 dense (rows, L, width) with zero channels appended."""
+    def cast_pad(self, x: View, width: int, rows: Optional[int] = None) -> View:
+        """fp32 dense (rows, L, C) -> bf16 dense (rows, L, width) with zero channels appended (rows: of the VIEW, which may
+        be a sub-batch of its tensor)."""
         assert x.t.dtype == torch.float32 and x.lstride == x.C and x.bstride == x.L * x.C
-        rows = x.t.shape[0]
+        rows = x.t.shape[0] if rows is None else int(rows)
         out = View(self.buf(rows, x.L, width, dtype=torch.bfloat16), x.L, width)
         op = cabi.Op()
         op.kind = cabi.OP_CAST
@@ -532,8 +541,16 @@ def lower_dit(p: Program, net: DiT1d, x: View, horizon: int, has_cond: bool, in_
     f32 = torch.float32
     X, QKV = p.act(L, d, f32), p.act(L, 3 * d, f32)
     Y, ATT, HID = p.act(L, d), p.act(L, d), p.act(L, 4 * d)
-    p.conv(x, w_linear(net.x_proj.weight), X, bias=_const_vec(p.packed(lambda: net.x_proj.bias)),
-           res=View(pos, L, d, bstride=0), in_batch_mod=in_batch_mod)
+    if p.math == cabi.MATH_BF16_TC and x.t.dtype == torch.float32 and x.lstride == x.C and x.bstride == L * x.C:
+        # x_t enters as a 32-channel-padded bf16 copy (kept fresh by the solver update, like the UNets' hand-over)
+        kin = 32 * ((x.C + 31) // 32)
+        xb = p.cast_pad(x, kin, rows=in_batch_mod or p.rows)
+        w_in = w_rows(lambda: F.pad(net.x_proj.weight, (0, kin - net.x_proj.weight.shape[1])))
+        p.token_linear(xb, w_in, X, bias=_const_vec(p.packed(lambda: net.x_proj.bias)),
+                       res=View(pos, L, d, bstride=0), in_batch_mod=in_batch_mod)
+    else:
+        p.conv(x, w_linear(net.x_proj.weight), X, bias=_const_vec(p.packed(lambda: net.x_proj.bias)),
+               res=View(pos, L, d, bstride=0), in_batch_mod=in_batch_mod)
     for i, blk in enumerate(net.blocks):
         o = 6 * d * i       # chunk order: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
         p.lnmod(X, Y, mod2d, o, o + d, blk.norm1.eps)
@@ -552,14 +569,14 @@ def lower_dit(p: Program, net: DiT1d, x: View, horizon: int, has_cond: bool, in_
     fl = net.final_layer
     p.lnmod(X, Y, mod2d, o, o + d, fl.norm_final.eps)
     out = p.act(L, net.in_dim, f32)
-    return p.conv(Y, w_linear(fl.linear.weight), out, bias=_const_vec(p.packed(lambda: fl.linear.bias)))
+    return p.token_linear(Y, w_linear(fl.linear.weight), out, bias=_const_vec(p.packed(lambda: fl.linear.bias)))
 
 
 def lower_denoiser(p: Program, net: nn.Module, x: View, x_shape, has_cond: bool, in_batch_mod: int) -> View:
     """Dispatch on the backbone type (reference instances are recognised structurally by class name)."""
     name = type(net).__name__
     if name in ("JannerUNet1d", "ChiUNet1d") and len(x_shape) == 2 and p.math == cabi.MATH_BF16_TC:
-        x = p.cast_pad(x, 32 * ((x.C + 31) // 32))           # TMA/UMMA want K in multiples of 32 bf16
+        x = p.cast_pad(x, 32 * ((x.C + 31) // 32), rows=in_batch_mod or p.rows)   # TMA/UMMA want K in multiples of 32 bf16
     if name == "JannerUNet1d" and len(x_shape) == 2:
         return lower_janner(p, net, x, x_shape[0], has_cond, in_batch_mod)
     if name == "ChiUNet1d" and len(x_shape) == 2:

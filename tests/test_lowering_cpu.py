@@ -223,8 +223,10 @@ def test_dit_linear_layers_lower_to_flattened_tensor_core_ops(monkeypatch):
     p = Program(torch.device("cpu"), B, 1, cabi.MATH_BF16_TC)
     lower_denoiser(p, net, View(p.buf(B, L, 29), L, 29), (L, 29), True, 0)
     tc = [op.u.conv for op in p.ops if op.kind == cabi.OP_CONV and op.u.conv.math == cabi.MATH_BF16_TC]
-    assert sorted((c.C_in, c.C_out) for c in tc) == sorted([(320, 960), (320, 320), (320, 1280), (1280, 320)] * 2)
+    # per block QKV / out-proj / fc1 / fc2, plus the input projection (x_t padded 29 -> 32 channels) and the 29-wide output head
+    assert sorted((c.C_in, c.C_out) for c in tc) == sorted([(320, 960), (320, 320), (320, 1280), (1280, 320)] * 2 + [(32, 320), (320, 29)])
     assert all(c.batch == B * L and c.L_in == 1 and c.sample_row_div == L for c in tc)
+    assert [op.kind for op in p.ops].count(cabi.OP_CAST) == 1
     assert all(op.u.lnmod.out_dtype == cabi.BF16 for op in p.ops if op.kind == cabi.OP_LNMOD)
     assert all(op.u.attn.out_dtype == cabi.BF16 for op in p.ops if op.kind == cabi.OP_ATTN)
     g = torch.Generator().manual_seed(2)
