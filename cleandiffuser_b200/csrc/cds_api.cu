@@ -108,6 +108,8 @@ int validate(const cds_op& op, Step* out) {
       int hd = a.C / a.heads;
       if (hd != 16 && hd != 32 && hd != 64) return fail(CDS_ERR_UNSUPPORTED, "attn: head_dim %d", hd);
       if ((size_t)a.L * hd * 8 > 200 * 1024) return fail(CDS_ERR_UNSUPPORTED, "attn: L=%d too long", a.L);
+      if (a.qkv_dtype == CDS_BF16 && (hd != 32 || a.L > cds::kAttnMaxL || a.C % 8 != 0 || ((uintptr_t)a.qkv % 16) != 0))
+        return fail(CDS_ERR_UNSUPPORTED, "attn: bf16 q/k/v needs head_dim 32, L <= %d, 16-byte aligned rows", cds::kAttnMaxL);
       return CDS_OK;
     }
     case CDS_OP_PREP: {
@@ -178,6 +180,7 @@ int preload_kernels() {
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<16>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<32>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<64>));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_mma_hd32_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::solver_update_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cm_prep_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cast_pad_kernel));

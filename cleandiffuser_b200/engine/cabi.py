@@ -55,7 +55,7 @@ class LnModOp(C.Structure):
 
 class AttnOp(C.Structure):
     _fields_ = [("batch", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32),
-                ("qkv", _f32p), ("out", C.c_void_p), ("out_dtype", C.c_int32)]
+                ("qkv", _f32p), ("out", C.c_void_p), ("out_dtype", C.c_int32), ("qkv_dtype", C.c_int32)]
 
 
 class PrepOp(C.Structure):

@@ -279,7 +279,7 @@ class Program:
         op.kind = cabi.OP_ATTN
         a = op.u.attn
         a.batch, a.L, a.C, a.heads = self.rows, out.L, out.C, int(heads)
-        a.qkv, a.out, a.out_dtype = qkv.ptr, out.ptr, out.dtype
+        a.qkv, a.out, a.out_dtype, a.qkv_dtype = qkv.ptr, out.ptr, out.dtype, qkv.dtype
         self.ops.append(op)
 
 
@@ -539,7 +539,9 @@ def lower_dit(p: Program, net: DiT1d, x: View, horizon: int, has_cond: bool, in_
     # attention output, the MLP hidden) has the program's activation dtype: bf16 on tensor-core programs, where those Linear
     # layers (97 % of DiT1d's FLOPs outside attention) run on tcgen05 over the flattened token stream
     f32 = torch.float32
-    X, QKV = p.act(L, d, f32), p.act(L, 3 * d, f32)
+    X = p.act(L, d, f32)
+    # head_dim 32 (every pipeline) and L <= 128: attention runs on tensor cores (mma.sync, bf16 q/k/v); otherwise fp32 CUDA cores
+    QKV = p.act(L, 3 * d) if (d // heads == 32 and L <= 128) else p.act(L, 3 * d, f32)
     Y, ATT, HID = p.act(L, d), p.act(L, d), p.act(L, 4 * d)
     if p.math == cabi.MATH_BF16_TC and x.t.dtype == torch.float32 and x.lstride == x.C and x.bstride == L * x.C:
         # x_t enters as a 32-channel-padded bf16 copy (kept fresh by the solver update, like the UNets' hand-over)

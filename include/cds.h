@@ -119,8 +119,9 @@ typedef struct cds_lnmod_op {
 /* qkv dense (batch, L, 3*C) with [q | k | v] column blocks, heads split C evenly; out dense (batch, L, C) */
 typedef struct cds_attn_op {
   int32_t batch, L, C, heads;
-  const float* qkv; void* out;
+  const void* qkv; void* out;
   int32_t out_dtype;                            /* cds_dtype of out */
+  int32_t qkv_dtype;                            /* cds_dtype of qkv: bf16 (head_dim 32, L <= 128) runs on tensor cores (mma.sync) */
 } cds_attn_op;
 
 /* dense fp32 (batch, L, C_in) -> dense bf16 (batch, L, C_out), channels [C_in, C_out) zero: gives x_t the 32-channel

@@ -143,7 +143,7 @@ def run_lnmod(m):
 
 def run_attn(a):
     hd = a.C // a.heads
-    qkv = _arr(a.qkv, (a.batch, a.L, 3, a.heads, hd), (a.L * 3 * a.C, 3 * a.C, a.C, hd, 1)).astype(np.float64)
+    qkv = _load(a.qkv, (a.batch, a.L, 3, a.heads, hd), (a.L * 3 * a.C, 3 * a.C, a.C, hd, 1), a.qkv_dtype).astype(np.float64)
     q, k, v = (qkv[:, :, i].transpose(0, 2, 1, 3) for i in range(3))        # (b, h, L, hd)
     s = q @ k.transpose(0, 1, 3, 2) / np.sqrt(hd)
     s = np.exp(s - s.max(-1, keepdims=True))
