@@ -80,6 +80,10 @@ template <int ACT>
 __device__ __forceinline__ float tc_act(int act, float x) {
   if constexpr (ACT == CDS_ACT_NONE) return x;
   else if constexpr (ACT == CDS_ACT_MISH) return fast_mish(x);
+  else if constexpr (ACT == CDS_ACT_GELU_TANH) {          // 0.5 x (1 + tanh(u)) = x sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)
+    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    return x * fast_sigmoid(2.f * u);
+  }
   else {
     switch (act) {
       case CDS_ACT_MISH: return fast_mish(x);
@@ -518,6 +522,81 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         using T0 = std::integral_constant<int, 0>;
         if (film == 1) { if (add_res) fast_tiles(T1{}, std::true_type{}); else fast_tiles(T1{}, std::false_type{}); }
         else { if (add_res) fast_tiles(T0{}, std::true_type{}); else fast_tiles(T0{}, std::false_type{}); }
+      }
+    }
+    // ---- plain lane: no GroupNorm, no FiLM, no residual -- bias + one activation + store (the resampling convs of the UNets,
+    // DiT1d's QKV and GELU Linear layers).  Same idea as the fast lane: dispatch once, strength-reduced addressing, fixed dtype.
+    const bool plain_ok = N >= 32 && !HAS_RES && !has_gn && film == 0 && !smp && !add_res && io_vec && p.res_batch_mod == 0 &&
+                          (p.act == CDS_ACT_NONE || p.act == CDS_ACT_GELU_TANH);
+    auto plain_tiles = [&](auto act_tag, auto bf16_tag) {
+      constexpr int ACT = decltype(act_tag)::value;
+      constexpr bool OUT_BF16 = decltype(bf16_tag)::value;
+      const int T_ = 128 >> p.log2L;
+      const int tb = m >> p.log2L, l = m & (p.L - 1);
+      const int nct = SPLIT > 1 ? SPLIT : p.n_col_tiles;
+      const int batch_ = p.batch, phases_ = p.phases, C_out_ = p.C_out;
+      const int64_t out_bs = p.out_bstride, out_ls = p.out_lstride;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it % Cfg::kAccBufs;
+        const uint32_t use = (uint32_t)(it / Cfg::kAccBufs);
+        const int n_off = (tile % nct) * N;
+        const int sc_off = SPLIT > 1 ? n_off : 0;
+        if (SPLIT == 1 && nct > 1) {                   // runtime column tiles: this tile's constants
+          ptx::named_bar_sync(1, kTcEpiThreads);
+          stage_cols(n_off);
+          ptx::named_bar_sync(1, kTcEpiThreads);
+        }
+        const int b = (tile / nct) * T_ + tb;
+        const bool valid = b < batch_;
+        const uint32_t t_row = t_lane + (uint32_t)(buf * Cfg::kColsPerTile);
+        ptx::mbar_wait(&tmem_full_bar[buf], use & 1);
+        ptx::tc_fence_after_sync();
+        if (threadIdx.x == 0 && it < 14) CDS_TRACE(10 + 4 * it, clock64());
+#pragma unroll 1
+        for (int ch = 0; ch < NH / 16; ++ch) {
+          const int n0 = col0 + ch * 16;
+          const int ng0 = n_off + n0;                               // layer column (phase-major for transposed convs)
+          const int phase = (phases_ == 1 || ng0 < C_out_) ? 0 : 1;
+          const int c0 = ng0 - phase * C_out_;
+          float v[16];
+          ptx::tmem_ld<16>(t_row + (uint32_t)n0, v);
+          const float4* b4 = reinterpret_cast<const float4*>(&s_col[0][sc_off + n0]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 bb = b4[k];
+            v[4 * k] = tc_act<ACT>(ACT, v[4 * k] + bb.x); v[4 * k + 1] = tc_act<ACT>(ACT, v[4 * k + 1] + bb.y);
+            v[4 * k + 2] = tc_act<ACT>(ACT, v[4 * k + 2] + bb.z); v[4 * k + 3] = tc_act<ACT>(ACT, v[4 * k + 3] + bb.w);
+          }
+          if (valid) {
+            const int64_t oo = (int64_t)b * out_bs + (int64_t)(l * phases_ + phase) * out_ls + c0;
+            if constexpr (OUT_BF16) {
+              uint32_t w[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) { __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]); w[k] = *reinterpret_cast<uint32_t*>(&h2); }
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + oo);
+              op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oo);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) op[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            }
+          }
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+        if (threadIdx.x == 0 && it < 14) CDS_TRACE(11 + 4 * it, clock64());
+      }
+    };
+    if constexpr (N >= 32 && !HAS_RES) {
+      if (plain_ok && it == 0) {
+        using G = std::integral_constant<int, CDS_ACT_GELU_TANH>;
+        using Z = std::integral_constant<int, CDS_ACT_NONE>;
+        const bool ob = p.out_dtype == CDS_BF16;
+        if (p.act == CDS_ACT_GELU_TANH) { if (ob) plain_tiles(G{}, std::true_type{}); else plain_tiles(G{}, std::false_type{}); }
+        else { if (ob) plain_tiles(Z{}, std::true_type{}); else plain_tiles(Z{}, std::false_type{}); }
       }
     }
     // generic lane (everything else; a no-op after the fast lane: `it` then already counts all of this CTA's tiles)

@@ -172,29 +172,55 @@ static __global__ void __launch_bounds__(256) cm_prep_kernel(const cds_prep_op p
   }
 }
 
-// one warp per token row: LayerNorm (biased variance, no affine) then x*(1+scale)+shift.  8 B / element
+// one warp per token row: LayerNorm (biased variance, no affine) then x*(1+scale)+shift.  8 B / element (6 with bf16 out).
+// Rows of up to 32*kLnRegs channels are held in registers: ONE pass over global memory (two-pass variance on the registers).
+constexpr int kLnRegs = 16;
 static __global__ void __launch_bounds__(256) ln_modulate_kernel(const cds_lnmod_op p) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t n_rows = (int64_t)p.batch * p.L;
+  const bool in_regs = p.C <= 32 * kLnRegs;
+  const float inv_c = 1.f / (float)p.C;
   for (int64_t r = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_rows;
        r += (int64_t)gridDim.x * warps_per_block) {
     const float* src = p.in + r * p.C;
-    float s = 0.f;
-    for (int c = lane; c < p.C; c += 32) s += src[c];
-    const float mean = warp_sum(s) / (float)p.C;
-    float q = 0.f;
-    for (int c = lane; c < p.C; c += 32) { float d = src[c] - mean; q = fmaf(d, d, q); }
-    const float rstd = rsqrtf(warp_sum(q) / (float)p.C + p.eps);
     const int b = (int)(r / p.L);
     const float* sh = p.shift + (int64_t)b * p.mod_bstride;
     const float* sc = p.scale + (int64_t)b * p.mod_bstride;
+    float x[kLnRegs];
+    float s = 0.f;
+    if (in_regs) {
+#pragma unroll
+      for (int k = 0; k < kLnRegs; ++k) { const int c = lane + 32 * k; x[k] = c < p.C ? src[c] : 0.f; s += x[k]; }
+    } else {
+      for (int c = lane; c < p.C; c += 32) s += src[c];
+    }
+    const float mean = warp_sum(s) * inv_c;
+    float q = 0.f;
+    if (in_regs) {
+#pragma unroll
+      for (int k = 0; k < kLnRegs; ++k) { const float d = (lane + 32 * k < p.C) ? x[k] - mean : 0.f; q = fmaf(d, d, q); }
+    } else {
+      for (int c = lane; c < p.C; c += 32) { float d = src[c] - mean; q = fmaf(d, d, q); }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_c + p.eps);
+    auto value = [&](int c, float xv) { return fmaf((xv - mean) * rstd, 1.f + sc[c], sh[c]); };
     if (p.out_dtype == CDS_BF16) {
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + r * p.C;
-      for (int c = lane; c < p.C; c += 32) dst[c] = __float2bfloat16_rn(fmaf((src[c] - mean) * rstd, 1.f + sc[c], sh[c]));
+      if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < kLnRegs; ++k) { const int c = lane + 32 * k; if (c < p.C) dst[c] = __float2bfloat16_rn(value(c, x[k])); }
+      } else {
+        for (int c = lane; c < p.C; c += 32) dst[c] = __float2bfloat16_rn(value(c, src[c]));
+      }
     } else {
       float* dst = reinterpret_cast<float*>(p.out) + r * p.C;
-      for (int c = lane; c < p.C; c += 32) dst[c] = fmaf((src[c] - mean) * rstd, 1.f + sc[c], sh[c]);
+      if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < kLnRegs; ++k) { const int c = lane + 32 * k; if (c < p.C) dst[c] = value(c, x[k]); }
+      } else {
+        for (int c = lane; c < p.C; c += 32) dst[c] = value(c, src[c]);
+      }
     }
   }
 }
