@@ -270,3 +270,28 @@ def test_chiunet_full_size_on_tensor_cores(monkeypatch):
     lower_denoiser(p, net, View(p.buf(B, 16, 7), 16, 7), (16, 7), True, 0)
     convs = [op.u.conv for op in p.ops if op.kind == cabi.OP_CONV and op.u.conv.taps > 1]
     assert len(convs) >= 28 and all(c.math == cabi.MATH_BF16_TC for c in convs), [(c.C_in, c.C_out, c.math) for c in convs]
+
+
+def test_dit_full_size_on_tensor_cores(monkeypatch):
+    """cfg4's backbone as the DD pipeline builds it (d_model 320, 10 heads of 32, depth 2, L = 100 tokens -- not a multiple of
+    the 16-row MMA tile: padded keys are masked, padded queries dropped): Linear layers on tcgen05 over the flattened token
+    stream, attention on mma.sync, checked against the module's own fp32 forward on the GPU."""
+    monkeypatch.setenv("CDS_MATH", "bf16")
+    from cleandiffuser_b200.engine.lower import Program, View, lower_denoiser
+    from cleandiffuser_b200.nn_diffusion import DiT1d
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = load_synth(DiT1d(29, emb_dim=128, d_model=320, n_heads=10, depth=2, timestep_emb_type="fourier"), seed=0).eval().to(DEV)
+    g = torch.Generator().manual_seed(2)
+    B, L = 37, 100                                                  # 3700 token rows: ragged last 128-row tile
+    x, cond = torch.randn(B, L, 29, generator=g).to(DEV), torch.randn(B, 128, generator=g).to(DEV)
+    t = torch.tensor([0.37], device=DEV)
+    with torch.no_grad():
+        want = net(x, t.expand(B), cond)
+    y = runtime.engine_forward(net, x, t, cond)
+    err = (y - want).abs()
+    assert torch.isfinite(y).all()
+    assert err.max().item() < 0.15 and err.mean().item() < 0.02, (err.max().item(), err.mean().item())
+    p = Program(torch.device(DEV), B, 1, cabi.MATH_BF16_TC)
+    lower_denoiser(p, net, View(p.buf(B, L, 29), L, 29), (L, 29), True, 0)
+    assert sum(1 for op in p.ops if op.kind == cabi.OP_CONV and op.u.conv.math == cabi.MATH_BF16_TC) == 10
+    assert all(op.u.attn.qkv_dtype == cabi.BF16 for op in p.ops if op.kind == cabi.OP_ATTN)
