@@ -211,9 +211,15 @@ def main():
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
     dist = None
+    saved_stdout = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the ONE JSON line
+        # keep stdout to the ONE JSON line: NCCL prints its version banner to stdout when NCCL_DEBUG is set in the environment
+        # (communicators are created lazily, at the first collective) -> everything written to fd 1 until the result line
+        # goes to stderr instead
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     from cleandiffuser_b200.engine import runtime
@@ -362,6 +368,10 @@ def main():
                         "sample": f"one full 100-step sample() on {sb} trajectories ({sec:.1f} s), oracle port of the "
                                   f"reference algorithm on torch CPU fp32"}
 
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
         line = {"metric": "sampled trajectories/sec (H=32, 100 DDPM steps)", "value": value, "unit": "trajectories/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
