@@ -40,7 +40,7 @@ struct Step {            // one validated operator + its kernel choice
   bool tc = false;       // tensor-core conv: tensor maps + launch geometry prepared at append time
   cds::ConvTcLaunch tcl;
   int branch = 0;        // (op.flags >> 8) & 0xff
-  bool skip = false;     // solver update that was fused into the preceding conv's epilogue (finalize)
+  bool skip = false;     // operator folded into another launch by a finalize-time peephole (none at present)
   bool ps = false;       // ... served by the position-sliced kernel (short sequences, conv_ps.cuh)
   cds::ConvPsLaunch psl;
 };
@@ -321,7 +321,7 @@ int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
 static bool advance_fused(const cds_plan* p) {
   if (p->n_branches > 1) return false;             // several updates per iteration: a one-thread kernel advances after the join
   for (int i = (int)p->steps.size() - 1; i >= 0; --i)
-    if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) return p->steps[i].op.kind == CDS_OP_UPDATE;   // also when that update is `skip`
+    if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) return p->steps[i].op.kind == CDS_OP_UPDATE;
   return false;
 }
 
@@ -341,7 +341,7 @@ static int enqueue_iteration(cds_plan* p, cudaStream_t st) {
     for (int i = 0; i < (int)p->steps.size(); ++i) if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) last = i;
     for (int i = 0; i < (int)p->steps.size(); ++i) {
       const Step& s = p->steps[i];
-      if ((s.op.flags & CDS_OPF_ONCE) || s.skip) continue;      // a skipped update runs (and advances) inside the head's epilogue
+      if ((s.op.flags & CDS_OPF_ONCE) || s.skip) continue;
       int rc = launch(s, p->d_iter, p->sm_count, st, (fused && i == last) ? p->d_iter : nullptr);
       if (rc != CDS_OK) return rc;
     }
