@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128) attention_f32_kernel(const cds_attn_op p)
     } else {
       float* dst = reinterpret_cast<float*>(p.out) + o_off;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) dst[d] = o[d] * inv;
+      for (int d = 0; d < HD; ++d) dst[d] = f32_for_store(o[d] * inv, p.out_dtype);
     }
   }
 }
@@ -185,8 +185,9 @@ __global__ void __launch_bounds__(128) attention_mma_hd32_kernel(const cds_attn_
         if (r1 < L) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * L + r1) * p.C + col) = pack_bf16x2(o[dn][2] * i1, o[dn][3] * i1);
       } else {
         float* out = reinterpret_cast<float*>(p.out);
-        if (r0 < L) { float* d = out + ((int64_t)b * L + r0) * p.C + col; d[0] = o[dn][0] * i0; d[1] = o[dn][1] * i0; }
-        if (r1 < L) { float* d = out + ((int64_t)b * L + r1) * p.C + col; d[0] = o[dn][2] * i1; d[1] = o[dn][3] * i1; }
+        const int od = p.out_dtype;
+        if (r0 < L) { float* d = out + ((int64_t)b * L + r0) * p.C + col; d[0] = f32_for_store(o[dn][0] * i0, od); d[1] = f32_for_store(o[dn][1] * i0, od); }
+        if (r1 < L) { float* d = out + ((int64_t)b * L + r1) * p.C + col; d[0] = f32_for_store(o[dn][2] * i1, od); d[1] = f32_for_store(o[dn][3] * i1, od); }
       }
     }
   }

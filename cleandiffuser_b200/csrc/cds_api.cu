@@ -65,7 +65,7 @@ int validate(const cds_op& op, Step* out) {
       if (c.groups > 0 && (!c.gn_gamma || !c.gn_beta)) return fail(CDS_ERR_INVALID, "conv: GroupNorm without affine");
       if (c.res_w && (!c.res_in || c.res_C <= 0)) return fail(CDS_ERR_INVALID, "conv: shortcut conv without input");
       if (c.res_w && (c.stride != 1 || c.phases != 1)) return fail(CDS_ERR_INVALID, "conv: shortcut conv needs stride 1");
-      if (c.math == CDS_MATH_BF16_TC) {
+      if (c.math == CDS_MATH_BF16_TC || c.math == CDS_MATH_TF32_TC) {
         if (!cds::conv_tc_eligible(c))
           return fail(CDS_ERR_INVALID, "conv: op is not eligible for the tensor-core kernel (ask cds_conv_tc_supported)");
         if (cds::conv_ps_eligible(c)) {
@@ -119,7 +119,8 @@ int validate(const cds_op& op, Step* out) {
     }
     case CDS_OP_CAST: {
       const cds_cast_op& k = op.u.cast;
-      if (k.batch <= 0 || k.L <= 0 || k.C_in <= 0 || k.C_out < k.C_in || (k.C_out & 1) || !k.in || !k.out)
+      if (k.batch <= 0 || k.L <= 0 || k.C_in <= 0 || k.C_out < k.C_in || (k.C_out & 1) || !k.in || !k.out ||
+          (k.out_dtype != CDS_F32 && k.out_dtype != CDS_BF16 && k.out_dtype != CDS_TF32))
         return fail(CDS_ERR_INVALID, "cast: bad arguments");
       return CDS_OK;
     }
@@ -237,7 +238,7 @@ const char* cds_last_error(void) { return g_err.c_str(); }
 int cds_conv_tc_supported(const cds_conv_op* op) {
   if (!op) return 0;
   cds_conv_op c = *op;
-  c.math = CDS_MATH_BF16_TC;
+  if (c.math != CDS_MATH_TF32_TC) c.math = CDS_MATH_BF16_TC;
   return cds::conv_tc_eligible(c) ? 1 : 0;
 }
 

@@ -51,6 +51,11 @@ __device__ __forceinline__ float apply_act(int act, float x) {
   }
 }
 
+// fp32 -> nearest TF32-representable fp32 (ties away from zero): two integer ops
+__device__ __forceinline__ float round_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// value as an operator stores it into a tensor of cds_dtype `dtype` (fp32 storage: CDS_F32 as is, CDS_TF32 rounded)
+__device__ __forceinline__ float f32_for_store(float x, int dtype) { return dtype == CDS_TF32 ? round_tf32(x) : x; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -61,11 +61,15 @@ struct ConvPsCfg {
   static_assert(kSmemBytes <= 227 * 1024, "stage ring does not fit");
 };
 
-template <int KC, int N, int P, bool HAS_RES>
+// TF32: fp32 activations / weights read as TF32 (kind::tf32); KC stays the row width in bf16-equivalents (row bytes / 2), see
+// conv_tc.cuh
+template <int KC, int N, int P, bool HAS_RES, bool TF32>
 __global__ void __launch_bounds__(kPsThreads, 1)
 conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ iter_ptr) {
   using Cfg = ConvPsCfg<KC, N, P, HAS_RES>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int KE = TF32 ? KC / 2 : KC;            // channels per chunk
+  constexpr int kActDtype = TF32 ? CDS_TF32 : CDS_BF16;      // output: fp32 storage rounded to TF32 / bf16
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
@@ -112,9 +116,9 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
         uint8_t* sb = smem_al + s * Cfg::kStageBytes + P * Cfg::kATile;
         if (!HAS_RES || c < n_main) {
           for (int j = 0; j < p.taps; ++j)
-            ptx::tma_load_2d(sb + (p.taps - 1 - j) * Cfg::kBTile, &p.tm_b, &full_bar[s], c * KC, j * p.C_out + n_off);   // slot = taps-1-j
+            ptx::tma_load_2d(sb + (p.taps - 1 - j) * Cfg::kBTile, &p.tm_b, &full_bar[s], c * KE, j * p.C_out + n_off);   // slot = taps-1-j
         } else {
-          ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], (c - n_main) * KC, n_off);
+          ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], (c - n_main) * KE, n_off);
         }
       };
       // weights do not depend on the previous kernel: arm the first ring fill and fetch them before the dependency wait
@@ -136,8 +140,8 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
         }
         uint8_t* sa = smem_al + s * Cfg::kStageBytes;
         for (int l = 0; l < P; ++l) {
-          if (is_main) ptx::tma_load_3d(sa + l * Cfg::kATile, &p.tm_a, &full_bar[s], c * KC, l, a_b0);
-          else ptx::tma_load_3d(sa + l * Cfg::kATile, &p.tm_a2, &full_bar[s], (c - n_main) * KC, l, r_b0);
+          if (is_main) ptx::tma_load_3d(sa + l * Cfg::kATile, &p.tm_a, &full_bar[s], c * KE, l, a_b0);
+          else ptx::tma_load_3d(sa + l * Cfg::kATile, &p.tm_a2, &full_bar[s], (c - n_main) * KE, l, r_b0);
         }
       }
       CDS_TRACE(8, clock64());
@@ -145,7 +149,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
   } else if (warp == kPsWarpMma) {
     // ===================================== MMA issuer =====================================
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, N);
+      constexpr uint32_t idesc = ptx::make_idesc<TF32>(128, N);
       uint32_t started = 0;                           // bit l': accumulator D_l' has received its first MMA
       for (int c = 0; c < n_chunks; ++c) {
         const int s = c % kStages;
@@ -166,17 +170,17 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
             const int hi = (l + p.pad) < (P - 1) ? (l + p.pad) : (P - 1);
             const int slot0 = p.taps - 1 - (l - lo + p.pad);              // slot of the tap that feeds output position lo
             const uint64_t db = ptx::make_kmajor_desc<Cfg::kRowBytes>(sb + slot0 * Cfg::kBTile);
-            const uint32_t idesc_m = ptx::make_idesc_bf16(128, (hi - lo + 1) * N);
+            const uint32_t idesc_m = ptx::make_idesc<TF32>(128, (hi - lo + 1) * N);
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
               if (c == 0 && k == 0) {
                 for (int lp = lo; lp <= hi; ++lp) {
                   const uint64_t dbj = ptx::make_kmajor_desc<Cfg::kRowBytes>(sb + (slot0 + lp - lo) * Cfg::kBTile);
-                  ptx::umma_bf16(tmem_base + (uint32_t)(lp * N), da, dbj, idesc, (started >> lp) & 1u);
+                  ptx::umma<TF32>(tmem_base + (uint32_t)(lp * N), da, dbj, idesc, (started >> lp) & 1u);
                   started |= 1u << lp;
                 }
               } else {
-                ptx::umma_bf16(tmem_base + (uint32_t)(lo * N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_m, 1u);
+                ptx::umma<TF32>(tmem_base + (uint32_t)(lo * N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_m, 1u);
               }
             }
           }
@@ -187,7 +191,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
             const uint64_t da = ptx::make_kmajor_desc<Cfg::kRowBytes>(sa + l * Cfg::kATile);
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k)
-              ptx::umma_bf16(tmem_base + (uint32_t)(P * N + l * N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+              ptx::umma<TF32>(tmem_base + (uint32_t)(P * N + l * N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                              (uint32_t)(c > n_main || k > 0));
           }
         }
@@ -278,7 +282,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
         float resv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) resv[j] = 0.f;
-        if (valid) load_row<16>(p.res, (int64_t)rb * p.res_bstride + (int64_t)lp * p.res_lstride + n_off + n0, CDS_BF16, resv);
+        if (valid) load_row<16>(p.res, (int64_t)rb * p.res_bstride + (int64_t)lp * p.res_lstride + n_off + n0, kActDtype, resv);
 #pragma unroll
         for (int j = 0; j < 16; ++j) addv[j] += resv[j];
       }
@@ -310,7 +314,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
         o[4 * k + 2] = mish_fma(fmaf(fmaf(v[4 * k + 2] + bb.z, ga, gc), gm.z, be.z), addv[4 * k + 2]);
         o[4 * k + 3] = mish_fma(fmaf(fmaf(v[4 * k + 3] + bb.w, ga, gc), gm.w, be.w), addv[4 * k + 3]);
       }
-      if (valid) store_row<16>(p.out, (int64_t)b * p.out_bstride + (int64_t)lp * p.out_lstride + n_off + n0, CDS_BF16, o);
+      if (valid) store_row<16>(p.out, (int64_t)b * p.out_bstride + (int64_t)lp * p.out_lstride + n_off + n0, kActDtype, o);
     }
     if (threadIdx.x == 0) { CDS_TRACE(11, clock64()); CDS_TRACE(5, 1LL); }
     ptx::tc_fence_before_sync();
@@ -343,7 +347,8 @@ inline bool conv_ps_eligible(const cds_conv_op& c) {
   if (c.groups != 8 || c.act != CDS_ACT_MISH || conv_ps_width(c) == 0) return false;
   if (c.C_in % 64 != 0 || (c.res_w && c.res_C % 64 != 0)) return false;
   if (c.bias.sample || c.scale.step || c.scale.sample || c.shift.sample) return false;
-  if (c.out_dtype != CDS_BF16 || (c.res && c.res_dtype != CDS_BF16)) return false;
+  if (conv_is_tf32(c)) { if (c.out_dtype != CDS_TF32 || (c.res && c.res_dtype == CDS_BF16)) return false; }
+  else if (c.out_dtype != CDS_BF16 || (c.res && c.res_dtype != CDS_BF16)) return false;
   if (c.in_batch_mod > 0 && c.in_batch_mod % 128 != 0) return false;
   if (c.res_batch_mod > 0 && c.res_batch_mod % 128 != 0) return false;
   const char* env = getenv("CDS_PS");
@@ -353,6 +358,7 @@ inline bool conv_ps_eligible(const cds_conv_op& c) {
 
 struct ConvPsLaunch {
   ConvPsParams prm;
+  bool tf32 = false;
   int n = 0;
   bool has_res = false;
   dim3 grid;
@@ -363,34 +369,37 @@ inline bool conv_ps_prepare(const cds_conv_op& c, ConvPsLaunch* out) {
   memset(&L.prm, 0, sizeof(L.prm));
   ConvPsParams& p = L.prm;
   constexpr int kc = kPsKC;
+  const bool tf32 = conv_is_tf32(c);
+  const int ke = tf32 ? kc / 2 : kc;
+  L.tf32 = tf32;
   L.n = conv_ps_width(c);
   L.has_res = c.res_w != nullptr;
   const uint64_t in_b = c.in_batch_mod > 0 ? (uint64_t)c.in_batch_mod : (uint64_t)c.batch;
   {
     uint64_t dims[3] = {(uint64_t)c.C_in, (uint64_t)c.L_in, in_b};
     uint64_t str[2] = {(uint64_t)c.in_lstride, (uint64_t)c.in_bstride};
-    uint32_t box[3] = {(uint32_t)kc, 1u, 128u};
-    if (!encode_bf16_map(&p.tm_a, c.in, 3, dims, str, box, kc)) return false;
+    uint32_t box[3] = {(uint32_t)ke, 1u, 128u};
+    if (!encode_act_map(&p.tm_a, c.in, 3, dims, str, box, kc, tf32)) return false;
   }
   {
     uint64_t dims[2] = {(uint64_t)c.C_in, (uint64_t)c.taps * c.C_out};
     uint64_t str[1] = {(uint64_t)c.C_in};
-    uint32_t box[2] = {(uint32_t)kc, (uint32_t)L.n};
-    if (!encode_bf16_map(&p.tm_b, c.w, 2, dims, str, box, kc)) return false;
+    uint32_t box[2] = {(uint32_t)ke, (uint32_t)L.n};
+    if (!encode_act_map(&p.tm_b, c.w, 2, dims, str, box, kc, tf32)) return false;
   }
   if (L.has_res) {
     const uint64_t r_b = c.res_batch_mod > 0 ? (uint64_t)c.res_batch_mod : (uint64_t)c.batch;
     uint64_t dims[3] = {(uint64_t)c.res_C, (uint64_t)c.L_out, r_b};
     uint64_t str[2] = {(uint64_t)c.res_in_lstride, (uint64_t)c.res_in_bstride};
-    uint32_t box[3] = {(uint32_t)kc, 1u, 128u};
-    if (!encode_bf16_map(&p.tm_a2, c.res_in, 3, dims, str, box, kc)) return false;
+    uint32_t box[3] = {(uint32_t)ke, 1u, 128u};
+    if (!encode_act_map(&p.tm_a2, c.res_in, 3, dims, str, box, kc, tf32)) return false;
     uint64_t d2[2] = {(uint64_t)c.res_C, (uint64_t)c.C_out};
     uint64_t s2[1] = {(uint64_t)c.res_C};
-    uint32_t b2[2] = {(uint32_t)kc, (uint32_t)L.n};
-    if (!encode_bf16_map(&p.tm_b2, c.res_w, 2, d2, s2, b2, kc)) return false;
+    uint32_t b2[2] = {(uint32_t)ke, (uint32_t)L.n};
+    if (!encode_act_map(&p.tm_b2, c.res_w, 2, d2, s2, b2, kc, tf32)) return false;
   }
   p.batch = c.batch; p.C_out = c.C_out; p.taps = c.taps; p.pad = c.pad;
-  p.kchunks = c.C_in / kc; p.kchunks2 = L.has_res ? c.res_C / kc : 0;
+  p.kchunks = c.C_in / ke; p.kchunks2 = L.has_res ? c.res_C / ke : 0;
   p.n_tiles = c.C_out / L.n;
   p.in_batch_mod = c.in_batch_mod; p.res_batch_mod = c.res_batch_mod;
   p.bias = c.bias; p.shift = c.shift;
@@ -401,18 +410,18 @@ inline bool conv_ps_prepare(const cds_conv_op& c, ConvPsLaunch* out) {
   return true;
 }
 
-template <int N, bool HAS_RES>
+template <int N, bool HAS_RES, bool TF32>
 cudaError_t conv_ps_launch_t(const ConvPsLaunch& L, const int* iter_ptr, cudaStream_t st) {
   using Cfg = ConvPsCfg<kPsKC, N, kPsPositions, HAS_RES>;
   static bool attr = false;
   static bool pdl = true;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_ps_kernel<kPsKC, N, kPsPositions, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_ps_kernel<kPsKC, N, kPsPositions, HAS_RES, TF32>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     if (getenv("CDS_DEBUG"))
-      fprintf(stderr, "[cds] conv_ps<%d,%d,%d,%d>: smem %d B, tmem %u columns\n", kPsKC, N, kPsPositions, (int)HAS_RES, Cfg::kSmemBytes,
-              Cfg::kTmemCols);
+      fprintf(stderr, "[cds] conv_ps<%d,%d,%d,%d,%s>: smem %d B, tmem %u columns\n", kPsKC, N, kPsPositions, (int)HAS_RES,
+              TF32 ? "tf32" : "bf16", Cfg::kSmemBytes, Cfg::kTmemCols);
     const char* pdl_env = getenv("CDS_PDL");
     pdl = !(pdl_env && pdl_env[0] == '0');
     attr = true;
@@ -425,35 +434,38 @@ cudaError_t conv_ps_launch_t(const ConvPsLaunch& L, const int* iter_ptr, cudaStr
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv_ps_kernel<kPsKC, N, kPsPositions, HAS_RES>, prm, iter_ptr);
+  return cudaLaunchKernelEx(&cfg, conv_ps_kernel<kPsKC, N, kPsPositions, HAS_RES, TF32>, prm, iter_ptr);
 }
-template <int N, bool HAS_RES>
+template <int N, bool HAS_RES, bool TF32>
 cudaError_t conv_ps_preload_t() {
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, conv_ps_kernel<kPsKC, N, kPsPositions, HAS_RES>);
+  return cudaFuncGetAttributes(&a, conv_ps_kernel<kPsKC, N, kPsPositions, HAS_RES, TF32>);
 }
 
+// X(N, HAS_RES, TF32) over every instantiation
+#define CDS_PS_VARIANTS(X)                                                                   \
+  X(32, false, false) X(32, true, false) X(64, false, false) X(64, true, false)             \
+  X(32, false, true) X(32, true, true) X(64, false, true) X(64, true, true)
+
 #ifndef CDS_PS_INSTANTIATE
-extern template cudaError_t conv_ps_launch_t<32, false>(const ConvPsLaunch&, const int*, cudaStream_t);
-extern template cudaError_t conv_ps_launch_t<32, true>(const ConvPsLaunch&, const int*, cudaStream_t);
-extern template cudaError_t conv_ps_launch_t<64, false>(const ConvPsLaunch&, const int*, cudaStream_t);
-extern template cudaError_t conv_ps_launch_t<64, true>(const ConvPsLaunch&, const int*, cudaStream_t);
-extern template cudaError_t conv_ps_preload_t<32, false>();
-extern template cudaError_t conv_ps_preload_t<32, true>();
-extern template cudaError_t conv_ps_preload_t<64, false>();
-extern template cudaError_t conv_ps_preload_t<64, true>();
+#define CDS_PS_EXTERN(N_, R_, T_)                                                                                 \
+  extern template cudaError_t conv_ps_launch_t<N_, R_, T_>(const ConvPsLaunch&, const int*, cudaStream_t);        \
+  extern template cudaError_t conv_ps_preload_t<N_, R_, T_>();
+CDS_PS_VARIANTS(CDS_PS_EXTERN)
+#undef CDS_PS_EXTERN
 
 inline cudaError_t conv_ps_launch(const ConvPsLaunch& L, const int* iter_ptr, cudaStream_t st) {
-  if (L.n == 32) return L.has_res ? conv_ps_launch_t<32, true>(L, iter_ptr, st) : conv_ps_launch_t<32, false>(L, iter_ptr, st);
-  if (L.n == 64) return L.has_res ? conv_ps_launch_t<64, true>(L, iter_ptr, st) : conv_ps_launch_t<64, false>(L, iter_ptr, st);
+#define CDS_PS_CASE(N_, R_, T_) if (L.n == N_ && L.has_res == R_ && L.tf32 == T_) return conv_ps_launch_t<N_, R_, T_>(L, iter_ptr, st);
+  CDS_PS_VARIANTS(CDS_PS_CASE)
+#undef CDS_PS_CASE
   return cudaErrorInvalidValue;
 }
 inline cudaError_t conv_ps_preload_all() {
   cudaError_t e;
-  if ((e = conv_ps_preload_t<32, false>()) != cudaSuccess) return e;
-  if ((e = conv_ps_preload_t<32, true>()) != cudaSuccess) return e;
-  if ((e = conv_ps_preload_t<64, false>()) != cudaSuccess) return e;
-  return conv_ps_preload_t<64, true>();
+#define CDS_PS_PRE(N_, R_, T_) if ((e = conv_ps_preload_t<N_, R_, T_>()) != cudaSuccess) return e;
+  CDS_PS_VARIANTS(CDS_PS_PRE)
+#undef CDS_PS_PRE
+  return cudaSuccess;
 }
 #endif
 

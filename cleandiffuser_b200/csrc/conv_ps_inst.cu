@@ -4,12 +4,9 @@
 #include "conv_ps.cuh"
 
 namespace cds {
-template cudaError_t conv_ps_launch_t<32, false>(const ConvPsLaunch&, const int*, cudaStream_t);
-template cudaError_t conv_ps_launch_t<32, true>(const ConvPsLaunch&, const int*, cudaStream_t);
-template cudaError_t conv_ps_launch_t<64, false>(const ConvPsLaunch&, const int*, cudaStream_t);
-template cudaError_t conv_ps_launch_t<64, true>(const ConvPsLaunch&, const int*, cudaStream_t);
-template cudaError_t conv_ps_preload_t<32, false>();
-template cudaError_t conv_ps_preload_t<32, true>();
-template cudaError_t conv_ps_preload_t<64, false>();
-template cudaError_t conv_ps_preload_t<64, true>();
+#define CDS_PS_INST(N_, R_, T_)                                                                            \
+  template cudaError_t conv_ps_launch_t<N_, R_, T_>(const ConvPsLaunch&, const int*, cudaStream_t);        \
+  template cudaError_t conv_ps_preload_t<N_, R_, T_>();
+CDS_PS_VARIANTS(CDS_PS_INST)
+#undef CDS_PS_INST
 }  // namespace cds

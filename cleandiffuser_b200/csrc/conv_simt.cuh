@@ -32,6 +32,7 @@ __device__ __forceinline__ float ld_act(const void* base, int64_t idx, int dtype
 }
 __device__ __forceinline__ void st_act(void* base, int64_t idx, int dtype, float v) {
   if (dtype == CDS_BF16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+  else if (dtype == CDS_TF32) reinterpret_cast<float*>(base)[idx] = round_tf32(v);
   else reinterpret_cast<float*>(base)[idx] = v;
 }
 

@@ -1,5 +1,9 @@
-// CDS_OP_CONV, tensor-core path (CDS_MATH_BF16_TC): implicit-GEMM 1-D convolution on tcgen05 with the UNet block
-// post-processing fused into the TMEM epilogue.
+// CDS_OP_CONV, tensor-core path (CDS_MATH_BF16_TC / CDS_MATH_TF32_TC): implicit-GEMM 1-D convolution on tcgen05 with the
+// UNet block post-processing fused into the TMEM epilogue.  Template parameter TF32 selects the operand type: bf16
+// activations / weights (kind::f16) or fp32 activations / weights read as TF32 (kind::tf32).  Everything about the operand
+// tiles is expressed in BYTES: "KC" is the row width of a chunk in bf16-equivalents (row bytes / 2: 64 -> 128-byte rows,
+// SWIZZLE_128B; 32 -> 64-byte rows, SWIZZLE_64B), i.e. KC channels of bf16 or KC/2 channels of fp32, and one MMA
+// instruction always consumes 32 bytes of K (16 bf16 / 8 tf32).
 //
 //   D[128 rows x N] (fp32, TMEM) = sum over (tap, 64- or 32-channel chunk) of  A_tap[128 x KC] * W_tap[N x KC]^T
 //
@@ -222,6 +226,11 @@ __device__ __forceinline__ void store_row(void* base, int64_t off, int dtype, co
         reinterpret_cast<uint4*>(p)[k] = u;
       }
     }
+  } else if (dtype == CDS_TF32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+#pragma unroll
+    for (int k = 0; k < W / 4; ++k)
+      p[k] = make_float4(round_tf32(v[4 * k]), round_tf32(v[4 * k + 1]), round_tf32(v[4 * k + 2]), round_tf32(v[4 * k + 3]));
   } else {
     float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
 #pragma unroll
@@ -229,11 +238,16 @@ __device__ __forceinline__ void store_row(void* base, int64_t off, int dtype, co
   }
 }
 
-template <int KC, int N, bool HAS_RES, int SPLIT>
+template <int KC, int N, bool HAS_RES, int SPLIT, bool TF32>
 __global__ void __launch_bounds__(kTcThreads, ConvTcCfg<KC, N, HAS_RES, SPLIT>::kMinBlocks)
 conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ iter_ptr) {
   using Cfg = ConvTcCfg<KC, N, HAS_RES, SPLIT>;
   constexpr int kTcStages = Cfg::kStages;
+  constexpr int KE = TF32 ? KC / 2 : KC;            // channels per chunk (elements along K of one operand row)
+  // the fast lanes write the mode's activation dtype (TF32 kernels: fp32 storage rounded to TF32, CDS_TF32) and read residuals
+  // of the same storage type (CDS_F32 and CDS_TF32 read alike)
+  constexpr int kActDtype = TF32 ? CDS_TF32 : CDS_BF16;
+  auto act_readable = [](int dt) { return TF32 ? (dt != CDS_BF16) : (dt == CDS_BF16); };
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kTcMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kTcMaxStages];
@@ -288,9 +302,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
           ptx::mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
           if (!HAS_RES || kb < n_kb_main) {
             const int tap = kb / p.kchunks, ck = kb - tap * p.kchunks;
-            ptx::tma_load_2d(sb, &p.tm_b, &full_bar[kb], ck * KC, tap * p.C_out * p.phases + n_off0);
+            ptx::tma_load_2d(sb, &p.tm_b, &full_bar[kb], ck * KE, tap * p.C_out * p.phases + n_off0);
           } else {
-            ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[kb], (kb - n_kb_main) * KC, n_off0);
+            ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[kb], (kb - n_kb_main) * KE, n_off0);
           }
         }
       }
@@ -314,12 +328,12 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         uint8_t* sb = sa + Cfg::kABytes;
         if (!HAS_RES || kb < n_kb_main) {
           const int tap = kb / p.kchunks, ck = kb - tap * p.kchunks;
-          ptx::tma_load_3d(sa, &p.tm_a, &full_bar[s], ck * KC, tap - p.pad, a_b0);
-          if (!w_done) ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KC, tap * p.C_out * p.phases + n_off);
+          ptx::tma_load_3d(sa, &p.tm_a, &full_bar[s], ck * KE, tap - p.pad, a_b0);
+          if (!w_done) ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KE, tap * p.C_out * p.phases + n_off);
         } else {
           const int ck = kb - n_kb_main;
-          ptx::tma_load_3d(sa, &p.tm_a2, &full_bar[s], ck * KC, 0, r_b0);
-          if (!w_done) ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], ck * KC, n_off);
+          ptx::tma_load_3d(sa, &p.tm_a2, &full_bar[s], ck * KE, 0, r_b0);
+          if (!w_done) ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], ck * KE, n_off);
         }
       }
       { const int t_i = (tile - blockIdx.x) / gridDim.x; if (t_i < 14) CDS_TRACE(8 + 4 * t_i, clock64()); }
@@ -328,7 +342,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   } else if (warp == 9) {
     // ===================================== MMA issuer =====================================
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, N);
+      constexpr uint32_t idesc = ptx::make_idesc<TF32>(128, N);
       int ring = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it % Cfg::kAccBufs;
@@ -350,8 +364,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         const bool first_of_acc = second ? (kb == n_kb_main) : (kb == 0);
 #pragma unroll
         for (int k = 0; k < KC / 16; ++k) {
-          // advancing 16 bf16 (32 B) along K inside the swizzle span = +2 in the (addr >> 4) field
-          ptx::umma_bf16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (first_of_acc && k == 0) ? 0u : 1u);
+          // advancing 16 bf16 / 8 tf32 (32 B) along K inside the swizzle span = +2 in the (addr >> 4) field
+          ptx::umma<TF32>(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (first_of_acc && k == 0) ? 0u : 1u);
         }
         ptx::umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
       }
@@ -409,7 +423,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     // scheduler at ~0.2 IPC each), so instructions per tile are what counts: the option dispatch happens ONCE per kernel (the
     // tile loop lives inside the specialisation), addresses are strength-reduced to one multiply-add per tile, dtypes are fixed.
     const bool fast_ok = N >= 32 && p.n_col_tiles <= 1 && has_gn && p.act == CDS_ACT_MISH && film != 2 && p.phases == 1 && io_vec &&
-                         p.out_dtype == CDS_BF16 && (!add_res || p.res_dtype == CDS_BF16) && p.res_batch_mod == 0;
+                         p.out_dtype == kActDtype && (!add_res || act_readable(p.res_dtype)) && p.res_batch_mod == 0;
     auto fast_tiles = [&](auto film_tag, auto res_tag) {
       constexpr bool SHIFT = decltype(film_tag)::value == 1;
       constexpr bool RES = decltype(res_tag)::value;
@@ -421,8 +435,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       const float inv_cnt = 1.f / (float)(p.L * CPG);
       const float eps = p.gn_eps;
       const int L_ = p.L, log2L_ = p.log2L, batch_ = p.batch;
-      __nv_bfloat16* const out_l = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)l * p.out_lstride;
-      const __nv_bfloat16* const res_l = RES ? reinterpret_cast<const __nv_bfloat16*>(p.res) + (int64_t)l * p.res_lstride : nullptr;
+      using ET = std::conditional_t<TF32, float, __nv_bfloat16>;     // activation element
+      ET* const out_l = reinterpret_cast<ET*>(p.out) + (int64_t)l * p.out_lstride;
+      const ET* const res_l = RES ? reinterpret_cast<const ET*>(p.res) + (int64_t)l * p.res_lstride : nullptr;
       const int64_t out_bs = p.out_bstride, res_bs = p.res_bstride;
       const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -432,8 +447,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         const int b = (tile / SPLIT) * T_ + tb;
         const bool valid = b < batch_;
         const uint32_t t_row = t_lane + (uint32_t)(buf * Cfg::kColsPerTile);
-        __nv_bfloat16* const out_row = out_l + (int64_t)b * out_bs + n_off;
-        const __nv_bfloat16* const res_row_p = RES ? res_l + (int64_t)b * res_bs + n_off : nullptr;
+        ET* const out_row = out_l + (int64_t)b * out_bs + n_off;
+        const ET* const res_row_p = RES ? res_l + (int64_t)b * res_bs + n_off : nullptr;
         ptx::mbar_wait(&tmem_full_bar[buf], use & 1);
         ptx::tc_fence_after_sync();
         if (threadIdx.x == 0 && it < 14) CDS_TRACE(10 + 4 * it, clock64());
@@ -468,7 +483,16 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
 #pragma unroll
               for (int j = 0; j < 16; ++j) addv[j] = 0.f;
             }
-            if constexpr (RES) {
+            if constexpr (RES && TF32) {
+              if (valid) {
+                const float4* rp = reinterpret_cast<const float4*>(res_row_p + n0 + 16 * h);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float4 rv = rp[k];
+                  addv[4 * k] += rv.x; addv[4 * k + 1] += rv.y; addv[4 * k + 2] += rv.z; addv[4 * k + 3] += rv.w;
+                }
+              }
+            } else if constexpr (RES) {
               uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
               if (valid) { const uint4* rp = reinterpret_cast<const uint4*>(res_row_p + n0 + 16 * h); u0 = rp[0]; u1 = rp[1]; }
               const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
@@ -498,14 +522,21 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
               const float o1 = mish_fma(fmaf(fmaf(v[16 * h + 4 * k + 1], ga[g], gc[g]), gm.y, be.y), addv[4 * k + 1]);
               const float o2 = mish_fma(fmaf(fmaf(v[16 * h + 4 * k + 2], ga[g], gc[g]), gm.z, be.z), addv[4 * k + 2]);
               const float o3 = mish_fma(fmaf(fmaf(v[16 * h + 4 * k + 3], ga[g], gc[g]), gm.w, be.w), addv[4 * k + 3]);
-              __nv_bfloat162 p01 = __floats2bfloat162_rn(o0, o1), p23 = __floats2bfloat162_rn(o2, o3);
-              packed[2 * k] = *reinterpret_cast<uint32_t*>(&p01);
-              packed[2 * k + 1] = *reinterpret_cast<uint32_t*>(&p23);
+              if constexpr (TF32) {
+                if (valid) reinterpret_cast<float4*>(out_row + n0 + 16 * h)[k] =
+                    make_float4(round_tf32(o0), round_tf32(o1), round_tf32(o2), round_tf32(o3));
+              } else {
+                __nv_bfloat162 p01 = __floats2bfloat162_rn(o0, o1), p23 = __floats2bfloat162_rn(o2, o3);
+                packed[2 * k] = *reinterpret_cast<uint32_t*>(&p01);
+                packed[2 * k + 1] = *reinterpret_cast<uint32_t*>(&p23);
+              }
             }
-            if (valid) {
-              uint4* op = reinterpret_cast<uint4*>(out_row + n0 + 16 * h);
-              op[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-              op[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            if constexpr (!TF32) {
+              if (valid) {
+                uint4* op = reinterpret_cast<uint4*>(out_row + n0 + 16 * h);
+                op[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                op[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+              }
             }
           }
         }
@@ -530,7 +561,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
                           (p.act == CDS_ACT_NONE || p.act == CDS_ACT_GELU_TANH);
     auto plain_tiles = [&](auto act_tag, auto bf16_tag) {
       constexpr int ACT = decltype(act_tag)::value;
-      constexpr bool OUT_BF16 = decltype(bf16_tag)::value;
+      constexpr int OUT_DT = decltype(bf16_tag)::value;            // cds_dtype of the output
+      constexpr bool OUT_BF16 = OUT_DT == CDS_BF16;
       const int T_ = 128 >> p.log2L;
       const int tb = m >> p.log2L, l = m & (p.L - 1);
       const int nct = SPLIT > 1 ? SPLIT : p.n_col_tiles;
@@ -580,7 +612,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
             } else {
               float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oo);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) op[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              for (int k = 0; k < 4; ++k) {
+                if constexpr (OUT_DT == CDS_TF32)
+                  op[k] = make_float4(round_tf32(v[4 * k]), round_tf32(v[4 * k + 1]), round_tf32(v[4 * k + 2]), round_tf32(v[4 * k + 3]));
+                else op[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              }
             }
           }
         }
@@ -594,9 +630,15 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       if (plain_ok && it == 0) {
         using G = std::integral_constant<int, CDS_ACT_GELU_TANH>;
         using Z = std::integral_constant<int, CDS_ACT_NONE>;
-        const bool ob = p.out_dtype == CDS_BF16;
-        if (p.act == CDS_ACT_GELU_TANH) { if (ob) plain_tiles(G{}, std::true_type{}); else plain_tiles(G{}, std::false_type{}); }
-        else { if (ob) plain_tiles(Z{}, std::true_type{}); else plain_tiles(Z{}, std::false_type{}); }
+        using DF = std::integral_constant<int, CDS_F32>;
+        using DB = std::integral_constant<int, CDS_BF16>;
+        using DT = std::integral_constant<int, CDS_TF32>;
+        const int od = p.out_dtype;
+        if (p.act == CDS_ACT_GELU_TANH) {
+          if (od == CDS_BF16) plain_tiles(G{}, DB{}); else if (od == CDS_TF32) plain_tiles(G{}, DT{}); else plain_tiles(G{}, DF{});
+        } else {
+          if (od == CDS_BF16) plain_tiles(Z{}, DB{}); else if (od == CDS_TF32) plain_tiles(Z{}, DT{}); else plain_tiles(Z{}, DF{});
+        }
       }
     }
     // generic lane (everything else; a no-op after the fast lane: `it` then already counts all of this CTA's tiles)
@@ -703,7 +745,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         for (int j = 0; j < 16; ++j) {
           if (c0 + j < p.C_out) {
             if (p.out_dtype == CDS_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[oo + j] = __float2bfloat16_rn(o[j]);
-            else reinterpret_cast<float*>(p.out)[oo + j] = o[j];
+            else reinterpret_cast<float*>(p.out)[oo + j] = f32_for_store(o[j], p.out_dtype);
           }
         }
       }
@@ -870,27 +912,33 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-// bf16 tensor, dims innermost-first; strides in elements for dims 1.. (dim 0 is contiguous)
-inline bool encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
-                            const uint32_t* box, int kc, const uint32_t* elem_strides = nullptr) {
+// bf16 (tf32 = false) or fp32 (tf32 = true) tensor, dims innermost-first; strides in elements for dims 1.. (dim 0 is
+// contiguous); kc = row bytes / 2 of the box (64: SWIZZLE_128B, 32: SWIZZLE_64B), box[0] = kc (bf16) or kc / 2 (fp32) elements
+inline bool encode_act_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                           const uint32_t* box, int kc, bool tf32, const uint32_t* elem_strides = nullptr) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t bx[3], es[3];
+  const int eb = tf32 ? 4 : 2;
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
-  for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_el[i - 1] * 2;
+  for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_el[i - 1] * eb;
   CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                   const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
 inline int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
 
-// channel-chunk width: 64 (SWIZZLE_128B) when every K extent is a multiple of 64, else 32 (SWIZZLE_64B)
+inline bool conv_is_tf32(const cds_conv_op& c) { return c.math == CDS_MATH_TF32_TC; }
+// operand row width in bf16-equivalents (row bytes / 2): 64 (128-byte rows, SWIZZLE_128B) when every K extent fills whole
+// 128-byte rows (64 bf16 / 32 fp32 channels), else 32 (64-byte rows, SWIZZLE_64B: 32 bf16 / 16 fp32 channels)
 inline int conv_tc_pick_kc(const cds_conv_op& c) {
-  bool k64 = (c.C_in % 64 == 0) && (!c.res_w || c.res_C % 64 == 0);
-  return k64 ? 64 : 32;
+  const int full = conv_is_tf32(c) ? 32 : 64;
+  bool wide = (c.C_in % full == 0) && (!c.res_w || c.res_C % full == 0);
+  return wide ? 64 : 32;
 }
 
 // GEMM width of the op: C_out*phases, or 16 for a narrow (C_out <= 16) 1x1 head whose missing weight rows the TMA
@@ -911,7 +959,13 @@ inline int conv_tc_width(const cds_conv_op& c) {
 
 // can the tensor-core kernel serve this op?  (otherwise the fp32 CUDA-core kernel runs it, any dtype)
 inline bool conv_tc_eligible(const cds_conv_op& c) {
-  if (c.math != CDS_MATH_BF16_TC || c.in_dtype != 1) return false;
+  if (c.math != CDS_MATH_BF16_TC && c.math != CDS_MATH_TF32_TC) return false;
+  const bool tf32 = conv_is_tf32(c);
+  // operand tensors (in, res_in) must have the mode's storage type: bf16, or fp32 (CDS_F32 / CDS_TF32 read alike)
+  auto operand_ok = [tf32](int dt) { return tf32 ? (dt == CDS_F32 || dt == CDS_TF32) : (dt == CDS_BF16); };
+  const int vec_el = tf32 ? 4 : 8;                    // elements per 16 bytes
+  const int kmin = tf32 ? 16 : 32;                    // channels in a 64-byte operand row
+  if (!operand_ok(c.in_dtype)) return false;
   if (c.stride != 1 && c.stride != 2) return false;
   if (c.phases != 1 && c.phases != 2) return false;
   int L = c.L_out;                                   // tile rows = 128/L trajectories x L output positions
@@ -920,14 +974,15 @@ inline bool conv_tc_eligible(const cds_conv_op& c) {
   if (conv_tc_width(c) == 0) return false;
   if (conv_tc_width(c) > 256 && c.groups != 0 && conv_tc_pick_kc(c) != 64) return false;   // wide GN variants: KC = 64 only
   if (c.sample_row_div > 1 && c.L_out != 1) return false;
-  if (c.C_in % 32 != 0) return false;
+  if (c.C_in % kmin != 0) return false;
   if (c.groups != 0 && (c.groups != 8 || c.phases != 1 || c.C_out < 32)) return false;
   if (c.phases == 2 && (c.res || c.res_w)) return false;
   int T = 128 / L;
   if (c.in_batch_mod > 0 && c.in_batch_mod % T != 0) return false;
   if (c.res_batch_mod > 0 && c.res_w && c.res_batch_mod % T != 0) return false;   // (the identity residual is read row by row)
-  if (c.res_w && (c.res_in_dtype != 1 || c.res_C % 32 != 0)) return false;
-  if ((c.in_lstride % 8) || (c.in_bstride % 8) || ((uintptr_t)c.in % 16)) return false;
+  if (c.res_w && (!operand_ok(c.res_in_dtype) || c.res_C % kmin != 0)) return false;
+  if ((c.in_lstride % vec_el) || (c.in_bstride % vec_el) || ((uintptr_t)c.in % 16)) return false;
+  if (c.res_w && ((c.res_in_lstride % vec_el) || (c.res_in_bstride % vec_el) || ((uintptr_t)c.res_in % 16))) return false;
   if (c.C_out % 16 == 0) {                           // vector stores
     if (c.out_dtype == 1 ? ((c.out_lstride % 8) || ((uintptr_t)c.out % 16)) : ((c.out_lstride % 4) || ((uintptr_t)c.out % 16)))
       return false;
@@ -939,6 +994,7 @@ inline bool conv_tc_eligible(const cds_conv_op& c) {
 
 struct ConvTcLaunch {
   ConvTcParams prm;
+  bool tf32 = false;              // fp32 operands read as TF32 (CDS_MATH_TF32_TC)
   int kc = 0, n = 0, split = 1;   // n = CTA tile width, split*n = layer width
   int max_ctas_per_sm = 0;        // > 0: use at most this many CTAs per SM (plans with parallel branches share the SMs)
   bool has_res = false;
@@ -960,6 +1016,9 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
   ConvTcLaunch& L = *out;
   memset(&L.prm, 0, sizeof(L.prm));
   const int kc = conv_tc_pick_kc(c);
+  const bool tf32 = conv_is_tf32(c);
+  const int ke = tf32 ? kc / 2 : kc;                   // channels per chunk
+  L.tf32 = tf32;
   ConvTcParams& p = L.prm;
   const int Lp = c.L_out, T = 128 / Lp;
   const int64_t rows = (int64_t)c.batch * Lp;
@@ -982,31 +1041,31 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
     uint64_t dims[3] = {(uint64_t)c.C_in, (uint64_t)c.L_in, in_b};
     uint64_t str[2] = {(uint64_t)c.in_lstride, (uint64_t)c.in_bstride};
     // stride-2 conv: the box walks the position axis with element stride 2 (box extent = 2*L traversed -> L loaded)
-    uint32_t box[3] = {(uint32_t)kc, (uint32_t)(Lp * c.stride), (uint32_t)T};
+    uint32_t box[3] = {(uint32_t)ke, (uint32_t)(Lp * c.stride), (uint32_t)T};
     uint32_t es[3] = {1u, (uint32_t)c.stride, 1u};
-    if (!encode_bf16_map(&p.tm_a, c.in, 3, dims, str, box, kc, es)) return false;
+    if (!encode_act_map(&p.tm_a, c.in, 3, dims, str, box, kc, tf32, es)) return false;
   }
   {
     // weight rows beyond taps*C_out*phases (narrow heads padded to N=16) are zero-filled by the TMA unit
     uint64_t dims[2] = {(uint64_t)c.C_in, (uint64_t)c.taps * c.C_out * c.phases};
     uint64_t str[1] = {(uint64_t)c.C_in};
-    uint32_t box[2] = {(uint32_t)kc, (uint32_t)L.n};
-    if (!encode_bf16_map(&p.tm_b, c.w, 2, dims, str, box, kc)) return false;
+    uint32_t box[2] = {(uint32_t)ke, (uint32_t)L.n};
+    if (!encode_act_map(&p.tm_b, c.w, 2, dims, str, box, kc, tf32)) return false;
   }
   if (L.has_res) {
     const uint64_t r_b = c.res_batch_mod > 0 ? (uint64_t)c.res_batch_mod : (uint64_t)c.batch;
     uint64_t dims[3] = {(uint64_t)c.res_C, (uint64_t)Lp, r_b};
     uint64_t str[2] = {(uint64_t)c.res_in_lstride, (uint64_t)c.res_in_bstride};
-    uint32_t box[3] = {(uint32_t)kc, (uint32_t)Lp, (uint32_t)T};
-    if (!encode_bf16_map(&p.tm_a2, c.res_in, 3, dims, str, box, kc)) return false;
+    uint32_t box[3] = {(uint32_t)ke, (uint32_t)Lp, (uint32_t)T};
+    if (!encode_act_map(&p.tm_a2, c.res_in, 3, dims, str, box, kc, tf32)) return false;
     uint64_t d2[2] = {(uint64_t)c.res_C, (uint64_t)c.C_out};
     uint64_t s2[1] = {(uint64_t)c.res_C};
-    uint32_t b2[2] = {(uint32_t)kc, (uint32_t)L.n};
-    if (!encode_bf16_map(&p.tm_b2, c.res_w, 2, d2, s2, b2, kc)) return false;
+    uint32_t b2[2] = {(uint32_t)ke, (uint32_t)L.n};
+    if (!encode_act_map(&p.tm_b2, c.res_w, 2, d2, s2, b2, kc, tf32)) return false;
   }
   p.batch = c.batch; p.L = Lp; p.log2L = ilog2(Lp); p.C_out = c.C_out; p.taps = c.taps; p.pad = c.pad;
   p.phases = c.phases;
-  p.kchunks = c.C_in / kc; p.kchunks2 = L.has_res ? c.res_C / kc : 0;
+  p.kchunks = c.C_in / ke; p.kchunks2 = L.has_res ? c.res_C / ke : 0;
   p.in_batch_mod = c.in_batch_mod;
   p.bias = c.bias; p.scale = c.scale; p.shift = c.shift;
   p.groups = c.groups; p.gn_gamma = c.gn_gamma; p.gn_beta = c.gn_beta; p.gn_eps = c.gn_eps; p.act = c.act;
@@ -1025,7 +1084,7 @@ long long* conv_tc_trace_hook(int grid);
 
 // Launch wrapper of one instantiation.  The instantiations are compiled in conv_tc_inst.cu (several translation units, built
 // in parallel); every other translation unit only sees the extern declarations below.
-template <int KC, int N, bool HAS_RES, int SPLIT>
+template <int KC, int N, bool HAS_RES, int SPLIT, bool TF32>
 cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStream_t st) {
   using Cfg = ConvTcCfg<KC, N, HAS_RES, SPLIT>;
   static bool attr = false;
@@ -1033,11 +1092,11 @@ cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStr
   static int sm_count = 0;
   static bool pdl = true;                    // chain with programmatic dependent launch (CDS_PDL=0: plain stream order)
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES, SPLIT, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     // several CTAs per SM for the narrow tiles: ask for the maximum shared-memory carve-out
-    e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(conv_tc_kernel<KC, N, HAS_RES, SPLIT, TF32>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
@@ -1052,8 +1111,8 @@ cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStr
     if (const char* cap = getenv("CDS_TC_MAXCTAS")) { int c = atoi(cap); if (c >= 1 && c < want) want = c; }
     if (want < 1) want = 1;
     if (getenv("CDS_DEBUG"))
-      fprintf(stderr, "[cds] conv_tc<%d,%d,%d,%d>: designed %d CTA/SM (tmem %d, smem %d), smem %d B, %d stages\n", KC, N,
-              (int)HAS_RES, SPLIT, want, by_tmem, by_smem, Cfg::kSmemBytes, Cfg::kStages);
+      fprintf(stderr, "[cds] conv_tc<%d,%d,%d,%d,%s>: designed %d CTA/SM (tmem %d, smem %d), smem %d B, %d stages\n", KC, N,
+              (int)HAS_RES, SPLIT, TF32 ? "tf32" : "bf16", want, by_tmem, by_smem, Cfg::kSmemBytes, Cfg::kStages);
     resident = want * sms;
     sm_count = sms;
     const char* pdl_env = getenv("CDS_PDL");
@@ -1071,13 +1130,13 @@ cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStr
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<KC, N, HAS_RES, SPLIT>, prm, iter_ptr);
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<KC, N, HAS_RES, SPLIT, TF32>, prm, iter_ptr);
 }
 // touch the kernel once (module load) so that nothing lazy happens inside a stream capture
-template <int KC, int N, bool HAS_RES, int SPLIT>
+template <int KC, int N, bool HAS_RES, int SPLIT, bool TF32>
 cudaError_t conv_tc_preload_t() {
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, conv_tc_kernel<KC, N, HAS_RES, SPLIT>);
+  return cudaFuncGetAttributes(&a, conv_tc_kernel<KC, N, HAS_RES, SPLIT, TF32>);
 }
 
 // every (KC, N, SPLIT) the dispatcher can pick (each with and without the shortcut accumulator); X(kc, n, split)
@@ -1087,18 +1146,24 @@ cudaError_t conv_tc_preload_t() {
   X(32, 16, 1) X(32, 32, 1) X(32, 64, 1) X(32, 128, 1) X(32, 256, 1) X(32, 32, 2) X(32, 64, 2) X(32, 128, 2)
 
 #ifndef CDS_TC_INSTANTIATE
-#define CDS_TC_EXTERN(KC_, N_, S_)                                                                                      \
-  extern template cudaError_t conv_tc_launch_t<KC_, N_, false, S_>(const ConvTcLaunch&, const int*, cudaStream_t);      \
-  extern template cudaError_t conv_tc_launch_t<KC_, N_, true, S_>(const ConvTcLaunch&, const int*, cudaStream_t);       \
-  extern template cudaError_t conv_tc_preload_t<KC_, N_, false, S_>();                                                  \
-  extern template cudaError_t conv_tc_preload_t<KC_, N_, true, S_>();
+#define CDS_TC_EXTERN2(KC_, N_, S_, T_)                                                                                 \
+  extern template cudaError_t conv_tc_launch_t<KC_, N_, false, S_, T_>(const ConvTcLaunch&, const int*, cudaStream_t);  \
+  extern template cudaError_t conv_tc_launch_t<KC_, N_, true, S_, T_>(const ConvTcLaunch&, const int*, cudaStream_t);   \
+  extern template cudaError_t conv_tc_preload_t<KC_, N_, false, S_, T_>();                                              \
+  extern template cudaError_t conv_tc_preload_t<KC_, N_, true, S_, T_>();
+#define CDS_TC_EXTERN(KC_, N_, S_) CDS_TC_EXTERN2(KC_, N_, S_, false) CDS_TC_EXTERN2(KC_, N_, S_, true)
 CDS_TC_VARIANTS(CDS_TC_EXTERN)
 #undef CDS_TC_EXTERN
+#undef CDS_TC_EXTERN2
 
 inline cudaError_t conv_tc_launch(const ConvTcLaunch& L, const int* iter_ptr, cudaStream_t st) {
-#define CDS_TC_CASE(KC_, N_, S_)                                                                 \
-  if (L.kc == KC_ && L.n == N_ && L.split == S_)                                                 \
-    return L.has_res ? conv_tc_launch_t<KC_, N_, true, S_>(L, iter_ptr, st) : conv_tc_launch_t<KC_, N_, false, S_>(L, iter_ptr, st);
+#define CDS_TC_CASE(KC_, N_, S_)                                                                                         \
+  if (L.kc == KC_ && L.n == N_ && L.split == S_) {                                                                       \
+    if (L.tf32) return L.has_res ? conv_tc_launch_t<KC_, N_, true, S_, true>(L, iter_ptr, st)                            \
+                                 : conv_tc_launch_t<KC_, N_, false, S_, true>(L, iter_ptr, st);                          \
+    return L.has_res ? conv_tc_launch_t<KC_, N_, true, S_, false>(L, iter_ptr, st)                                       \
+                     : conv_tc_launch_t<KC_, N_, false, S_, false>(L, iter_ptr, st);                                     \
+  }
   CDS_TC_VARIANTS(CDS_TC_CASE)
 #undef CDS_TC_CASE
   return cudaErrorInvalidValue;
@@ -1106,9 +1171,11 @@ inline cudaError_t conv_tc_launch(const ConvTcLaunch& L, const int* iter_ptr, cu
 
 inline cudaError_t conv_tc_preload_all() {
   cudaError_t e;
-#define CDS_TC_PRE(KC_, N_, S_)                                                       \
-  if ((e = conv_tc_preload_t<KC_, N_, false, S_>()) != cudaSuccess) return e;         \
-  if ((e = conv_tc_preload_t<KC_, N_, true, S_>()) != cudaSuccess) return e;
+#define CDS_TC_PRE(KC_, N_, S_)                                                              \
+  if ((e = conv_tc_preload_t<KC_, N_, false, S_, false>()) != cudaSuccess) return e;         \
+  if ((e = conv_tc_preload_t<KC_, N_, true, S_, false>()) != cudaSuccess) return e;          \
+  if ((e = conv_tc_preload_t<KC_, N_, false, S_, true>()) != cudaSuccess) return e;          \
+  if ((e = conv_tc_preload_t<KC_, N_, true, S_, true>()) != cudaSuccess) return e;
   CDS_TC_VARIANTS(CDS_TC_PRE)
 #undef CDS_TC_PRE
   return cudaSuccess;

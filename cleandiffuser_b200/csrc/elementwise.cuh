@@ -89,7 +89,10 @@ __device__ __forceinline__ void solver_update_element(const cds_update_op& p, co
                                         (p.xhat_prev && r.kind == CDS_UPD_X2M) ? p.xhat_prev[i] : 0.f, &xhat);
   if (p.xhat_prev && r.kind != CDS_UPD_CM && r.kind != CDS_UPD_DDPM && r.kind != CDS_UPD_DDIM) p.xhat_prev[i] = xhat;
   p.x[i] = out;
-  if (p.x_cast) reinterpret_cast<__nv_bfloat16*>(p.x_cast)[cast_off] = __float2bfloat16_rn(out);
+  if (p.x_cast) {
+    if (p.x_cast_dtype == CDS_BF16) reinterpret_cast<__nv_bfloat16*>(p.x_cast)[cast_off] = __float2bfloat16_rn(out);
+    else reinterpret_cast<float*>(p.x_cast)[cast_off] = f32_for_store(out, p.x_cast_dtype);
+  }
 }
 
 // the last block of a grid to finish bumps the iteration counter ([0] = counter, [1] = blocks finished): saves the
@@ -129,10 +132,12 @@ static __global__ void __launch_bounds__(256) solver_update_kernel(const cds_upd
       reinterpret_cast<float4*>(p.x)[g] = make_float4(os[0], os[1], os[2], os[3]);
       if (p.x_cast) {
         unsigned rr = i0 / (unsigned)p.cast_C_in, c = i0 - rr * (unsigned)p.cast_C_in;
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.x_cast);
+        const bool cast_bf16 = p.x_cast_dtype == CDS_BF16;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          dst[(int64_t)rr * p.cast_C_out + c] = __float2bfloat16_rn(os[k]);
+          const int64_t o = (int64_t)rr * p.cast_C_out + c;
+          if (cast_bf16) reinterpret_cast<__nv_bfloat16*>(p.x_cast)[o] = __float2bfloat16_rn(os[k]);
+          else reinterpret_cast<float*>(p.x_cast)[o] = f32_for_store(os[k], p.x_cast_dtype);
           if (++c == (unsigned)p.cast_C_in) { c = 0; ++rr; }
         }
       }
@@ -217,26 +222,27 @@ static __global__ void __launch_bounds__(256) ln_modulate_kernel(const cds_lnmod
       float* dst = reinterpret_cast<float*>(p.out) + r * p.C;
       if (in_regs) {
 #pragma unroll
-        for (int k = 0; k < kLnRegs; ++k) { const int c = lane + 32 * k; if (c < p.C) dst[c] = value(c, x[k]); }
+        for (int k = 0; k < kLnRegs; ++k) { const int c = lane + 32 * k; if (c < p.C) dst[c] = f32_for_store(value(c, x[k]), p.out_dtype); }
       } else {
-        for (int c = lane; c < p.C; c += 32) dst[c] = value(c, src[c]);
+        for (int c = lane; c < p.C; c += 32) dst[c] = f32_for_store(value(c, src[c]), p.out_dtype);
       }
     }
   }
 }
 
-// fp32 (rows, C_in) -> bf16 (rows, C_out) zero padded; one thread per output pair.  4*C_in + 2*C_out B / row
+// fp32 (rows, C_in) -> bf16 or fp32 (rows, C_out) zero padded; one thread per output pair.  4*C_in + (2|4)*C_out B / row
 static __global__ void __launch_bounds__(256) cast_pad_kernel(const cds_cast_op p) {
   const int64_t rows = (int64_t)p.batch * p.L;
   const int pairs = p.C_out >> 1;
   const int64_t total = rows * pairs;
-  __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(p.out);
+  const bool bf16 = p.out_dtype == CDS_BF16;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / pairs;
     const int c = (int)(i - r * pairs) * 2;
     const float a = c < p.C_in ? p.in[r * p.C_in + c] : 0.f;
     const float b = c + 1 < p.C_in ? p.in[r * p.C_in + c + 1] : 0.f;
-    out[i] = __floats2bfloat162_rn(a, b);
+    if (bf16) reinterpret_cast<__nv_bfloat162*>(p.out)[i] = __floats2bfloat162_rn(a, b);
+    else reinterpret_cast<float2*>(p.out)[i] = make_float2(f32_for_store(a, p.out_dtype), f32_for_store(b, p.out_dtype));
   }
 }
 

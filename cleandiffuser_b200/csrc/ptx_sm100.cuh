@@ -85,6 +85,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with fp32 operands read as TF32 (kind::tf32: K = 8 elements = 32 bytes per instruction, fp32 accumulate)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TF32) umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+  else umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
 // arrive on an mbarrier when all tcgen05.mma issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -180,6 +195,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | ((uint32_t)(N >> 3) << 17)   // n_dim
          | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
+
+// ... for kind::tf32: fp32 accumulator, TF32 A and B (format code 2), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <bool TF32>
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) { return TF32 ? make_idesc_tf32(M, N) : make_idesc_bf16(M, N); }
 
 }  // namespace ptx
 }  // namespace cds

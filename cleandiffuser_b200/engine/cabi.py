@@ -10,13 +10,14 @@ import os
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "libcds.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 OPF_BRANCH_SHIFT = 8   # cds_op.flags bits 8..15: branch index (independent chains run on parallel streams)
 OPF_ONCE = 1          # cds_op.flags: run once per plan run (before its first iteration), not in every iteration
 OP_CONV, OP_UPDATE, OP_LNMOD, OP_ATTN, OP_PREP, OP_CAST = range(6)
 ACT_NONE, ACT_MISH, ACT_SILU, ACT_GELU_TANH, ACT_MISH_SILU = range(5)
-MATH_FP32, MATH_BF16_TC = 0, 1
-F32, BF16 = 0, 1
+MATH_FP32, MATH_BF16_TC, MATH_TF32_TC = 0, 1, 2
+TC_MODES = (MATH_BF16_TC, MATH_TF32_TC)
+F32, BF16, TF32 = 0, 1, 2      # cds_dtype; TF32 = fp32 storage, values rounded to TF32 when written
 ROW_FLOATS = 12
 
 _f32p = C.c_void_p   # device pointers are passed as integers
@@ -65,7 +66,7 @@ class PrepOp(C.Structure):
 
 class CastOp(C.Structure):
     _fields_ = [("batch", C.c_int32), ("L", C.c_int32), ("C_in", C.c_int32), ("C_out", C.c_int32),
-                ("in_", _f32p), ("out", C.c_void_p)]
+                ("in_", _f32p), ("out", C.c_void_p), ("out_dtype", C.c_int32)]
 
 
 class UpdateOp(C.Structure):
@@ -75,7 +76,7 @@ class UpdateOp(C.Structure):
         ("noise", _f32p), ("noise_slot_stride", C.c_int64), ("prior", _f32p), ("mask", _f32p), ("x_min", _f32p),
         ("x_max", _f32p),
         ("xhat_prev", _f32p), ("coef", _f32p), ("predict_noise", C.c_int32), ("final_clip", C.c_int32),
-        ("x_cast", C.c_void_p), ("cast_C_in", C.c_int32), ("cast_C_out", C.c_int32),
+        ("x_cast", C.c_void_p), ("cast_C_in", C.c_int32), ("cast_C_out", C.c_int32), ("x_cast_dtype", C.c_int32),
     ]
 
 

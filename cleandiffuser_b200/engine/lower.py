@@ -28,8 +28,6 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import cabi
-from ..nn_diffusion import ChiUNet1d, DiT1d, DQLMlp, JannerUNet1d
-from ..utils import GroupNorm1d
 
 
 class Unsupported(Exception):
@@ -40,8 +38,11 @@ class View:
     """A channels-last activation: element (b, l, c) at base + b*bstride + l*lstride + c (elements of its dtype)."""
 
     def __init__(self, tensor: torch.Tensor, L: int, Cn: int, offset: int = 0, bstride: Optional[int] = None,
-                 lstride: Optional[int] = None):
+                 lstride: Optional[int] = None, tf32: bool = False):
         assert tensor.dtype in (torch.float32, torch.bfloat16)
+        # tf32: fp32 storage that feeds a TF32 tensor-core operator -> producers round to TF32 when they write it (cds_dtype
+        # CDS_TF32); readers treat it as fp32
+        self.tf32 = bool(tf32) and tensor.dtype == torch.float32
         # module dims may be numpy ints (np.cumprod(dim_mult)); ctypes wants python ints
         self.t, self.L, self.C, self.offset = tensor, int(L), int(Cn), int(offset)
         self.lstride = self.C if lstride is None else int(lstride)
@@ -53,10 +54,10 @@ class View:
 
     @property
     def dtype(self):
-        return cabi.BF16 if self.t.dtype == torch.bfloat16 else cabi.F32
+        return cabi.BF16 if self.t.dtype == torch.bfloat16 else (cabi.TF32 if self.tf32 else cabi.F32)
 
     def channels(self, start: int, count: int) -> "View":
-        return View(self.t, self.L, count, self.offset + int(start), self.bstride, self.lstride)
+        return View(self.t, self.L, count, self.offset + int(start), self.bstride, self.lstride, self.tf32)
 
 
 def _vec(step: Optional[torch.Tensor] = None, sample: Optional[torch.Tensor] = None, col: int = 0) -> cabi.Vec:
@@ -81,7 +82,7 @@ class WSpec:
     """Where a GEMM weight comes from; packed lazily in the layout of the kernel that ends up running the op.
 
     kn() -> fp32 [K = taps*C_in, N = C_out*phases]   (CUDA-core kernel: K rows, N contiguous)
-    nk() -> [taps, C_out, C_in]                      (tensor-core kernel: K contiguous; cast to bf16), or None"""
+    nk() -> [taps, C_out, C_in]                      (tensor-core kernel: K contiguous; cast to bf16 / rounded to TF32), or None"""
 
     def __init__(self, kn: Callable[[], torch.Tensor], nk: Optional[Callable[[], torch.Tensor]] = None):
         self.kn, self.nk = kn, nk
@@ -128,6 +129,14 @@ def w_convT(conv: nn.ConvTranspose1d) -> WSpec:
     return WSpec(make, make_nk)
 
 
+def round_tf32(w: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest TF32-representable fp32 (10-bit mantissa, ties away from zero like cvt.rna.tf32.f32).  tcgen05
+    kind::tf32 ignores the low 13 mantissa bits of its operands, i.e. truncates; weights are rounded once here so that
+    their part of the error is unbiased."""
+    bits = w.detach().to(torch.float32).contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 class Program:
     def __init__(self, device: torch.device, rows: int, n_iters: int, math: int = cabi.MATH_FP32):
         self.device, self.rows, self.n_iters, self.math = device, rows, n_iters, math
@@ -144,11 +153,24 @@ class Program:
 
     @property
     def act_dtype(self):
-        """Intermediate activations: bf16 when the program runs on the tensor-core kernels, else fp32."""
+        """Intermediate activations: bf16 on CDS_MATH_BF16_TC programs, fp32 otherwise (CUDA-core and TF32 programs)."""
         return torch.bfloat16 if self.math == cabi.MATH_BF16_TC else torch.float32
 
+    @property
+    def tc(self) -> bool:
+        """Does this program ask for the tensor-core kernels?"""
+        return self.math in cabi.TC_MODES
+
+    @property
+    def k_align(self) -> int:
+        """Channel granularity of a tensor-core operand row (64 bytes): what x_t is padded to."""
+        return 16 if self.math == cabi.MATH_TF32_TC else 32
+
     def act(self, L: int, Cn: int, dtype=None) -> View:
-        return View(self.buf(self.rows, L, Cn, dtype=self.act_dtype if dtype is None else dtype), L, Cn)
+        """A (rows, L, Cn) activation.  Without an explicit dtype it is an inter-layer activation in the program's activation
+        type (bf16 / TF32-rounded fp32 / fp32); an explicit torch.float32 is kept exact (predictions, DiT's residual stream)."""
+        return View(self.buf(self.rows, L, Cn, dtype=self.act_dtype if dtype is None else dtype), L, Cn,
+                    tf32=dtype is None and self.math == cabi.MATH_TF32_TC)
 
     def packed(self, make: Callable[[], torch.Tensor], dtype=torch.float32) -> torch.Tensor:
         """Persistent packed copy of parameters; ``make`` is re-evaluated into it when weights change."""
@@ -164,7 +186,7 @@ class Program:
 
     # ---- operator emitters --------------------------------------------------------------------
     def conv(self, x: View, w: WSpec, out: View, *, taps=1, stride=1, pad=0, phases=1, L_out=None,
-             bias: Optional[cabi.Vec] = None, gn: Optional[GroupNorm1d] = None, act=cabi.ACT_NONE,
+             bias: Optional[cabi.Vec] = None, gn: Optional[nn.Module] = None, act=cabi.ACT_NONE,
              scale: Optional[cabi.Vec] = None, shift: Optional[cabi.Vec] = None, res: Optional[View] = None,
              res_conv=None, in_batch_mod=0, res_batch_mod=0, rows=None, sample_row_div=0):
         """Emit one CDS_OP_CONV.  ``res_conv`` = (View, WSpec of the 1x1 weight, bias tensor maker)."""
@@ -200,18 +222,22 @@ class Program:
 
         # kernel family: tensor cores when the program asks for them AND this op qualifies, else CUDA cores
         use_tc = False
-        if self.math == cabi.MATH_BF16_TC and w.nk is not None and (res_conv is None or res_conv[1].nk is not None):
+        if self.tc and w.nk is not None and (res_conv is None or res_conv[1].nk is not None):
+            c.math = self.math
             use_tc = bool(cabi.load().cds_conv_tc_supported(C.byref(c)))
-        c.math = cabi.MATH_BF16_TC if use_tc else cabi.MATH_FP32
+        c.math = self.math if use_tc else cabi.MATH_FP32
+        tf32 = self.math == cabi.MATH_TF32_TC
+        wdt = torch.float32 if tf32 else torch.bfloat16            # tensor-core weight element
+        wfix = round_tf32 if tf32 else (lambda t: t)
         if use_tc:
-            wt = self.packed(lambda: w.nk().reshape(taps * out.C * phases, x.C), torch.bfloat16)
+            wt = self.packed(lambda: wfix(w.nk().reshape(taps * out.C * phases, x.C)), wdt)
         else:
             wt = self.packed(w.kn)
             assert wt.shape == (taps * x.C, out.C * phases), (wt.shape, taps, x.C, out.C, phases)
         c.w = wt.data_ptr()
         if res_conv is not None:
             rw = res_conv[1]
-            rwt = self.packed(lambda: rw.nk().reshape(out.C, rx.C), torch.bfloat16) if use_tc else self.packed(rw.kn)
+            rwt = self.packed(lambda: wfix(rw.nk().reshape(out.C, rx.C)), wdt) if use_tc else self.packed(rw.kn)
             c.res_w, c.res_bias = rwt.data_ptr(), self.packed(res_conv[2]).data_ptr()
         self.ops.append(op)
         return out
@@ -229,8 +255,8 @@ class Program:
                 res_period = L
             else:
                 dense = dense and res.lstride == res.C and res.bstride == L * res.C
-        if self.math == cabi.MATH_BF16_TC and dense and x.t.dtype == torch.bfloat16 and w.nk is not None and kw.get("res_conv") is None:
-            flat = lambda v: View(v.t, 1, v.C, v.offset, v.C, v.C)
+        if self.tc and dense and x.t.dtype == self.act_dtype and w.nk is not None and kw.get("res_conv") is None:
+            flat = lambda v: View(v.t, 1, v.C, v.offset, v.C, v.C, v.tf32)
             probe = cabi.Op()
             c = probe.u.conv
             c.batch, c.L_in, c.L_out, c.C_in, c.C_out, c.taps, c.stride, c.pad, c.phases = self.rows * L, 1, 1, x.C, out.C, 1, 1, 0, 1
@@ -239,6 +265,7 @@ class Program:
             c.act = kw.get("act", cabi.ACT_NONE)
             c.sample_row_div = L
             c.in_batch_mod = int(kw.get("in_batch_mod", 0)) * L
+            c.math = self.math
             if res is not None:
                 c.res, c.res_bstride, c.res_lstride, c.res_dtype = res.ptr, res.C, res.C, res.dtype
                 c.res_batch_mod = res_period
@@ -252,15 +279,15 @@ class Program:
         return self.conv(x, w, out, **kw)
 
     def cast_pad(self, x: View, width: int, rows: Optional[int] = None) -> View:
-        """fp32 dense (rows, L, C) -> bf16 dense (rows, L, width) with zero channels appended (rows: of the VIEW, which may
-        be a sub-batch of its tensor)."""
+        """fp32 dense (rows, L, C) -> dense (rows, L, width) of the program's activation dtype with zero channels appended
+        (rows: of the VIEW, which may be a sub-batch of its tensor)."""
         assert x.t.dtype == torch.float32 and x.lstride == x.C and x.bstride == x.L * x.C
         rows = x.t.shape[0] if rows is None else int(rows)
-        out = View(self.buf(rows, x.L, width, dtype=torch.bfloat16), x.L, width)
+        out = View(self.buf(rows, x.L, width, dtype=self.act_dtype), x.L, width, tf32=self.math == cabi.MATH_TF32_TC)
         op = cabi.Op()
         op.kind = cabi.OP_CAST
         k = op.u.cast
-        k.batch, k.L, k.C_in, k.C_out, k.in_, k.out = rows, x.L, x.C, int(width), x.ptr, out.ptr
+        k.batch, k.L, k.C_in, k.C_out, k.in_, k.out, k.out_dtype = rows, x.L, x.C, int(width), x.ptr, out.ptr, out.dtype
         self.ops.append(op)
         return out
 
@@ -284,10 +311,17 @@ class Program:
 
 
 # =============================================================================== UNets
+def _is_groupnorm(m) -> bool:
+    """GroupNorm1d recognised structurally (class name + the attributes the kernels need), so that modules built from the
+    reference's own classes (cleandiffuser/utils/building_blocks.py:60-76) lower exactly like this package's."""
+    return (type(m).__name__ in ("GroupNorm1d", "GroupNorm") and hasattr(m, "num_groups") and hasattr(m, "eps")
+            and isinstance(getattr(m, "weight", None), torch.Tensor) and isinstance(getattr(m, "bias", None), torch.Tensor))
+
+
 def _lower_conv_block(p: Program, seq: nn.Sequential, x: View, out: View, k: int, **kw):
     """Conv1d -> GroupNorm1d -> Mish as ONE operator."""
     conv, gn = seq[0], seq[1]
-    if not isinstance(gn, GroupNorm1d):
+    if not _is_groupnorm(gn):
         raise Unsupported("norm_type other than groupnorm")
     return p.conv(x, w_conv(conv, x.C), out, taps=k, pad=k // 2, bias=_const_vec(p.packed(lambda: conv.bias)),
                   gn=gn, act=cabi.ACT_MISH, **kw)
@@ -316,7 +350,7 @@ def _unet_body(p: Program, net, x: View, horizon: int, k: int, film_of: Callable
         raise Unsupported("horizon too short for the number of stages")
     # cat buffer of up-stage u holds [x | skip h[n-1-u]] at resolution n-1-u
     cats = [View(p.buf(p.rows, lens[n - 1 - u], 2 * chans[n - 1 - u], dtype=p.act_dtype), lens[n - 1 - u],
-                 2 * chans[n - 1 - u]) for u in range(n - 1)]
+                 2 * chans[n - 1 - u], tf32=p.math == cabi.MATH_TF32_TC) for u in range(n - 1)]
 
     def skip_slot(s):     # where h[s] lives
         if s == 0 or n == 1:
@@ -370,7 +404,7 @@ def _all_resblocks(net):
     return blocks
 
 
-def lower_janner(p: Program, net: JannerUNet1d, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
+def lower_janner(p: Program, net: nn.Module, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
     if any(not isinstance(s[2], nn.Identity) for s in list(net.downs) + list(net.ups)) or \
             not isinstance(net.mid_attn, nn.Identity):
         raise Unsupported("JannerUNet1d(attention=True)")
@@ -414,7 +448,7 @@ def lower_janner(p: Program, net: JannerUNet1d, x: View, horizon: int, has_cond:
                bias=_const_vec(p.packed(lambda: torch.cat([b.emb_mlp[1].bias for b in blocks], 0))))
         film = {id(b): dict(shift=_vec(sample=tb.t.view(p.rows, total), col=o)) for b, o in zip(blocks, offs)}
 
-    x = View(x.t, x.L, x.C, x.offset, x.bstride, x.lstride)
+    x = View(x.t, x.L, x.C, x.offset, x.bstride, x.lstride, x.tf32)
     # first conv reads x_t; under two-branch CFG both halves of the doubled batch read the same rows
     first = blocks[0]
     pred = _unet_body_with_mod(p, net, x, horizon, k, lambda b: film[id(b)], 4, 5, in_batch_mod, first)
@@ -437,7 +471,7 @@ def _unet_body_with_mod(p, net, x, horizon, k, film_of, stage_len, final_k, in_b
     return pred
 
 
-def lower_chi(p: Program, net: ChiUNet1d, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
+def lower_chi(p: Program, net: nn.Module, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
     if not net.obs_as_global_cond:
         raise Unsupported("ChiUNet1d(obs_as_global_cond=False)")
     if not has_cond:
@@ -470,7 +504,7 @@ def lower_chi(p: Program, net: ChiUNet1d, x: View, horizon: int, has_cond: bool,
 
 
 # =============================================================================== DQLMlp
-def lower_dql(p: Program, net: DQLMlp, x: View, has_cond: bool, in_batch_mod: int) -> View:
+def lower_dql(p: Program, net: nn.Module, x: View, has_cond: bool, in_batch_mod: int) -> View:
     act_dim = x.C
     lin1 = net.mid_layer[0]
     e_dim = net.time_mlp[2].out_features
@@ -500,7 +534,7 @@ def lower_dql(p: Program, net: DQLMlp, x: View, has_cond: bool, in_batch_mod: in
 
 
 # =============================================================================== DiT1d
-def lower_dit(p: Program, net: DiT1d, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
+def lower_dit(p: Program, net: nn.Module, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
     d = net.d_model
     depth = len(net.blocks)
     heads = net.blocks[0].attn.num_heads
@@ -543,9 +577,9 @@ def lower_dit(p: Program, net: DiT1d, x: View, horizon: int, has_cond: bool, in_
     # head_dim 32 (every pipeline) and L <= 128: attention runs on tensor cores (mma.sync, bf16 q/k/v); otherwise fp32 CUDA cores
     QKV = p.act(L, 3 * d) if (d // heads == 32 and L <= 128) else p.act(L, 3 * d, f32)
     Y, ATT, HID = p.act(L, d), p.act(L, d), p.act(L, 4 * d)
-    if p.math == cabi.MATH_BF16_TC and x.t.dtype == torch.float32 and x.lstride == x.C and x.bstride == L * x.C:
-        # x_t enters as a 32-channel-padded bf16 copy (kept fresh by the solver update, like the UNets' hand-over)
-        kin = 32 * ((x.C + 31) // 32)
+    if p.tc and x.t.dtype == torch.float32 and x.lstride == x.C and x.bstride == L * x.C:
+        # x_t enters as a channel-padded copy in the activation dtype (kept fresh by the solver update, like the UNets' hand-over)
+        kin = p.k_align * ((x.C + p.k_align - 1) // p.k_align)
         xb = p.cast_pad(x, kin, rows=in_batch_mod or p.rows)
         w_in = w_rows(lambda: F.pad(net.x_proj.weight, (0, kin - net.x_proj.weight.shape[1])))
         p.token_linear(xb, w_in, X, bias=_const_vec(p.packed(lambda: net.x_proj.bias)),
@@ -577,8 +611,9 @@ def lower_dit(p: Program, net: DiT1d, x: View, horizon: int, has_cond: bool, in_
 def lower_denoiser(p: Program, net: nn.Module, x: View, x_shape, has_cond: bool, in_batch_mod: int) -> View:
     """Dispatch on the backbone type (reference instances are recognised structurally by class name)."""
     name = type(net).__name__
-    if name in ("JannerUNet1d", "ChiUNet1d") and len(x_shape) == 2 and p.math == cabi.MATH_BF16_TC:
-        x = p.cast_pad(x, 32 * ((x.C + 31) // 32), rows=in_batch_mod or p.rows)   # TMA/UMMA want K in multiples of 32 bf16
+    if name in ("JannerUNet1d", "ChiUNet1d") and len(x_shape) == 2 and p.tc:
+        # TMA/UMMA want K in whole 64-byte rows: 32 bf16 / 16 fp32 channels
+        x = p.cast_pad(x, p.k_align * ((x.C + p.k_align - 1) // p.k_align), rows=in_batch_mod or p.rows)
     if name == "JannerUNet1d" and len(x_shape) == 2:
         return lower_janner(p, net, x, x_shape[0], has_cond, in_batch_mod)
     if name == "ChiUNet1d" and len(x_shape) == 2:

@@ -14,7 +14,9 @@ odd shapes ...) and the caller continues on the PyTorch path; a missing/unsound 
 
 Environment switches (no flag system, pipelines stay unchanged):
   CDS_BACKEND = auto | torch | cuda    (torch: never use the engine; cuda: raise instead of falling back)
-  CDS_MATH    = fp32 | bf16            (operand precision of the conv/linear GEMMs)
+  CDS_MATH    = tf32 | bf16 | fp32     (conv/linear GEMMs: tcgen05 with fp32 activations read as TF32 -- the default, the
+                                        arithmetic of the reference's own GPU path --, tcgen05 with bf16 operands and
+                                        activations, or fp32 FMA on CUDA cores)
   CDS_GRAPH   = 1 | 0                  (0: launch kernels directly, for profilers)
 """
 import os
@@ -33,8 +35,14 @@ def _backend():
     return os.environ.get("CDS_BACKEND", "auto")
 
 
+_MATH_MODES = {"fp32": cabi.MATH_FP32, "bf16": cabi.MATH_BF16_TC, "tf32": cabi.MATH_TF32_TC}
+
+
 def _math_mode():
-    return cabi.MATH_BF16_TC if os.environ.get("CDS_MATH", "fp32") == "bf16" else cabi.MATH_FP32
+    name = os.environ.get("CDS_MATH", "tf32")
+    if name not in _MATH_MODES:
+        raise ValueError(f"CDS_MATH={name!r}: expected one of {sorted(_MATH_MODES)}")
+    return _MATH_MODES[name]
 
 
 def _weights_version(module: torch.nn.Module):
@@ -151,6 +159,7 @@ class SamplerPlan:
                 if cop.kind == cabi.OP_CAST and cop.u.cast.in_ == self.x.data_ptr() + fo and cop.u.cast.batch == sub:
                     cop.flags |= cabi.OPF_ONCE
                     u.x_cast, u.cast_C_in, u.cast_C_out = cop.u.cast.out, cop.u.cast.C_in, cop.u.cast.C_out
+                    u.x_cast_dtype = cop.u.cast.out_dtype
             self._update_ops.append(op)
             p.ops.append(op)
             self._fillers += [(fn, sl) for fn in p.per_call]

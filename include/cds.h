@@ -29,7 +29,7 @@
  *  - activations are "channels last": element (b, l, c) of a (batch, L, C) tensor sits at
  *    base + b*bstride + l*lstride + c (strides in elements), which is also the reference's public (b, horizon, dim)
  *    layout, so x_t needs no permute on entry or exit.  x_t, predictions and all tables are fp32; intermediate
- *    activations are fp32 (CDS_MATH_FP32 programs) or bf16 (CDS_MATH_BF16_TC programs).
+ *    activations are fp32 (CDS_MATH_FP32 and CDS_MATH_TF32_TC programs) or bf16 (CDS_MATH_BF16_TC programs).
  *  - "per-iteration" operands are indexed by a device-resident iteration counter, so one captured graph
  *    serves every reverse iteration:  vec(b, c) = step[iter*step_stride + c] + sample[b*sample_stride + c]
  *    (either part may be NULL = 0).
@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CDS_ABI_VERSION 4
+#define CDS_ABI_VERSION 5
 
 typedef enum cds_status {
   CDS_OK = 0,
@@ -59,10 +59,18 @@ typedef enum cds_op_kind { CDS_OP_CONV = 0, CDS_OP_UPDATE = 1, CDS_OP_LNMOD = 2,
                            CDS_OP_CAST = 5 } cds_op_kind;
 typedef enum cds_act { CDS_ACT_NONE = 0, CDS_ACT_MISH = 1, CDS_ACT_SILU = 2, CDS_ACT_GELU_TANH = 3,
                        CDS_ACT_MISH_SILU = 4 /* silu(mish(x)): DiT's map_emb tail feeding every adaLN (dit.py:26,43,71) */ } cds_act;
-/* math mode of CDS_OP_CONV: fp32 CUDA-core FMA (bit-faithful to the fp32 oracle up to summation order), or
- * tcgen05 tensor cores with bf16 operands / fp32 TMEM accumulation */
-typedef enum cds_math { CDS_MATH_FP32 = 0, CDS_MATH_BF16_TC = 1 } cds_math;
-typedef enum cds_dtype { CDS_F32 = 0, CDS_BF16 = 1 } cds_dtype;
+/* math mode of CDS_OP_CONV:
+ *   CDS_MATH_FP32     fp32 CUDA-core FMA (bit-faithful to the fp32 oracle up to summation order)
+ *   CDS_MATH_BF16_TC  tcgen05 tensor cores, bf16 operands and bf16 inter-layer activations, fp32 TMEM accumulation
+ *   CDS_MATH_TF32_TC  tcgen05 tensor cores kind::tf32: fp32 activations and weights in memory, read by the MMA as TF32
+ *                     (10-bit mantissa), fp32 accumulation -- the arithmetic of the reference's own GPU path
+ *                     (torch.backends.cudnn.allow_tf32 = True is PyTorch's default for convolutions)            */
+typedef enum cds_math { CDS_MATH_FP32 = 0, CDS_MATH_BF16_TC = 1, CDS_MATH_TF32_TC = 2 } cds_math;
+/* element type of an activation tensor.  CDS_TF32 is fp32 STORAGE whose values are rounded to the nearest TF32 (10-bit
+ * mantissa, ties away from zero, like cvt.rna.tf32.f32) when an operator writes them: tcgen05 kind::tf32 ignores the low 13
+ * mantissa bits of its fp32 operands (truncation), so an operand that is already rounded is read exactly and its rounding
+ * error is unbiased and half as large.  Producers honour it on store; consumers read CDS_TF32 exactly like CDS_F32. */
+typedef enum cds_dtype { CDS_F32 = 0, CDS_BF16 = 1, CDS_TF32 = 2 } cds_dtype;
 /* update shapes; must match cleandiffuser_b200/diffusion/solvers.py */
 typedef enum cds_update_kind { CDS_UPD_DDPM = 0, CDS_UPD_DDIM = 1, CDS_UPD_EPS = 2, CDS_UPD_X = 3, CDS_UPD_X2M = 4, CDS_UPD_CM = 5 } cds_update_kind;
 
@@ -92,14 +100,15 @@ typedef struct cds_conv_op {
   int32_t in_batch_mod;            /* >0: read in() at batch index b % in_batch_mod (CFG branches share x_t) */
   const void* in;   int64_t in_bstride;  int32_t in_lstride;   /* strides in ELEMENTS of the tensor's dtype */
   const void*  w;                  /* CDS_MATH_FP32: fp32 [taps*C_in][C_out*phases] (K rows, N contiguous)
-                                      CDS_MATH_BF16_TC: bf16 [taps][C_out][C_in]     (K contiguous, TMA/UMMA K-major) */
+                                      CDS_MATH_BF16_TC: bf16 [taps][C_out][C_in]     (K contiguous, TMA/UMMA K-major)
+                                      CDS_MATH_TF32_TC: fp32 [taps][C_out][C_in]     (same packing, fp32 elements) */
   cds_vec bias;
   int32_t groups; const float* gn_gamma; const float* gn_beta; float gn_eps;
   int32_t act;
   cds_vec scale, shift;
   const void* res; int64_t res_bstride; int32_t res_lstride; int32_t res_batch_mod;
   const void* res_in; int64_t res_in_bstride; int32_t res_in_lstride; int32_t res_C;
-  const void* res_w; const float* res_bias;   /* res_w: fp32 [res_C][C_out] or bf16 [C_out][res_C], as `w` */
+  const void* res_w; const float* res_bias;   /* res_w: fp32 [res_C][C_out] (FP32) or bf16 / fp32 [C_out][res_C] (TC modes), as `w` */
   void* out; int64_t out_bstride; int32_t out_lstride;
   int32_t math;                    /* cds_math: which kernel family / weight layout */
   int32_t in_dtype, out_dtype, res_dtype, res_in_dtype;   /* cds_dtype of the activation tensors */
@@ -124,11 +133,13 @@ typedef struct cds_attn_op {
   int32_t qkv_dtype;                            /* cds_dtype of qkv: bf16 (head_dim 32, L <= 128) runs on tensor cores (mma.sync) */
 } cds_attn_op;
 
-/* dense fp32 (batch, L, C_in) -> dense bf16 (batch, L, C_out), channels [C_in, C_out) zero: gives x_t the 32-channel
- * bf16 form the tensor-core conv reads through TMA (the UNets' first conv has C_in = obs+act dims, e.g. 14) */
+/* dense fp32 (batch, L, C_in) -> dense (batch, L, C_out) of out_dtype, channels [C_in, C_out) zero: gives x_t the
+ * channel-padded form the tensor-core conv reads through TMA (the UNets' first conv has C_in = obs+act dims, e.g. 14:
+ * 32 bf16 channels for CDS_MATH_BF16_TC, 16 fp32 channels for CDS_MATH_TF32_TC -- rows must be multiples of 16 bytes) */
 typedef struct cds_cast_op {
   int32_t batch, L, C_in, C_out;
   const float* in; void* out;
+  int32_t out_dtype;             /* cds_dtype of out */
 } cds_cast_op;
 
 /* consistency model: if row.NOISE: x += K2 * noise[slot];  xin = K3 * x */
@@ -157,6 +168,7 @@ typedef struct cds_update_op {
    * element (r, c) of the dense (rows, cast_C_in) view of x goes to x_cast[r*cast_C_out + c]; pad channels are never
    * written (a CDS_OPF_ONCE cast zeroes them and converts the initial x_t).  NULL = no copy. */
   void* x_cast; int32_t cast_C_in; int32_t cast_C_out;
+  int32_t x_cast_dtype;          /* cds_dtype of x_cast */
 } cds_update_op;
 
 /* cds_op.flags */
@@ -181,9 +193,10 @@ const char* cds_last_error(void);
 /* number of SMs etc. of `device`, -1 on error; used by the host to size workspaces */
 int         cds_device_sm_count(int device);
 
-/* 1 if the tensor-core (CDS_MATH_BF16_TC) kernel can run `op` as described (dtypes, strides, shapes; `w` may still be
- * NULL), else 0: the host lowering asks before choosing the weight layout; ops that are not eligible run on the
- * CUDA-core kernel with math = CDS_MATH_FP32 (which accepts fp32 or bf16 activations).  Pure host logic. */
+/* 1 if the tensor-core kernel of op->math (CDS_MATH_BF16_TC or CDS_MATH_TF32_TC; anything else is read as BF16_TC) can run
+ * `op` as described (dtypes, strides, shapes; `w` may still be NULL), else 0: the host lowering asks before choosing the
+ * weight layout; ops that are not eligible run on the CUDA-core kernel with math = CDS_MATH_FP32 (which accepts fp32 or
+ * bf16 activations).  Pure host logic. */
 int cds_conv_tc_supported(const cds_conv_op* op);
 
 /* A plan = the per-iteration operator program for one (model, shape, option set) on one device. */

@@ -45,3 +45,28 @@ def oracle_cond_emb(spec, cond):
 def tape_of(npz, name):
     n = int(npz[name + "/n_draws"])
     return [npz[f"{name}/z{j}"] for j in range(n)]
+
+
+# ---------------------------------------------------------------- BASELINE configs (cleandiffuser_b200/workloads.py)
+def workload_oracle(wl, prior, cond, draws):
+    """The CPU oracle's result for the workload's computation on ``prior`` / ``cond`` (a slice of the batch) with the noise
+    draws ``draws`` (list of arrays, already sliced).  Resolves the plain-data ``wl.oracle`` description."""
+    import oracle.sampler as osamp
+    spec = wl.oracle
+    net_kw = dict(spec["net"])
+    net_fn = getattr(onets, net_kw.pop("fn"))
+    model = wl.agent.model_ema if hasattr(wl.agent, "model_ema") else wl.agent.model
+    sd = {k: v.detach().cpu().clone() for k, v in model["diffusion"].state_dict().items()}
+    fn = lambda x, t, c=None: net_fn(sd, x, t, c, **net_kw)   # noqa: E731
+    cond_emb = None
+    if cond is not None:
+        cspec = spec.get("cond")
+        if cspec is None:
+            cond_emb = cond * 1.
+        else:
+            csd = {k: v.detach().cpu().clone() for k, v in model["condition"].state_dict().items()}
+            act = {"silu": torch.nn.functional.silu}[cspec["act"]]
+            cond_emb = getattr(onets, cspec["fn"])(csd, cond, act, cspec["n_hidden"])
+    with torch.no_grad():
+        return getattr(osamp, spec["sampler"])(fn, prior, osamp.Tape(draws), fix_mask=spec["fix_mask"], cond_emb=cond_emb,
+                                               **spec["kwargs"])

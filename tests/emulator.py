@@ -30,9 +30,15 @@ def _f32_to_bf16(x):
     return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
 
 
+def _rn_tf32(x):
+    """fp32 -> nearest TF32 (ties away from zero): what producers store into a CDS_TF32 tensor"""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 def _load(ptr, shape, strides, dtype):
     """float32 COPY of an fp32 / bf16 activation view (strides in elements)."""
-    if dtype == cabi.F32:
+    if dtype in (cabi.F32, cabi.TF32):
         return np.array(_arr(ptr, shape, strides))
     extent = 1 + sum((s - 1) * abs(st) for s, st in zip(shape, strides))
     flat = np.ctypeslib.as_array((ctypes.c_uint16 * extent).from_address(ptr))
@@ -40,8 +46,8 @@ def _load(ptr, shape, strides, dtype):
 
 
 def _store(ptr, shape, strides, dtype, values):
-    if dtype == cabi.F32:
-        _arr(ptr, shape, strides)[...] = values
+    if dtype in (cabi.F32, cabi.TF32):
+        _arr(ptr, shape, strides)[...] = _rn_tf32(values) if dtype == cabi.TF32 else values
         return
     extent = 1 + sum((s - 1) * abs(st) for s, st in zip(shape, strides))
     flat = np.ctypeslib.as_array((ctypes.c_uint16 * extent).from_address(ptr))
@@ -79,15 +85,23 @@ def _act(kind, x):
     return x
 
 
+def _tf32_trunc(x):
+    """what tcgen05 kind::tf32 sees of an fp32 operand: the low 13 mantissa bits are ignored"""
+    return (np.ascontiguousarray(x, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 def run_conv(c, it):
     B, N = c.batch, c.C_out * c.phases
     bmod = c.in_batch_mod if c.in_batch_mod > 0 else B
     xin = _load(c.in_, (bmod, c.L_in, c.C_in), (c.in_bstride, c.in_lstride, 1), c.in_dtype)
     xin = xin[np.arange(B) % bmod]
-    tc = c.math == cabi.MATH_BF16_TC
-    if tc:      # bf16 [taps][C_out*phases][C_in]
-        assert c.in_dtype == cabi.BF16
-        w = _load(c.w, (c.taps, N, c.C_in), (N * c.C_in, c.C_in, 1), cabi.BF16).transpose(0, 2, 1)
+    tc = c.math in cabi.TC_MODES
+    wdt = cabi.F32 if c.math == cabi.MATH_TF32_TC else cabi.BF16
+    if tc:      # bf16 / fp32 [taps][C_out*phases][C_in]
+        assert c.in_dtype == wdt or (wdt == cabi.F32 and c.in_dtype == cabi.TF32)
+        w = _load(c.w, (c.taps, N, c.C_in), (N * c.C_in, c.C_in, 1), wdt).transpose(0, 2, 1)
+        if c.math == cabi.MATH_TF32_TC:
+            xin, w = _tf32_trunc(xin), _tf32_trunc(w)
     else:
         w = _arr(c.w, (c.taps, c.C_in, N), (c.C_in * N, N, 1))
     acc = np.zeros((B, c.L_out, N), dtype=np.float64)
@@ -124,7 +138,9 @@ def run_conv(c, it):
     if c.res_w:
         rin = _load(c.res_in, (rmod, c.L_out, c.res_C), (c.res_in_bstride, c.res_in_lstride, 1),
                     c.res_in_dtype)[np.arange(B) % rmod]
-        rw = _load(c.res_w, (c.C_out, c.res_C), (c.res_C, 1), cabi.BF16).T if tc else _arr(c.res_w, (c.res_C, N), (N, 1))
+        rw = _load(c.res_w, (c.C_out, c.res_C), (c.res_C, 1), wdt).T if tc else _arr(c.res_w, (c.res_C, N), (N, 1))
+        if c.math == cabi.MATH_TF32_TC:
+            rin, rw = _tf32_trunc(rin), _tf32_trunc(rw)
         y = y + (rin.astype(np.float64) @ rw.astype(np.float64)).astype(np.float32)
         if c.res_bias:
             y = y + _arr(c.res_bias, (c.C_out,), (1,))[chan]
@@ -156,7 +172,7 @@ def run_cast(k):
     x = _arr(k.in_, (k.batch, k.L, k.C_in), (k.L * k.C_in, k.C_in, 1))
     y = np.zeros((k.batch, k.L, k.C_out), dtype=np.float32)
     y[..., :k.C_in] = x
-    _store(k.out, (k.batch, k.L, k.C_out), (k.L * k.C_out, k.C_out, 1), cabi.BF16, y)
+    _store(k.out, (k.batch, k.L, k.C_out), (k.L * k.C_out, k.C_out, 1), k.out_dtype, y)
 
 
 def _row(coef, it):
@@ -227,9 +243,9 @@ def run_update(u, it):
     x[...] = out.astype(np.float32)
     if u.x_cast:                     # bf16 channel-padded copy of the new x_t (pad channels untouched)
         rows = n // u.cast_C_in
-        y = _load(u.x_cast, (rows, u.cast_C_out), (u.cast_C_out, 1), cabi.BF16)
+        y = _load(u.x_cast, (rows, u.cast_C_out), (u.cast_C_out, 1), u.x_cast_dtype)
         y[:, :u.cast_C_in] = x.reshape(rows, u.cast_C_in)
-        _store(u.x_cast, (rows, u.cast_C_out), (u.cast_C_out, 1), cabi.BF16, y)
+        _store(u.x_cast, (rows, u.cast_C_out), (u.cast_C_out, 1), u.x_cast_dtype, y)
 
 
 def run_program(ops, n_iters, first=0):

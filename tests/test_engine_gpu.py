@@ -246,6 +246,66 @@ def test_parallel_branches_give_the_same_bits(math, monkeypatch):
         assert torch.equal(v, ref), k
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# TF32 tensor-core programs (CDS_MATH=tf32, the library default and what bench.py measures): fp32 activations and weights in
+# memory, tcgen05 kind::tf32 (operands read with a 10-bit mantissa), fp32 TMEM accumulation and fp32 GN/Mish epilogue -- the
+# arithmetic of the reference's own GPU path (cuDNN TF32 convs).  Stated tolerance vs the fp32 reference: max-abs 2e-2,
+# mean-abs 2e-3 (per forward and after a full sampler; emulated figures: ~4e-3 / ~9e-4 per forward).
+TF32_MAX, TF32_MEAN = 2e-2, 2e-3
+
+
+@pytest.mark.parametrize("name", list(cases.NETS))
+def test_denoiser_forward_tf32_tensor_cores(golden, name, monkeypatch):
+    monkeypatch.setenv("CDS_MATH", "tf32")
+    case = cases.NETS[name]
+    net, _ = product_net(case)
+    net = net.to(DEV)
+    x, t, cond = cases.net_inputs(case)
+    cond_emb = None if cond is None else cond.to(DEV)
+    want = golden["nets"][name + "/y"]
+    for i in range(cases.NET_BATCH):
+        y = runtime.engine_forward(net, x.to(DEV), t[i:i + 1], cond_emb)
+        err = np.abs(y[i].cpu().numpy() - want[i])
+        assert err.max() < TF32_MAX and err.mean() < TF32_MEAN, (name, i, float(err.max()), float(err.mean()))
+
+
+@pytest.mark.parametrize("name", ["disc_dup_ddpm_x0", "disc_dup_ddim_eps", "cont_ddim_eps", "cont_sde_dpmsolverpp_2M_x0",
+                                  "cont_cfg2branch_2M", "disc_warm_ddim"])
+def test_sampler_tf32_tensor_cores_goldens(golden, name, monkeypatch):
+    """Reverse loop on the TF32 programs (once-cast + update-fused fp32 x_t copy + programmatic dependent launch) against the
+    reference goldens; graph replay and direct launches must give the same bits."""
+    monkeypatch.setenv("CDS_MATH", "tf32")
+    spec = cases.sampler_cases()[name]
+    outs = []
+    for graph in ("1", "0"):
+        monkeypatch.setenv("CDS_GRAPH", graph)
+        agent, inp, kw = build_agent(spec, device=DEV)
+        for k in ("condition_cfg", "warm_start_reference"):
+            if kw.get(k) is not None:
+                kw[k] = kw[k].to(DEV)
+        tape = NoiseTape(tape_of(golden["samplers"], name))
+        with tape.active(), torch.no_grad():
+            x0, _ = agent.sample(inp["prior"].to(DEV), **kw)
+        outs.append(x0.cpu())
+        err = np.abs(x0.cpu().numpy() - golden["samplers"][name + "/x0"])
+        # two-branch CFG (w_cfg = 2.5) multiplies the rounding of the two predictions by |w| + |1 - w| = 4, and that toy case
+        # clips most outputs to x_max: an element crossing the clip boundary at a different iteration is an isolated outlier
+        mx, mean = (0.15, 4 * TF32_MEAN) if "cfg2branch" in name else (TF32_MAX, TF32_MEAN)
+        assert err.max() < mx and err.mean() < mean, (name, graph, float(err.max()), float(err.mean()))
+    assert torch.equal(outs[0], outs[1])         # graph replay == direct launches
+
+
+def test_tf32_is_the_default_math_mode(monkeypatch):
+    monkeypatch.delenv("CDS_MATH", raising=False)
+    assert runtime._math_mode() == cabi.MATH_TF32_TC
+    from cleandiffuser_b200.engine.lower import Program, View, lower_denoiser
+    net, _ = product_net(cases.NETS["janner_cfg2"])
+    p = Program(torch.device(DEV), 256, 1, runtime._math_mode())
+    lower_denoiser(p, net.to(DEV), View(p.buf(256, 32, 14), 32, 14), (32, 14), False, 0)
+    convs = [op.u.conv for op in p.ops if op.kind == cabi.OP_CONV]
+    assert len(convs) == 40 and all(c.math == cabi.MATH_TF32_TC and c.in_dtype == cabi.TF32 for c in convs)
+
+
 def test_chiunet_full_size_on_tensor_cores(monkeypatch):
     """cfg3's backbone exactly as the DP pipelines build it (model_dim 256 -> 256/512/1024 channels, 68.9 M parameters): every conv,
     the C_out = 512 / 1024 ones included (2 / 4 CTAs of 256 columns, two-pass GroupNorm), runs on tcgen05; checked against the

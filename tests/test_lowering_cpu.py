@@ -96,6 +96,61 @@ def test_lowered_denoiser_bf16(golden, name, monkeypatch):
         assert err.max() < 0.08 and err.mean() < 0.015, (name, i, err.max(), err.mean())
 
 
+@pytest.mark.parametrize("name", list(cases.NETS))
+def test_lowered_denoiser_tf32(golden, name, monkeypatch):
+    """TF32 programs (the default math mode): fp32 activations, fp32 [tap][Cout][Cin] weights rounded to TF32, operands
+    truncated to a 10-bit mantissa by the interpreter as tcgen05 kind::tf32 does."""
+    monkeypatch.setenv("CDS_MATH", "tf32")
+    case = cases.NETS[name]
+    net, _ = product_net(case)
+    x, t, cond = cases.net_inputs(case)
+    want = golden["nets"][name + "/y"]
+    for i in range(cases.NET_BATCH):
+        y = runtime.engine_forward(net, x, t[i:i + 1], cond)
+        err = np.abs(y[i].numpy() - want[i])
+        assert err.max() < 2e-2 and err.mean() < 2e-3, (name, i, err.max(), err.mean())
+
+
+def test_tf32_program_uses_tensor_core_ops(monkeypatch):
+    monkeypatch.delenv("CDS_MATH", raising=False)            # tf32 is the default
+    from cleandiffuser_b200.engine import cabi
+    from cleandiffuser_b200.engine.lower import Program, View, lower_denoiser
+    assert runtime._math_mode() == cabi.MATH_TF32_TC
+    net, _ = product_net(cases.NETS["janner_cfg2"])
+    p = Program(torch.device("cpu"), 8, 1, cabi.MATH_TF32_TC)
+    xin = p.buf(8, 32, 14)
+    lower_denoiser(p, net, View(xin, 32, 14), (32, 14), False, 0)
+    convs = [op.u.conv for op in p.ops if op.kind == cabi.OP_CONV]
+    # x_t is handed over as a 16-channel fp32 copy (64-byte rows), every conv of the UNet is a TF32 tensor-core operator; what
+    # feeds a TF32 MMA is written TF32-rounded (cds_dtype CDS_TF32), the prediction itself stays exact fp32
+    assert p.ops[0].kind == cabi.OP_CAST and p.ops[0].u.cast.C_out == 16 and p.ops[0].u.cast.out_dtype == cabi.TF32
+    assert len(convs) == 40 and all(c.math == cabi.MATH_TF32_TC and c.in_dtype == cabi.TF32 for c in convs)
+    assert all(c.out_dtype == cabi.TF32 for c in convs[:-1]) and convs[-1].out_dtype == cabi.F32
+
+
+@pytest.mark.parametrize("name", ["disc_dup_ddpm_x0", "cont_ddim_eps", "cont_cfg2branch_2M"])
+def test_lowered_sampler_tf32(golden, name, monkeypatch):
+    monkeypatch.setenv("CDS_MATH", "tf32")
+    from cleandiffuser_b200.engine import cabi
+    spec = cases.sampler_cases()[name]
+    agent, inp, kw = build_agent(spec)
+    tape = NoiseTape(tape_of(golden["samplers"], name))
+    with tape.active(), torch.no_grad():
+        x0, _ = agent.sample(inp["prior"], **kw)
+    plan = next(iter(agent._engine_plans.values()))
+    ops = plan.program.ops
+    casts = [op for op in ops if op.kind == cabi.OP_CAST]
+    assert len(casts) == 1 and casts[0].flags & cabi.OPF_ONCE
+    upd = ops[-1].u.update
+    assert ops[-1].kind == cabi.OP_UPDATE and upd.x_cast == casts[0].u.cast.out and upd.cast_C_out == 16
+    assert upd.x_cast_dtype == cabi.TF32
+    err = np.abs(x0.numpy() - golden["samplers"][name + "/x0"])
+    # two-branch CFG (w_cfg = 2.5) multiplies the rounding of the two predictions by |w| + |1 - w| = 4, and this toy case clips
+    # most of its outputs to x_max: an element that crosses the clip boundary at a different iteration is an isolated outlier
+    mx, mean = (0.15, 8e-3) if "cfg2branch" in name else (2e-2, 2e-3)
+    assert err.max() < mx and err.mean() < mean, (float(err.max()), float(err.mean()))
+
+
 def test_bf16_program_uses_tensor_core_ops(monkeypatch):
     monkeypatch.setenv("CDS_MATH", "bf16")
     from cleandiffuser_b200.engine import cabi
