@@ -175,7 +175,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="trajectories per GPU (default: the BASELINE config)")
-    ap.add_argument("--math", default=os.environ.get("CDS_MATH", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--math", default=os.environ.get("CDS_MATH", "tf32"), choices=["tf32", "bf16", "fp32"],
+                    help="tf32 (default = the library default): tcgen05 kind::tf32 over fp32 activations; bf16: tcgen05 with bf16 "
+                         "operands and activations; fp32: CUDA-core FMA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -329,7 +331,7 @@ def main():
         for i, (op, t_ms) in enumerate(zip(ops, per_op)):
             if op.kind == 0:
                 c = op.u.conv
-                log(f"op {i:2d} conv {'tc ' if c.math == 1 else 'f32'} L {c.L_in:3d}->{c.L_out * c.phases:3d} C {c.C_in:4d}->{c.C_out:4d} "
+                log(f"op {i:2d} conv {('f32', 'bf16', 'tf32')[c.math]:4s} L {c.L_in:3d}->{c.L_out * c.phases:3d} C {c.C_in:4d}->{c.C_out:4d} "
                     f"k{c.taps} s{c.stride} gn{c.groups} res{'W' if c.res_w else ('I' if c.res else '-')}: {t_ms * 1e3:8.1f} us")
             else:
                 log(f"op {i:2d} kind {op.kind}{' (once per call)' if op.flags & 1 else ''}: {t_ms * 1e3:8.1f} us")
@@ -376,7 +378,8 @@ def main():
         line = {"metric": "sampled trajectories/sec (H=32, 100 DDPM steps)", "value": value, "unit": "trajectories/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if args.math == "fp32" else "bf16 operands / f32 accumulate", "data": "synthetic",
+                "dtype": {"fp32": "f32", "tf32": "tf32 (fp32 activations and weights in HBM, tcgen05 kind::tf32, f32 accumulate)",
+                          "bf16": "bf16 operands and activations / f32 accumulate"}[args.math], "data": "synthetic",
                 "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": prior_host.numel() * 4,
                         "d2h_bytes_per_step": B * H * D * 4, "ms_per_step": ms_e2e / args.steps},

@@ -6,3 +6,4 @@ runs ``sample()``'s reverse loop as hand-written sm_100a CUDA behind a C-ABI (``
 __version__ = "0.1.0"
 
 from . import utils, nn_condition, nn_diffusion, diffusion  # noqa: F401
+from .overlay import install, uninstall  # noqa: F401  (drop-in route A: rebind the installed reference's sampler classes)

@@ -34,6 +34,23 @@ int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(CDS_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
   } while (0)
 
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: a plan may live on a
+// GPU that is not the calling thread's current one (multi-GPU processes), and PyTorch's notion of "current device" must not
+// change under the caller.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;          // nothing to restore
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define CDS_ON_DEVICE(dev)                                                                                       \
+  DeviceGuard guard__(dev);                                                                                      \
+  if (guard__.err != cudaSuccess) return fail(CDS_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (int)(dev), cudaGetErrorString(guard__.err))
+
 struct Step {            // one validated operator + its kernel choice
   cds_op op;
   int conv_bn = 0;
@@ -262,7 +279,7 @@ int cds_plan_create(int device, cds_plan** out) {
 
 int cds_plan_destroy(cds_plan* p) {
   if (!p) return CDS_OK;
-  cudaSetDevice(p->device);
+  DeviceGuard guard(p->device);
   if (p->exec) cudaGraphExecDestroy(p->exec);
   if (p->graph) cudaGraphDestroy(p->graph);
   if (p->exec_multi) cudaGraphExecDestroy(p->exec_multi);
@@ -295,7 +312,7 @@ int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
   if (!p) return fail(CDS_ERR_INVALID, "plan_finalize: null plan");
   if (p->finalized) return fail(CDS_ERR_STATE, "plan already finalized");
   if (n_iters <= 0 || p->steps.empty()) return fail(CDS_ERR_INVALID, "plan_finalize: empty program");
-  CDS_CUDA(cudaSetDevice(p->device));
+  CDS_ON_DEVICE(p->device);
   { int rc = preload_kernels(); if (rc != CDS_OK) return rc; }
   CDS_CUDA(cudaMalloc(&p->d_iter, 2 * sizeof(int)));      // [0] iteration counter, [1] finished-block count of the update
   CDS_CUDA(cudaMemset(p->d_iter, 0, 2 * sizeof(int)));
@@ -383,7 +400,7 @@ int cds_plan_run(cds_plan* p, int32_t first, int32_t count, void* stream, int32_
   if (first < 0 || count < 0 || first + count > p->n_iters)
     return fail(CDS_ERR_INVALID, "plan_run: iterations [%d, %d) outside [0, %d)", first, first + count, p->n_iters);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CDS_CUDA(cudaSetDevice(p->device));
+  CDS_ON_DEVICE(p->device);
   if (use_graph && !p->exec) {
     // capture on a private stream (the caller's may be the legacy default stream, which cannot capture);
     // capture itself never executes anything.
@@ -429,7 +446,7 @@ int cds_plan_profile(cds_plan* p, int32_t iter, void* stream, float* ms_per_op, 
   if (!ms_per_op || n_ops != (int)p->steps.size()) return fail(CDS_ERR_INVALID, "plan_profile: n_ops != %d", (int)p->steps.size());
   if (iter < 0 || iter >= p->n_iters) return fail(CDS_ERR_INVALID, "plan_profile: bad iteration");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CDS_CUDA(cudaSetDevice(p->device));
+  CDS_ON_DEVICE(p->device);
   std::vector<cudaEvent_t> ev(2 * n_ops);
   for (auto& e : ev) CDS_CUDA(cudaEventCreate(&e));
   cds::set_iter_kernel<<<1, 1, 0, st>>>(p->d_iter, iter);
@@ -470,7 +487,7 @@ int cds_debug_trace(void* device_buffer, int64_t capacity_entries, int32_t targe
 
 int cds_run_op(int device, const cds_op* op, int32_t iter, void* stream) {
   if (!op) return fail(CDS_ERR_INVALID, "run_op: null op");
-  CDS_CUDA(cudaSetDevice(device));
+  CDS_ON_DEVICE(device);
   Step s;
   int rc = validate(*op, &s);
   if (rc != CDS_OK) return rc;

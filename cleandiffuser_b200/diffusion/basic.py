@@ -55,8 +55,11 @@ class DiffusionModel:
         self.fix_mask = to_tensor(fix_mask, self.device)[None, ] if fix_mask is not None else 0.
         self.loss_weight = to_tensor(loss_weight, self.device)[None, ] if loss_weight is not None else 1.
 
-        # sm_100a sampling plans, keyed by (which weights, shapes, option set); see engine/runtime.py
+        # sm_100a sampling plans, keyed by (which weights, shapes, option set); see engine/runtime.py.  The plans hold packed
+        # copies of the weights: ``_weights_epoch`` is bumped by everything in this class that mutates parameters (optimiser
+        # step, EMA update, checkpoint load) and is part of the version the plans compare before every run.
         self._engine_plans = {}
+        self._weights_epoch = 0
 
     # ---- mode toggles -----------------------------------------------------
     def _classifier_net(self):
@@ -77,7 +80,10 @@ class DiffusionModel:
         keep = self.ema_rate
         with torch.no_grad():
             for live, avg in zip(self.model.parameters(), self.model_ema.parameters()):
-                avg.data.mul_(keep).add_(live.data, alpha=1. - keep)
+                # in-place on the parameter itself (not ``.data``): bumps its version counter, which the engine's packed-weight
+                # cache also watches
+                avg.mul_(keep).add_(live.detach(), alpha=1. - keep)
+        self._weights_epoch += 1
 
     def save(self, path: str):
         torch.save({"model": self.model.state_dict(), "model_ema": self.model_ema.state_dict()}, path)
@@ -86,6 +92,7 @@ class DiffusionModel:
         ckpt = torch.load(path, map_location=self.device)
         self.model.load_state_dict(ckpt["model"])
         self.model_ema.load_state_dict(ckpt["model_ema"])
+        self._weights_epoch += 1
         self._engine_plans.clear()   # packed weights are stale
 
     # ---- to be provided by the concrete diffusion process ------------------

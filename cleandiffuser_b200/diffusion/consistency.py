@@ -205,6 +205,7 @@ class ContinuousConsistencyModel(DiffusionModel):
             if self.grad_clip_norm else None
         self.optimizer.step()
         self.optimizer.zero_grad()
+        self._weights_epoch += 1
         if update_ema:
             self.ema_update()
         if loss_type == "training":

@@ -10,7 +10,7 @@ runs as one replayed CUDA-graph of hand-written sm_100a kernels with x_t residen
 (``engine/runtime.py``).  Everything else -- CPU tensors, user-defined backbones,
 ``requires_grad=True`` (Diffusion-QL back-propagates through the loop), classifier guidance,
 ``preserve_history`` -- takes the PyTorch loop below, which is step-for-step the reference
-algorithm and is pinned bit-exactly against it on CPU (tests/test_sampler_host.py).
+algorithm and is pinned against the reference's goldens on CPU (tests/test_host_golden.py).
 """
 from typing import Callable, Dict, Optional, Union
 
@@ -94,6 +94,7 @@ class BaseDiffusionSDE(DiffusionModel):
             if self.grad_clip_norm else None
         self.optimizer.step()
         self.optimizer.zero_grad()
+        self._weights_epoch += 1
         if update_ema:
             self.ema_update()
         return {"loss": loss.item(), "grad_norm": grad_norm}

@@ -18,8 +18,11 @@ Environment switches (no flag system, pipelines stay unchanged):
                                         arithmetic of the reference's own GPU path --, tcgen05 with bf16 operands and
                                         activations, or fp32 FMA on CUDA cores)
   CDS_GRAPH   = 1 | 0                  (0: launch kernels directly, for profilers)
+  CDS_NOISE_TAPE_MB                    (cap of the pre-drawn noise tape, default 4096: longer loops are run in chunks)
+  CDS_MAX_PLANS                        (plans kept per agent, default 8, least recently used evicted)
 """
 import os
+import types
 from typing import Optional
 
 import torch
@@ -45,15 +48,49 @@ def _math_mode():
     return _MATH_MODES[name]
 
 
-def _weights_version(module: torch.nn.Module):
-    acc = 0
+def _weights_version(module: torch.nn.Module, epoch: int = 0):
+    """Fingerprint of the parameters a plan has packed copies of: tensor identities + autograd version counters (bumped by
+    every in-place op on the parameter) + the owner's ``_weights_epoch`` (bumped by optimiser steps, EMA updates and
+    checkpoint loads of DiffusionModel -- writes through ``.data`` do not touch the version counters)."""
+    acc = int(epoch) & 0xFFFFFFFFFFFF
     for p in module.parameters():
         acc = (acc * 1000003 + p._version * 31 + p.data_ptr()) & 0xFFFFFFFFFFFF
     return acc
 
 
 def _device_ok(device: torch.device) -> bool:
-    return device.type == "cuda"
+    """Can the engine serve tensors on ``device``?  CDS_BACKEND=auto: only a CUDA device of compute capability >= 10.0 with
+    the sm_100a library built; anything else (CPU, A100/H100, extension not built) quietly takes the PyTorch loop like the
+    reference would.  CDS_BACKEND=cuda: any CUDA device qualifies here and a missing library / wrong architecture fails
+    loudly further down (tests and bench run that way)."""
+    if device.type != "cuda":
+        return False
+    if _backend() == "cuda":
+        return True
+    try:
+        major = torch.cuda.get_device_capability(device)[0]
+    except Exception:
+        return False
+    return major >= 10 and os.path.exists(cabi.lib_path())
+
+
+def _tape_budget_bytes():
+    return int(float(os.environ.get("CDS_NOISE_TAPE_MB", "4096")) * (1 << 20))
+
+
+def _randn_is_patched():
+    """True when a harness replaced torch.randn_like (tests replay recorded draws through it)."""
+    return not isinstance(torch.randn_like, types.BuiltinFunctionType)
+
+
+def _draw_noise(dst, like):
+    """One of the loop's ``torch.randn_like(x_t)`` draws, written into tape slot ``dst`` (batch, row).  Filling the slot in
+    place with ``normal_`` consumes the device generator exactly like ``randn_like`` (= ``empty_like().normal_()``) without
+    the temporary and the copy; a patched ``torch.randn_like`` (replay harness) is honoured."""
+    if _randn_is_patched():
+        dst.copy_(torch.randn_like(like).reshape(dst.shape))
+    else:
+        dst.view(like.shape).normal_()
 
 
 def _make_handle(device: torch.device, ops, n_iters: int):
@@ -171,7 +208,7 @@ class SamplerPlan:
                 root.packers += p.packers
 
         self.handle: Optional[cabi.Plan] = None
-        self.version = _weights_version(net)
+        self.version = None              # set by the first refresh_weights()
 
     def build(self, w_cfg: float):
         for op in self._update_ops:
@@ -179,14 +216,22 @@ class SamplerPlan:
         self.w_cfg = w_cfg
         self.handle = _make_handle(self.device, self.program.ops, self.n_iters)
 
-    def refresh_weights(self):
-        v = _weights_version(self.net)
-        if v != self.version:
+    def refresh_weights(self, epoch: int = 0):
+        v = _weights_version(self.net, epoch)
+        if self.version is None:         # packed at construction
+            self.version = v
+        elif v != self.version:
             for fn in self.program.packers:
                 fn()
             self.version = v
 
-    def run(self, t_all, cond_emb, use_graph=True, t_key=None):
+    def close(self):
+        if self.handle is not None:
+            self.handle.close()
+            self.handle = None
+
+    def fill_tables(self, t_all, cond_emb, t_key=None):
+        """Per-call tables (time-conditioning rows, per-trajectory condition terms), once per ``sample()``."""
         # table fillers that depend on (weights, timesteps) only are skipped when neither changed since the last call
         fresh = t_key is None or (t_key, self.version) != getattr(self, "_time_tables_key", None)
         with torch.no_grad():
@@ -194,16 +239,38 @@ class SamplerPlan:
                 if fresh or not getattr(fn, "time_only", False):
                     fn(_Ctx(t_all, _cond_rows(self.cfg_mode, None if cond_emb is None else cond_emb[sl])))
         self._time_tables_key = (t_key, self.version) if t_key is not None else None
+
+    def run(self, t_all, cond_emb, use_graph=True, t_key=None, first=0, count=None, fill=True):
+        if fill:
+            self.fill_tables(t_all, cond_emb, t_key)
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
         timed = STATS.get("time_loop") and self.device.type == "cuda"
         if timed:           # bench.py: device time of the reverse loop alone (events on the launching stream)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        self.handle.run(0, self.n_iters, stream, use_graph)
+        self.handle.run(first, self.n_iters - first if count is None else count, stream, use_graph)
         if timed:
             e1.record()
             STATS.setdefault("loop_events", []).append((e0, e1))
         STATS["launches"] = self.handle.launches_per_iter() * self.n_iters + 1
+
+    def run_chunked(self, t_all, cond_emb, xt, noise_rows, use_graph=True, t_key=None):
+        """The whole loop, with the noise tape refilled between chunks when it is shorter than the number of draws
+        (``noise_rows[n]`` = does iteration n draw?).  The draws are taken in loop order, so a seeded run consumes the
+        generator like the reference loop; everything is enqueued on one stream, so a refill cannot overtake its readers."""
+        cap = self.noise.shape[0] if self.noise is not None else 0
+        self.fill_tables(t_all, cond_emb, t_key)
+        first, used = 0, 0
+        with torch.no_grad():
+            for n in range(self.n_iters + 1):
+                draws = n < self.n_iters and bool(noise_rows[n])
+                if n == self.n_iters or (draws and used == cap):
+                    if n > first:
+                        self.run(t_all, cond_emb, use_graph, t_key, first=first, count=n - first, fill=False)
+                    first, used = n, 0
+                if draws:
+                    _draw_noise(self.noise[used], xt)
+                    used += 1
 
 
 def _row(t, x_shape, device):
@@ -229,12 +296,18 @@ def _cfg_mode(w_cfg, cond_emb):
 
 
 def _get_plan(agent, key, factory):
-    plan = agent._engine_plans.get(key)
+    """Plan cache of one agent: least-recently-used order, at most CDS_MAX_PLANS entries (each pins device buffers)."""
+    plans = agent._engine_plans
+    plan = plans.pop(key, None)
     if plan is None:
         plan = factory()
-        agent._engine_plans[key] = plan
-    else:
-        plan.refresh_weights()
+        limit = max(1, int(os.environ.get("CDS_MAX_PLANS", "8")))
+        while len(plans) >= limit:
+            old = plans.pop(next(iter(plans)))
+            if hasattr(old, "close"):
+                old.close()
+    plans[key] = plan                      # (re-)insert at the most-recently-used end
+    plan.refresh_weights(getattr(agent, "_weights_epoch", 0))
     return plan
 
 
@@ -285,11 +358,17 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
     has_mask = isinstance(agent.fix_mask, torch.Tensor)
     has_min, has_max = agent.x_min is not None, agent.x_max is not None
     math = _math_mode()
-    key = ("sde", id(net), batch, x_shape, len(order), n_slots > 0, cfg_mode, bool(agent.predict_noise), has_mask,
+    row_elems = 1
+    for s_ in x_shape:
+        row_elems *= s_
+    # noise tape: all draws of the loop up front when they fit the budget, else as many slots as fit (the loop then runs in
+    # chunks with the tape refilled in between -- O(budget) memory instead of O(sample_steps x batch x row))
+    tape_slots = min(n_slots, max(1, _tape_budget_bytes() // (4 * batch * row_elems))) if n_slots > 0 else 0
+    key = ("sde", id(net), batch, x_shape, len(order), tape_slots, cfg_mode, bool(agent.predict_noise), has_mask,
            has_min, has_max, keep_history, math, float(w_cfg) if cfg_mode == 2 else 0.0)
 
     def factory():
-        plan = SamplerPlan(device, net, batch, x_shape, len(order), n_slots, cfg_mode=cfg_mode,
+        plan = SamplerPlan(device, net, batch, x_shape, len(order), tape_slots, cfg_mode=cfg_mode,
                            predict_noise=agent.predict_noise, has_mask=has_mask, has_min=has_min, has_max=has_max,
                            keep_history=keep_history, math=math)
         plan.build(w_cfg)
@@ -303,14 +382,18 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
         if e.code == -3:
             return _fallback(str(e))
         raise
-    if plan.noise is not None and plan.noise.shape[0] < n_slots:
-        return _fallback("noise tape smaller than needed")
 
     # ---- fill the resident buffers ----------------------------------------------------------------------
     with torch.no_grad():
         plan.x.copy_(xt)
         if getattr(plan, "_coef_key", None) != sched_key:
-            plan.coef.copy_(table)
+            if tape_slots and tape_slots < n_slots:          # slots are reused chunk by chunk: k-th draw -> slot k mod tape_slots
+                local = table.clone()
+                draws = local[:, S.R_NOISE] > 0
+                local[draws, S.R_NOISE] = (local[draws, S.R_NOISE] - 1) % tape_slots + 1
+                plan.coef.copy_(local)
+            else:
+                plan.coef.copy_(table)
             plan._coef_key = sched_key
         if has_mask:
             plan.prior.copy_(prior)
@@ -319,12 +402,11 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
             plan.x_min.copy_(_row(agent.x_min, x_shape, device))
         if has_max:
             plan.x_max.copy_(_row(agent.x_max, x_shape, device))
-        for k in range(n_slots):          # same calls, same order, same shapes as the reference loop's draws
-            plan.noise[k].copy_(torch.randn_like(xt).reshape(batch, -1))
         idx = torch.as_tensor(order, dtype=torch.long)
         t_all = t_cpu[idx].to(device)      # int64 (discrete) or float32 (continuous), one entry per iteration
-    plan.run(t_all, cond_emb, use_graph=os.environ.get("CDS_GRAPH", "1") != "0",
-             t_key=(t_cpu.numpy().tobytes(), tuple(order)))
+    # the loop's draws: same calls, same order, same shapes as the reference loop's (diffusionsde.py:548,571,...)
+    plan.run_chunked(t_all, cond_emb, xt, (table[:, S.R_NOISE] > 0).tolist(), use_graph=os.environ.get("CDS_GRAPH", "1") != "0",
+                     t_key=(t_cpu.numpy().tobytes(), tuple(order)))
     STATS["engine_calls"] += 1
     return plan.x.clone()
 
@@ -388,7 +470,7 @@ def try_sample_consistency(agent, *, model, xt, prior, sigmas, order, cond_emb, 
         if has_max:
             plan.x_max.copy_(_row(agent.x_max, x_shape, device))
         for k in range(n_slots):
-            plan.noise[k].copy_(torch.randn_like(xt).reshape(batch, -1))
+            _draw_noise(plan.noise[k], xt)
         t_all = table[:, S.R_T].to(device)             # the network sees c_noise = ln(sigma)/4 as its "time"
     plan.run(t_all, cond_emb, use_graph=os.environ.get("CDS_GRAPH", "1") != "0")
     STATS["engine_calls"] += 1

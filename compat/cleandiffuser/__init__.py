@@ -14,3 +14,14 @@ for _name in ("diffusion", "nn_diffusion", "nn_condition", "utils"):
     globals()[_name] = _mod
 
 __version__ = _impl.__version__
+__cleandiffuser_b200_alias__ = True
+
+# sub-packages of the reference that are NOT on the hot path and are not provided by the alias
+_NOT_PORTED = ("classifier", "nn_classifier", "dataset", "env", "invdynamic")
+
+
+def __getattr__(name):
+    if name in _NOT_PORTED:
+        raise ImportError(f"cleandiffuser.{name} is outside the B200 engine's scope (SURVEY section 8) and not part of the alias "
+                          "package: install the reference and call cleandiffuser_b200.install() instead (drop-in route A)")
+    raise AttributeError(name)

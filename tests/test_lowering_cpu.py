@@ -290,3 +290,65 @@ def test_dit_linear_layers_lower_to_flattened_tensor_core_ops(monkeypatch):
         want = net(x, t.expand(B), cond).numpy()
     err = np.abs(runtime.engine_forward(net, x, t, cond).numpy() - want)
     assert err.max() < 0.12 and err.mean() < 0.02, (float(err.max()), float(err.mean()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host runtime: noise-tape chunking, weight-version tracking through EMA updates, plan cache eviction
+@pytest.mark.parametrize("name", ["disc_dup_ddpm_x0", "disc_dx_sde_dpmsolverpp_2M_eps", "cont_sde_dpmsolver_1_eps"])
+def test_noise_tape_chunks_give_the_same_result(golden, name, monkeypatch):
+    """A tape shorter than the loop's number of draws (CDS_NOISE_TAPE_MB) is refilled chunk by chunk: memory O(budget), same
+    draws in the same order, same result as the all-up-front tape."""
+    spec = cases.sampler_cases()[name]
+    monkeypatch.setenv("CDS_NOISE_TAPE_MB", "0.0001")           # ~100 bytes: ONE slot of these toy shapes
+    agent, inp, kw = build_agent(spec)
+    tape = NoiseTape(tape_of(golden["samplers"], name))
+    with tape.active(), torch.no_grad():
+        x0, _ = agent.sample(inp["prior"], **kw)
+    assert tape.pos == len(tape.draws)
+    plan = next(iter(agent._engine_plans.values()))
+    n_draws = len(tape.draws) - 1                                # the first draw is the initial x_T, not a loop draw
+    assert plan.noise is not None and plan.noise.shape[0] < n_draws, (plan.noise.shape, n_draws)
+    np.testing.assert_allclose(x0.numpy(), golden["samplers"][name + "/x0"], rtol=1e-4, atol=3e-4)
+
+
+def test_ema_update_invalidates_packed_weights(golden):
+    """sample(use_ema=True) -> update() -> sample(use_ema=True): the EMA twin changed through ema_update(), the plan must
+    re-pack (writes through .data do not bump tensor versions; the agent's weight epoch does)."""
+    name = "disc_dup_ddpm_x0"
+    spec = cases.sampler_cases()[name]
+    agent, inp, kw = build_agent(spec)
+    agent.ema_rate = 0.5
+
+    def run(backend, monkey_env):
+        tape = NoiseTape(tape_of(golden["samplers"], name))
+        with tape.active(), torch.no_grad():
+            return agent.sample(inp["prior"], **kw)[0].numpy()
+
+    a0 = run("cuda", None)
+    x0 = torch.randn(8, *inp["prior"].shape[1:])
+    agent.update(x0)                                             # optimiser step + ema_update()
+    agent.model_ema.eval()
+    a1 = run("cuda", None)
+    assert np.abs(a1 - a0).max() > 1e-5
+    import os
+    os.environ["CDS_BACKEND"] = "torch"
+    try:
+        t1 = run("torch", None)
+    finally:
+        os.environ["CDS_BACKEND"] = "cuda"
+    np.testing.assert_allclose(a1, t1, rtol=1e-4, atol=3e-4)
+
+
+def test_plan_cache_is_bounded(golden, monkeypatch):
+    monkeypatch.setenv("CDS_MAX_PLANS", "2")
+    name = "disc_dup_ddpm_x0"
+    spec = cases.sampler_cases()[name]
+    agent, inp, kw = build_agent(spec)
+    for n in (2, 3, 4, 5):
+        with torch.no_grad():
+            agent.sample(inp["prior"][:n], **{**kw, "n_samples": n})
+        assert len(agent._engine_plans) <= 2
+    keys = list(agent._engine_plans)
+    with torch.no_grad():
+        agent.sample(inp["prior"][:4], **{**kw, "n_samples": 4})      # cached plan: moves to the most-recently-used end
+    assert list(agent._engine_plans)[-1] == keys[0] and len(agent._engine_plans) == 2
