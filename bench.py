@@ -3,7 +3,11 @@
 Workload (BASELINE.json configs[1], SURVEY 8d "cfg2"): JannerUNet1d(in 14, model_dim 32, dim_mult [1,2,2,2], k=5),
 H=32, d=14, DiscreteDiffusionSDE(predict_noise=False, 100 diffusion steps, cosine), DDPM solver with 100 sampling
 steps, temperature 0.5, fix_mask on the first observation, batch 4096 candidate trajectories PER GPU (weak scaling),
-synthetic weights (seed 0) / inputs (seed 1) / noise (seed 2 + rank).
+synthetic weights (seed 0) / inputs (seed 1) / noise (seed 2 + rank).  The workload definitions live in
+``cleandiffuser_b200/workloads.py`` and are the ones the full-size parity tests run (tests/test_baseline_configs_gpu.py).
+
+Math mode: ``tf32`` (the library default): tcgen05 kind::tf32 over fp32 activations and weights, fp32 accumulate -- the
+arithmetic of the reference's own GPU path (cuDNN TF32 convs); ``--math bf16`` / ``--math fp32`` select the other programs.
 
 One "step" = one complete ``sample()`` call (initial noise, 100 reverse iterations, final all-gather when N > 1).
 
@@ -12,8 +16,13 @@ One "step" = one complete ``sample()`` call (initial noise, 100 reverse iteratio
   torchrun ... bench.py --gpus N ...                         # one rank per GPU, NCCL
 
 Prints ONE JSON line (rank 0).  See the task contract for the keys; additionally:
-  roofline      live per-kernel measurement of the dominant kernel family (fused conv GEMM) via cds_plan_profile
-  cpu_baseline  the oracle port timed on the host cores on a bounded sample of the same workload
+  roofline            live per-kernel measurement of the dominant kernel family (fused conv GEMM) via cds_plan_profile
+  cpu_baseline        the oracle port timed on the host cores on a bounded sample of the same workload
+  gpu_eager_baseline  the SAME sample() on the SAME GPU through this package's PyTorch loop (CDS_BACKEND=torch: ATen / cuDNN /
+                      cuBLAS kernels launched op by op from Python, TF32 convs as torch defaults) -- what the reference's own
+                      code path costs on this B200 (SURVEY 8d's "beat this" number); N = 1 only
+  other_configs       short measurements of BASELINE configs 3 / 4 / 5 at their per-GPU batch on the same ranks (value is the
+                      whole-job aggregate like the headline), with their tensor-roofline fraction
 """
 import argparse
 import json
@@ -47,14 +56,10 @@ def peaks():
 
 
 def build_agent(device, seed=0):
-    from cleandiffuser_b200.diffusion import DiscreteDiffusionSDE
-    from cleandiffuser_b200.nn_diffusion import JannerUNet1d
-    from cleandiffuser_b200.testing import load_synth
-    net = load_synth(JannerUNet1d(D, model_dim=32, emb_dim=32, kernel_size=5, dim_mult=[1, 2, 2, 2]), seed=seed)
-    mask = torch.zeros(H, D)
-    mask[0, :OBS] = 1.
-    agent = DiscreteDiffusionSDE(net, None, fix_mask=mask, predict_noise=False, diffusion_steps=T_DIFF, device=device)
-    return agent, net, mask
+    """cfg2's diffusion object (cleandiffuser_b200/workloads.py::cfg2) -> (agent, denoiser, fix_mask)"""
+    from cleandiffuser_b200 import workloads
+    wl = workloads.cfg2(device, batch=1, steps=T_DIFF, seed=seed)
+    return wl.agent, wl.agent.model["diffusion"], wl.agent.fix_mask[0].cpu()
 
 
 def make_prior(batch, seed=1):
@@ -62,6 +67,17 @@ def make_prior(batch, seed=1):
     prior = torch.zeros(batch, H, D)
     prior[:, 0, :OBS] = torch.randn(batch, OBS, generator=g)
     return prior
+
+
+def tensor_peaks():
+    """(tf32 dense TFLOP/s, bf16 dense TFLOP/s, source): bf16 measured (MEASURED_PEAKS.json, sustained), tf32 = half of it (the
+    tensor pipe runs kind::tf32 at half the bf16 rate; no measured tf32 figure exists in MEASURED_PEAKS.json)"""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            bf16 = json.load(f)["bf16_tflops_sustained"]
+        return bf16 / 2, bf16, "MEASURED_PEAKS.json bf16_tflops_sustained (tf32 = half)"
+    return 1125.0, 2250.0, "fallback (B200_PROFILING.md nominal dense)"
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -128,8 +144,8 @@ def log(msg):
 def cpu_reference_arm(steps, warmup, sample_batch=256):
     """The reference's algorithm on the host cores: oracle port of JannerUNet1d + DiscreteDiffusionSDE.sample
     (PyTorch CPU primitives, exactly what the reference executes on CPU), on a bounded sample of the workload.
-    Thread count: the fastest of {all cores, 64, 32, 16} on a 3-forward probe (small convs stop scaling, and can get
-    slower, long before 128 threads); the count used is reported as ``cores``."""
+    Thread count: the fastest of {64, 32, 16} (capped by the core count) on a 2-forward probe (small convs stop scaling, and
+    get much slower, long before 128 threads); the count used is reported as ``cores``."""
     import oracle.nets as onets
     import oracle.sampler as osamp
     _, net, mask = build_agent("cpu")
@@ -139,16 +155,16 @@ def cpu_reference_arm(steps, warmup, sample_batch=256):
     g = torch.Generator().manual_seed(2)
     ncpu = os.cpu_count() or 1
     best = (None, 1)
-    for nt in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
+    for nt in sorted({min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
         torch.set_num_threads(nt)
         xp, tp = torch.randn(sample_batch, H, D), torch.full((sample_batch,), 7)
         with torch.no_grad():
             fn(xp, tp)
             t0 = time.perf_counter()
-            for _ in range(3):
+            for _ in range(2):
                 fn(xp, tp)
             dt = time.perf_counter() - t0
-        log(f"cpu probe: {nt} threads -> {dt / 3 * 1e3:.1f} ms / forward (B={sample_batch})")
+        log(f"cpu probe: {nt} threads -> {dt / 2 * 1e3:.1f} ms / forward (B={sample_batch})")
         if best[0] is None or dt < best[0]:
             best = (dt, nt)
     torch.set_num_threads(best[1])
@@ -167,6 +183,89 @@ def cpu_reference_arm(steps, warmup, sample_batch=256):
     return sample_batch * steps / dt, dt / steps, sample_batch
 
 
+def device_timed(fn, n, dist, world, device):
+    """n calls of fn bracketed by barrier + synchronize, CUDA events on the current stream, MAX over ranks (ms)."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def measure_other_configs(device, world, dist, math, reps=2):
+    """BASELINE configs 3 / 4 / 5 at their per-GPU batch: every rank runs its own share (weak scaling, like the headline), one
+    warm-up call (plan build, graph capture) + ``reps`` timed calls, device time, max over ranks.  Roofline: algorithmic FLOPs
+    per trajectory against the tensor peak of the math mode."""
+    from cleandiffuser_b200 import workloads
+    from cleandiffuser_b200.engine import runtime
+    tf32_peak, bf16_peak, src = tensor_peaks()
+    peak = {"tf32": tf32_peak, "bf16": bf16_peak}.get(math)
+    out = {}
+    for name in ("cfg3", "cfg4", "cfg5"):
+        try:
+            wl = workloads.BUILDERS[name](device)
+            prior, cond = wl.prior.to(device), None if wl.cond is None else wl.cond.to(device)
+            B = prior.shape[0]
+            before = runtime.STATS["engine_calls"]
+
+            def call():
+                return wl.sample(device, prior=prior, cond=cond)
+            with torch.no_grad():
+                call()
+                torch.cuda.synchronize()
+                ms = device_timed(call, reps, dist, world, device) / reps
+            v = world * B / (ms * 1e-3)
+            tfl = v * wl.gflop / 1e3 / world
+            out[name] = {"workload": wl.describe, "value": v, "unit": "trajectories/s", "ms_per_call": ms, "batch_per_gpu": B,
+                         "n_gpus": world, "dtype": math, "gflop_per_traj": wl.gflop, "tflops_per_gpu": tfl,
+                         "roofline": {"bound": "tensor", "achieved": tfl, "peak": peak, "unit": "TFLOP/s",
+                                      "frac": (tfl / peak) if peak else None, "peak_source": src},
+                         "engine_calls": runtime.STATS["engine_calls"] - before}
+            log(f"{name}: {ms:.1f} ms / call, {v:,.0f} traj/s, {tfl:.0f} TFLOP/s per GPU")
+            del wl, prior, cond
+            torch.cuda.empty_cache()
+        except Exception as e:            # a secondary measurement must never take the headline line down
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            log(f"{name}: FAILED {out[name]['error']}")
+    return out
+
+
+def gpu_eager_baseline(agent, prior_dev, kw, B):
+    """cfg2's sample() on this GPU through the PyTorch loop of this package (the reference's algorithm step for step, ATen kernels
+    launched from Python, cuDNN convs in TF32 as torch defaults): 1 warm-up + 1 timed call."""
+    old = os.environ.get("CDS_BACKEND")
+    os.environ["CDS_BACKEND"] = "torch"
+    try:
+        with torch.no_grad():
+            agent.sample(prior_dev, **kw)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            agent.sample(prior_dev, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        return {"value": B / (ms * 1e-3), "unit": "trajectories/s", "ms_per_step": ms, "batch": B,
+                "what": "this package's PyTorch path (CDS_BACKEND=torch): the reference's loop and modules as ATen/cuDNN/cuBLAS "
+                        "launches from Python, torch default precision (cudnn.allow_tf32=True, matmul fp32)",
+                "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+                "matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32)}
+    finally:
+        if old is None:
+            os.environ.pop("CDS_BACKEND", None)
+        else:
+            os.environ["CDS_BACKEND"] = old
+
+
 # ------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -179,6 +278,9 @@ def main():
                     help="tf32 (default = the library default): tcgen05 kind::tf32 over fp32 activations; bf16: tcgen05 with bf16 "
                          "operands and activations; fp32: CUDA-core FMA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=256, help="trajectories per step of the CPU arm (bounded sample)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -187,22 +289,29 @@ def main():
     config = {"workload": WORKLOAD, "backbone": "JannerUNet1d(14,32,[1,2,2,2],k5)", "horizon": H, "dim": D,
               "solver": "ddpm", "sample_steps": S_STEPS, "batch_per_gpu": args.batch,
               "global_batch": args.batch * world, "parallelism": f"dp{world}",
-              "l2": "working set (activations + 100-slot noise tape, ~1 GB) exceeds the 126 MB L2; no explicit flush"}
+              "l2": "working set (fp32 activations + 99-slot noise tape, ~1.5 GB) exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        warm = max(1, min(args.warmup, 1))
-        steps = max(1, min(args.steps, 3))
-        value, sec, sb = cpu_reference_arm(steps, warm)
+        # K timed steps after W warm-up steps as asked; a step = one full 100-step sample() on a BOUNDED sample of the batch
+        # (cpu_sample_batch trajectories; the full 4096 would take ~35 s per step on these cores).  The sample size is shrunk
+        # if K + W steps would not end within a few minutes.
+        sb = args.cpu_sample_batch
+        while sb > 32 and (args.steps + args.warmup) * (sb / 100.0) > 240:      # ~100 traj/s on 16 threads -> seconds per step
+            sb //= 2
+        value, sec, sb = cpu_reference_arm(max(args.steps, 1), max(args.warmup, 0), sample_batch=sb)
         cores = torch.get_num_threads()
+        config = dict(config, cpu_sample_batch=sb,
+                      note=f"CPU arm: every step runs the full 100-step sample() on {sb} of the {args.batch} trajectories "
+                           "(bounded sample; throughput in trajectories/s is batch-size independent to first order)")
         line = {"impl": "reference", "metric": "sampled trajectories/sec (H=32, 100 DDPM steps)", "value": value,
-                "unit": "trajectories/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+                "unit": "trajectories/s", "n_gpus": args.gpus, "steps": max(args.steps, 1), "warmup": max(args.warmup, 0),
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                                 "sample": f"full 100-step sample() on {sb} trajectories per step (oracle port, "
-                                           f"torch CPU fp32, {cores} threads)"},
+                                 "sample": f"full 100-step sample() on {sb} trajectories per step (oracle port of the reference "
+                                           f"algorithm, torch CPU fp32, {cores} threads)"},
                 "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
@@ -247,20 +356,7 @@ def main():
         return x0.cpu()
 
     def timed(fn, n):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-        if world > 1:
-            dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return device_timed(fn, n, dist, world, device)
 
     with torch.no_grad():
         log("warm-up")
@@ -288,8 +384,7 @@ def main():
             clocks["samples_inside_timed_region"] = row1 - row0
             clocks["untimed_steps_of_the_same_load_sampled_after"] = extended
         runtime.STATS["time_loop"] = False
-        runtime.STATS["loop_events"] = runtime.STATS["loop_events"][:args.steps]
-        loop_ms = [a.elapsed_time(b) for a, b in runtime.STATS["loop_events"]]
+        loop_ms = [a.elapsed_time(b) for a, b in runtime.STATS["loop_events"][:args.steps]]      # one event pair per sample() call
         loop_ms_mean = sum(loop_ms) / max(len(loop_ms), 1)
         log(f"timed: {ms / args.steps:.1f} ms/step; reverse loop alone {loop_ms_mean:.2f} ms "
             f"({loop_ms_mean * 1e3 / S_STEPS:.1f} us / iteration)")
@@ -343,29 +438,54 @@ def main():
         loop_iter_ms = loop_ms_mean / S_STEPS
         conv_ms_graph = loop_iter_ms * share
         achieved = conv_bytes / (conv_ms_graph * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("conv_dram_bytes_per_launch")
+                tj = json.load(f)
+            ent = tj.get(args.math) if isinstance(tj.get(args.math), dict) else None
+            if ent:
+                traffic, traffic_src = ent.get("conv_dram_bytes_per_launch"), ent.get("source")
+        tf32_peak, bf16_peak, tsrc = tensor_peaks()
+        tpeak = {"tf32": tf32_peak, "bf16": bf16_peak}.get(args.math)
+        tfl = conv_flops / (conv_ms_graph * 1e-3) / 1e12
         roofline = {"bound": "hbm", "kernel": "conv_tc_kernel / conv_ps_kernel (fused Conv1d+GroupNorm+Mish+FiLM+residual), all "
                                               f"{n_conv} conv launches of one reverse iteration",
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "peak_source": peak_src, "traffic": traffic,
+                    "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                     "how": "algorithmic bytes (SURVEY 8d: fp32 in+out of every fused conv) of one iteration / (event-timed graph-replay "
                            "loop time per iteration x conv share of the iteration)",
                     "launches_per_iter": n_conv, "avg_launch_us": conv_ms_graph / max(n_conv, 1) * 1e3,
                     "alg_bytes_per_launch": conv_bytes / max(n_conv, 1), "alg_bytes_per_iter": conv_bytes,
-                    "conv_share_of_iter": share, "tflops_effective": conv_flops / (conv_ms_graph * 1e-3) / 1e12,
+                    "conv_share_of_iter": share, "tflops_effective": tfl,
+                    "tensor": {"achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": (tfl / tpeak) if tpeak else None,
+                               "peak_source": tsrc, "note": "nominal conv FLOPs incl. zero-padding taps"},
                     "direct_launch": {"avg_launch_us": conv_ms / max(n_conv, 1) * 1e3,
                                       "achieved": conv_bytes / (conv_ms * 1e-3) / 1e9},
                     "sample_level": {"alg_bytes_per_traj": ALG_BYTES_PER_TRAJ,
                                      "achieved_GBs": ALG_BYTES_PER_TRAJ * value / world / 1e9,
                                      "frac": ALG_BYTES_PER_TRAJ * value / world / 1e9 / hbm_peak}}
 
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        try:
+            eager = gpu_eager_baseline(agent, prior_dev, kw, B)
+            log(f"gpu eager baseline: {eager['ms_per_step']:.0f} ms / step, {eager['value']:,.0f} traj/s")
+        except Exception as e:
+            eager = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # free cfg2's plan before the other configs build theirs
+    others = None
+    if not args.no_other_configs and args.math in ("tf32", "bf16"):
+        for pl in list(agent._engine_plans.values()):
+            pl.close()
+        agent._engine_plans.clear()
+        torch.cuda.empty_cache()
+        others = measure_other_configs(device, world, dist, args.math)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, sb = cpu_reference_arm(1, 1, sample_batch=256)
+        v, sec, sb = cpu_reference_arm(1, 1, sample_batch=args.cpu_sample_batch)
         cpu_baseline = {"value": v, "unit": "trajectories/s", "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"one full 100-step sample() on {sb} trajectories ({sec:.1f} s), oracle port of the "
                                   f"reference algorithm on torch CPU fp32"}
@@ -384,6 +504,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": prior_host.numel() * 4,
                         "d2h_bytes_per_step": B * H * D * 4, "ms_per_step": ms_e2e / args.steps},
                 "loop_ms_per_step": loop_ms_mean, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "gpu_eager_baseline": eager, "other_configs": others,
                 "engine": {"calls": runtime.STATS["engine_calls"], "fallbacks": runtime.STATS["fallbacks"]}}
         print(json.dumps(line), flush=True)
     if world > 1:

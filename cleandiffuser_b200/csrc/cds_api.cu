@@ -108,6 +108,7 @@ int validate(const cds_op& op, Step* out) {
       const cds_update_op& u = op.u.update;
       if (u.batch <= 0 || u.row <= 0 || !u.x || !u.pred || !u.coef) return fail(CDS_ERR_INVALID, "update: bad arguments");
       if (u.mask && !u.prior) return fail(CDS_ERR_INVALID, "update: mask without prior");
+      if (u.aux && !u.xhat_prev) return fail(CDS_ERR_INVALID, "update: aux history without xhat_prev");
       if (u.x_cast && (u.cast_C_in <= 0 || u.cast_C_out < u.cast_C_in || u.row % u.cast_C_in != 0))
         return fail(CDS_ERR_INVALID, "update: bad x_cast geometry");
       return CDS_OK;

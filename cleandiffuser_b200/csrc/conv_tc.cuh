@@ -1006,6 +1006,7 @@ struct ConvTcLaunch {
 inline int conv_tc_pick_split(const cds_conv_op& c, int n_total, int m_tiles) {
   if (n_total > 256) return n_total / 256;
   if (c.phases != 1 || n_total < 64) return 1;
+  if (const char* ns = getenv("CDS_TC_NOSPLIT")) { if (ns[0] == '1') return 1; if (ns[0] == '2' && n_total == 128) return 1; }   // experiment
   if (n_total >= 128) return 2;
   const char* e = getenv("CDS_TC_SPLIT64");
   if (e && e[0] == '1') return 2;                    // experiment: C_out = 64 always as two N = 32 CTAs (3 CTAs/SM residency)

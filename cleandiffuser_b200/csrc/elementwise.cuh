@@ -38,10 +38,26 @@ __device__ __forceinline__ UpdRow load_upd_row(const cds_update_op& p, int iter)
 // pr = the network prediction (after the CFG combine), z = this iteration's noise draw (ignored without a slot), prior = the
 // conditioning value under the mask, hist = previous x0 estimate of the 2M solvers; *xhat_out receives the new estimate.
 __device__ __forceinline__ float solver_update_value(const cds_update_op& p, const UpdRow& r, int e, float x, float pr, float z,
-                                                     float prior, float hist, float* xhat_out) {
+                                                     float prior, float hist, float* xhat_out, float aux_in = 0.f,
+                                                     float* aux_out = nullptr) {
   const float alpha = r.alpha, sigma = r.sigma;
   float out;
-  if (r.kind == CDS_UPD_CM) {
+  if (r.kind == CDS_UPD_EDM || r.kind == CDS_UPD_EDM_HEUN) {
+    // D = c_skip*x + c_out*net ; clip ; Euler / Heun step of the probability-flow ODE (newedm.py:142-148, :411-431)
+    float d_theta = add_(mul_(r.k0, x), mul_(r.k1, pr));
+    if (p.final_clip) {
+      if (p.x_min) d_theta = fmaxf(d_theta, p.x_min[e]);
+      if (p.x_max) d_theta = fminf(d_theta, p.x_max[e]);
+    }
+    const float slope = div_(sub_(x, d_theta), sigma);
+    if (r.kind == CDS_UPD_EDM) {
+      out = sub_(x, mul_(slope, r.k2));
+      if (xhat_out) *xhat_out = x;
+      if (aux_out) *aux_out = slope;
+    } else {
+      out = sub_(hist, mul_(div_(add_(aux_in, slope), 2.f), r.k2));
+    }
+  } else if (r.kind == CDS_UPD_CM) {
     // f = c_skip*x + c_out*net ; clip (consistency_model.py:257-261)
     out = add_(mul_(r.k0, x), mul_(r.k1, pr));
     if (p.final_clip) {
@@ -84,10 +100,16 @@ __device__ __forceinline__ float solver_update_value(const cds_update_op& p, con
 // (ignored when x_cast is NULL).  Reads x (+noise, prior, xhat_prev), writes x (+xhat_prev, +the bf16 channel-padded copy).
 __device__ __forceinline__ void solver_update_element(const cds_update_op& p, const UpdRow& r, int64_t i, int e, int64_t cast_off,
                                                       float pr) {
-  float xhat = 0.f;
+  float xhat = 0.f, aux = 0.f;
+  const bool heun2 = r.kind == CDS_UPD_EDM_HEUN;
   const float out = solver_update_value(p, r, e, p.x[i], pr, r.noise ? r.noise[i] : 0.f, p.mask ? p.prior[i] : 0.f,
-                                        (p.xhat_prev && r.kind == CDS_UPD_X2M) ? p.xhat_prev[i] : 0.f, &xhat);
-  if (p.xhat_prev && r.kind != CDS_UPD_CM && r.kind != CDS_UPD_DDPM && r.kind != CDS_UPD_DDIM) p.xhat_prev[i] = xhat;
+                                        (p.xhat_prev && (r.kind == CDS_UPD_X2M || heun2)) ? p.xhat_prev[i] : 0.f, &xhat,
+                                        (p.aux && heun2) ? p.aux[i] : 0.f, &aux);
+  if (r.kind == CDS_UPD_EDM) {
+    if (r.k4 != 0.f && p.xhat_prev && p.aux) { p.xhat_prev[i] = xhat; p.aux[i] = aux; }      // predictor of a Heun step
+  } else if (p.xhat_prev && !heun2 && r.kind != CDS_UPD_CM && r.kind != CDS_UPD_DDPM && r.kind != CDS_UPD_DDIM) {
+    p.xhat_prev[i] = xhat;
+  }
   p.x[i] = out;
   if (p.x_cast) {
     if (p.x_cast_dtype == CDS_BF16) reinterpret_cast<__nv_bfloat16*>(p.x_cast)[cast_off] = __float2bfloat16_rn(out);

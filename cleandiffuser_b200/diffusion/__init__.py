@@ -1,4 +1,5 @@
 from .basic import DiffusionModel
 from .sde import BaseDiffusionSDE, DiscreteDiffusionSDE, ContinuousDiffusionSDE
 from .consistency import ContinuousConsistencyModel
+from .edm import ContinuousEDM
 from .solvers import SUPPORTED_SOLVERS

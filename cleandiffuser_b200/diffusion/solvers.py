@@ -32,7 +32,7 @@ SUPPORTED_SOLVERS = [
     "sde_dpmsolver_1", "sde_dpmsolver++_1", "sde_dpmsolver++_2M", ]
 
 # update shapes (must match enum cds_update_kind in include/cds.h)
-UPD_DDPM, UPD_DDIM, UPD_EPS, UPD_X, UPD_X2M, UPD_CM = 0, 1, 2, 3, 4, 5
+UPD_DDPM, UPD_DDIM, UPD_EPS, UPD_X, UPD_X2M, UPD_CM, UPD_EDM, UPD_EDM_HEUN = 0, 1, 2, 3, 4, 5, 6, 7
 
 # row layout of the per-iteration coefficient table (floats)
 ROW = 12

@@ -75,7 +75,7 @@ class UpdateOp(C.Structure):
         ("pred", _f32p), ("pred_uncond", _f32p), ("w_cfg", C.c_float), ("w_uncond", C.c_float),
         ("noise", _f32p), ("noise_slot_stride", C.c_int64), ("prior", _f32p), ("mask", _f32p), ("x_min", _f32p),
         ("x_max", _f32p),
-        ("xhat_prev", _f32p), ("coef", _f32p), ("predict_noise", C.c_int32), ("final_clip", C.c_int32),
+        ("xhat_prev", _f32p), ("aux", _f32p), ("coef", _f32p), ("predict_noise", C.c_int32), ("final_clip", C.c_int32),
         ("x_cast", C.c_void_p), ("cast_C_in", C.c_int32), ("cast_C_out", C.c_int32), ("x_cast_dtype", C.c_int32),
     ]
 

@@ -128,7 +128,10 @@ class SamplerPlan:
     """Everything resident on the device for one (model, batch, x_shape, option set)."""
 
     def __init__(self, device, net, batch, x_shape, n_iters, n_slots, *, cfg_mode, predict_noise, has_mask,
-                 has_min, has_max, keep_history, math, consistency=False):
+                 has_min, has_max, keep_history, math, consistency=False, aux_history=False):
+        """consistency: the EDM-preconditioned family (ContinuousConsistencyModel, ContinuousEDM): a CDS_OP_PREP in front of the
+        denoiser (re-noise + c_in scaling) and the c_skip / c_out combine in the update; aux_history: second history buffer (the
+        EDM Heun corrector needs the predictor's x_t and slope)."""
         self.device, self.net, self.batch, self.x_shape = device, net, batch, tuple(x_shape)
         row = 1
         for s in x_shape:
@@ -147,6 +150,7 @@ class SamplerPlan:
         self.coef = root.buf(n_iters, cabi.ROW_FLOATS)
         self.noise = root.buf(max(n_slots, 1), batch, row) if n_slots > 0 else None
         self.xhat_prev = root.buf(batch, row) if keep_history else None
+        self.aux = root.buf(batch, row) if (keep_history and aux_history) else None
         if consistency:
             self.xin = root.buf(batch, *x_shape)
 
@@ -187,6 +191,7 @@ class SamplerPlan:
             u.x_min = self.x_min.data_ptr() if has_min else None
             u.x_max = self.x_max.data_ptr() if has_max else None
             u.xhat_prev = self.xhat_prev.data_ptr() + fo if keep_history else None
+            u.aux = self.aux.data_ptr() + fo if self.aux is not None else None
             u.coef = self.coef.data_ptr()
             u.predict_noise = 1 if predict_noise else 0
             u.final_clip = 1 if consistency else 0
@@ -244,14 +249,7 @@ class SamplerPlan:
         if fill:
             self.fill_tables(t_all, cond_emb, t_key)
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
-        timed = STATS.get("time_loop") and self.device.type == "cuda"
-        if timed:           # bench.py: device time of the reverse loop alone (events on the launching stream)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
         self.handle.run(first, self.n_iters - first if count is None else count, stream, use_graph)
-        if timed:
-            e1.record()
-            STATS.setdefault("loop_events", []).append((e0, e1))
         STATS["launches"] = self.handle.launches_per_iter() * self.n_iters + 1
 
     def run_chunked(self, t_all, cond_emb, xt, noise_rows, use_graph=True, t_key=None):
@@ -260,6 +258,10 @@ class SamplerPlan:
         generator like the reference loop; everything is enqueued on one stream, so a refill cannot overtake its readers."""
         cap = self.noise.shape[0] if self.noise is not None else 0
         self.fill_tables(t_all, cond_emb, t_key)
+        timed = STATS.get("time_loop") and self.device.type == "cuda"
+        if timed:           # bench.py: device time of the reverse loop alone (noise draws + replayed iterations; events on the
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)    # launching stream)
+            e0.record()
         first, used = 0, 0
         with torch.no_grad():
             for n in range(self.n_iters + 1):
@@ -271,6 +273,9 @@ class SamplerPlan:
                 if draws:
                     _draw_noise(self.noise[used], xt)
                     used += 1
+        if timed:
+            e1.record()
+            STATS.setdefault("loop_events", []).append((e0, e1))
 
 
 def _row(t, x_shape, device):
@@ -471,6 +476,81 @@ def try_sample_consistency(agent, *, model, xt, prior, sigmas, order, cond_emb, 
             plan.x_max.copy_(_row(agent.x_max, x_shape, device))
         for k in range(n_slots):
             _draw_noise(plan.noise[k], xt)
+        t_all = table[:, S.R_T].to(device)             # the network sees c_noise = ln(sigma)/4 as its "time"
+    plan.run(t_all, cond_emb, use_graph=os.environ.get("CDS_GRAPH", "1") != "0")
+    STATS["engine_calls"] += 1
+    return plan.x.clone()
+
+
+def try_sample_edm(agent, *, model, xt, prior, solver, sigmas, order, cond_emb, w_cfg, n_samples):
+    """ContinuousEDM.sample on the engine (newedm.py:395-431).  Every network evaluation is one engine iteration:
+    ``euler``: one per reverse step; ``heun``: predictor + corrector (two evaluations) for every step but the last.
+    ``sigmas``: the Karras grid (sample_steps + 1 entries, fp32), ``order``: the reverse steps i in loop order."""
+    if _backend() == "torch":
+        return None
+    device = _device_of(agent)
+    if not _device_ok(device) or xt.dtype != torch.float32:
+        return None
+    net = model["diffusion"]
+    cfg_mode = _cfg_mode(w_cfg, cond_emb)
+    if cfg_mode is None:
+        return _fallback("two-branch CFG without condition")
+    batch, x_shape = xt.shape[0], tuple(xt.shape[1:])
+    if n_samples != batch:
+        return _fallback("n_samples != prior.shape[0]")
+    sig = sigmas.detach().float().cpu()
+    sd = agent.sigma_data
+    evals = []                                   # (sigma of the evaluation, kind, dt, predictor flag)
+    for i in order:
+        dt = sig[i] - sig[i - 1]
+        heun = solver == "heun" and i > 1
+        evals.append((sig[i], S.UPD_EDM, dt, 1.0 if heun else 0.0))
+        if heun:
+            # the corrector evaluates at t = t_i / sigma_i * sigma_{i-1} (newedm.py:421) = sigma_{i-1} exactly (x / x == 1)
+            evals.append((sig[i - 1], S.UPD_EDM_HEUN, dt, 0.0))
+    n_iters = len(evals)
+    table = torch.zeros((n_iters, S.ROW), dtype=torch.float32)
+    for n, (s, kind, dt, pred_flag) in enumerate(evals):   # 0-d fp32 tensors, reference op order (newedm.py:128-148)
+        table[n, S.R_K0] = float(sd ** 2 / (sd ** 2 + s ** 2))                  # c_skip
+        table[n, S.R_K1] = float(s * sd / (sd ** 2 + s ** 2).sqrt())            # c_out
+        table[n, S.R_K3] = float(1 / (sd ** 2 + s ** 2).sqrt())                 # c_in
+        table[n, S.R_K2] = float(dt)
+        table[n, S.R_K4] = pred_flag
+        table[n, S.R_SIGMA] = float(s)                                          # the slope divides by it
+        table[n, S.R_KIND] = float(kind)
+        table[n, S.R_T] = float(0.25 * s.log())                                 # c_noise
+    has_mask = isinstance(agent.fix_mask, torch.Tensor)
+    has_min, has_max = agent.x_min is not None, agent.x_max is not None
+    math = _math_mode()
+    heun = solver == "heun"
+    key = ("edm", id(net), batch, x_shape, n_iters, cfg_mode, has_mask, has_min, has_max, heun, math,
+           float(w_cfg) if cfg_mode == 2 else 0.0)
+
+    def factory():
+        plan = SamplerPlan(device, net, batch, x_shape, n_iters, 0, cfg_mode=cfg_mode, predict_noise=False,
+                           has_mask=has_mask, has_min=has_min, has_max=has_max, keep_history=heun, math=math,
+                           consistency=True, aux_history=heun)
+        plan.build(w_cfg)
+        return plan
+
+    try:
+        plan = _get_plan(agent, key, factory)
+    except Unsupported as e:
+        return _fallback(str(e))
+    except cabi.CdsError as e:
+        if e.code == -3:
+            return _fallback(str(e))
+        raise
+    with torch.no_grad():
+        plan.x.copy_(xt)
+        plan.coef.copy_(table, non_blocking=True)
+        if has_mask:
+            plan.prior.copy_(prior)
+            plan.mask.copy_(_row(agent.fix_mask, x_shape, device))
+        if has_min:
+            plan.x_min.copy_(_row(agent.x_min, x_shape, device))
+        if has_max:
+            plan.x_max.copy_(_row(agent.x_max, x_shape, device))
         t_all = table[:, S.R_T].to(device)             # the network sees c_noise = ln(sigma)/4 as its "time"
     plan.run(t_all, cond_emb, use_graph=os.environ.get("CDS_GRAPH", "1") != "0")
     STATS["engine_calls"] += 1

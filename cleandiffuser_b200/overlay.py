@@ -2,8 +2,8 @@
 
 ``install()`` rebinds the hot-path classes INSIDE the imported reference package,
 
-    cleandiffuser.diffusion.{DiscreteDiffusionSDE, ContinuousDiffusionSDE, ContinuousConsistencyModel}
-    (+ the defining sub-modules cleandiffuser.diffusion.diffusionsde / .consistency_model)
+    cleandiffuser.diffusion.{DiscreteDiffusionSDE, ContinuousDiffusionSDE, ContinuousConsistencyModel, ContinuousEDM}
+    (+ the defining sub-modules cleandiffuser.diffusion.diffusionsde / .consistency_model / .newedm)
 
 to this package's classes, so that a pipeline's ``from cleandiffuser.diffusion import DiscreteDiffusionSDE`` -- and
 everything else it imports from the reference: datasets, envs, classifiers, ``nn_classifier``, ``utils.report_parameters``
@@ -24,7 +24,8 @@ _PATCHED: List[Tuple[object, str, object]] = []      # (module, attribute, origi
 
 # reference module -> names rebound there
 _TARGETS: Dict[str, Tuple[str, ...]] = {
-    "cleandiffuser.diffusion": ("DiscreteDiffusionSDE", "ContinuousDiffusionSDE", "ContinuousConsistencyModel"),
+    "cleandiffuser.diffusion": ("DiscreteDiffusionSDE", "ContinuousDiffusionSDE", "ContinuousConsistencyModel", "ContinuousEDM"),
+    "cleandiffuser.diffusion.newedm": ("ContinuousEDM",),
     "cleandiffuser.diffusion.diffusionsde": ("DiscreteDiffusionSDE", "ContinuousDiffusionSDE"),
     "cleandiffuser.diffusion.consistency_model": ("ContinuousConsistencyModel",),
 }

@@ -72,7 +72,13 @@ typedef enum cds_math { CDS_MATH_FP32 = 0, CDS_MATH_BF16_TC = 1, CDS_MATH_TF32_T
  * error is unbiased and half as large.  Producers honour it on store; consumers read CDS_TF32 exactly like CDS_F32. */
 typedef enum cds_dtype { CDS_F32 = 0, CDS_BF16 = 1, CDS_TF32 = 2 } cds_dtype;
 /* update shapes; must match cleandiffuser_b200/diffusion/solvers.py */
-typedef enum cds_update_kind { CDS_UPD_DDPM = 0, CDS_UPD_DDIM = 1, CDS_UPD_EPS = 2, CDS_UPD_X = 3, CDS_UPD_X2M = 4, CDS_UPD_CM = 5 } cds_update_kind;
+typedef enum cds_update_kind { CDS_UPD_DDPM = 0, CDS_UPD_DDIM = 1, CDS_UPD_EPS = 2, CDS_UPD_X = 3, CDS_UPD_X2M = 4, CDS_UPD_CM = 5,
+  /* ContinuousEDM (newedm.py:142-148, :411-431).  D = K0*x + K1*net (c_skip, c_out), clipped to [x_min, x_max] when final_clip;
+   *   CDS_UPD_EDM       Euler step   d = (x - D)/SIGMA;  x <- x - d*K2 (K2 = sigma_i - sigma_{i-1});  when K4 != 0 the step is
+   *                     the predictor of a Heun step: the old x goes to xhat_prev and d to aux
+   *   CDS_UPD_EDM_HEUN  corrector    d' = (x - D)/SIGMA (x = the predictor's result, SIGMA = sigma_{i-1});
+   *                     x <- xhat_prev - (aux + d')/2 * K2                                                              */
+  CDS_UPD_EDM = 6, CDS_UPD_EDM_HEUN = 7 } cds_update_kind;
 
 /* per-iteration coefficient row (floats), one row per reverse iteration */
 enum { CDS_ROW_ALPHA = 0, CDS_ROW_SIGMA = 1, CDS_ROW_K0 = 2, CDS_ROW_K1 = 3, CDS_ROW_K2 = 4, CDS_ROW_K3 = 5,
@@ -160,7 +166,8 @@ typedef struct cds_update_op {
   int64_t noise_slot_stride;     /* floats between slots; 0 = batch*row (the op covers the whole tape) */
   const float* prior; const float* mask;      /* mask: `row` floats or NULL */
   const float* x_min; const float* x_max;     /* `row` floats or NULL */
-  float* xhat_prev;              /* (batch,row) history for the 2M solvers or NULL */
+  float* xhat_prev;              /* (batch,row) history for the 2M solvers / the EDM Heun corrector, or NULL */
+  float* aux;                    /* (batch,row) second history buffer (EDM Heun: the predictor's slope) or NULL */
   const float* coef;
   int32_t predict_noise;
   int32_t final_clip;            /* CM only: clip the combined prediction to [x_min, x_max] */

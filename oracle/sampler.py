@@ -230,3 +230,57 @@ def sample_consistency(net, prior, tape, *, steps=1, temperature=1.0, fix_mask=0
         px = cm_denoise(net, x, t, cond_emb, **kw)
         px = px * (1. - fix_mask) + prior * fix_mask
     return px
+
+
+# ----------------------------------------------------------------------------- EDM
+def edm_denoise(net, x, sigma, cond_emb, w_cfg, *, sigma_data=0.5):
+    """ContinuousEDM.D under classifier-free guidance, newedm.py:142-148, :240-269; ``sigma`` is a (b,) tensor."""
+    def D(xx, ss, cc):
+        shape = (-1,) + (1,) * (xx.dim() - 1)
+        c_skip = sigma_data ** 2 / (sigma_data ** 2 + ss ** 2)
+        c_out = ss * sigma_data / (sigma_data ** 2 + ss ** 2).sqrt()
+        c_in = 1 / (sigma_data ** 2 + ss ** 2).sqrt()
+        return c_skip.reshape(shape) * xx + c_out.reshape(shape) * net(c_in.reshape(shape) * xx, 0.25 * ss.log(), cc)
+    if w_cfg != 0.0 and w_cfg != 1.0:
+        b = x.shape[0]
+        both = D(torch.cat([x, x], 0), torch.cat([sigma, sigma], 0), torch.cat([cond_emb, torch.zeros_like(cond_emb)], 0))
+        pc, pu = both[:b], both[b:]
+    elif w_cfg == 0.0:
+        pc, pu = 0., D(x, sigma, None)
+    else:
+        pc, pu = D(x, sigma, cond_emb), 0.
+    return w_cfg * pc + (1 - w_cfg) * pu
+
+
+def sample_edm(net, prior, tape, *, steps, solver="euler", temperature=1.0, fix_mask=0., cond_emb=None, w_cfg=0.0,
+               sigma_data=0.5, sigma_min=0.002, sigma_max=80., rho=7.0, x_min=None, x_max=None, diffusion_x=0,
+               warm_start=None, warm_level=0.3):
+    """ContinuousEDM.sample (no classifier), newedm.py:372-438: Euler / Heun on the Karras grid."""
+    assert solver in ("euler", "heun")
+    n = prior.shape[0]
+    if warm_start is not None and warm_level > 0.:
+        top = sigma_min + (sigma_max - sigma_min) * warm_level
+        x = warm_start + top * tape(warm_start)
+    else:
+        top = sigma_max
+        x = tape(prior) * sigma_max * temperature
+    x = x * (1. - fix_mask) + prior * fix_mask
+    sig = (sigma_min ** (1 / rho) + torch.arange(steps + 1) / steps * (top ** (1 / rho) - sigma_min ** (1 / rho))) ** rho
+    clip = x_min is not None or x_max is not None
+
+    def slope(xx, s_eval, s_div):
+        pred = edm_denoise(net, xx, torch.full((n,), s_eval, dtype=torch.float32), cond_emb, w_cfg, sigma_data=sigma_data)
+        if clip:
+            pred = pred.clip(x_min, x_max)
+        return (xx - pred) / s_div
+    for i in reversed([1] * diffusion_x + list(range(1, steps + 1))):
+        d = slope(x, sig[i], sig[i])
+        dt = sig[i] - sig[i - 1]
+        nxt = (x - d * dt) * (1. - fix_mask) + prior * fix_mask
+        if solver == "heun" and i > 1:
+            d2 = slope(nxt, sig[i] / sig[i] * sig[i - 1], sig[i - 1])
+            nxt = (x - (d + d2) / 2. * dt) * (1. - fix_mask) + prior * fix_mask
+        x = nxt
+    if clip:
+        x = x.clip(x_min, x_max)
+    return x

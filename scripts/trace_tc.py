@@ -9,7 +9,8 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 from cleandiffuser_b200.engine import cabi  # noqa: E402
 
-os.environ.update(CDS_BACKEND="cuda", CDS_MATH="bf16", CDS_GRAPH="0")
+os.environ.update(CDS_BACKEND="cuda", CDS_GRAPH="0")
+os.environ.setdefault("CDS_MATH", "tf32")
 targets = [int(a) for a in sys.argv[1:]] or [0, 4, 17, 18, 39]        # ordinal of the conv_tc launch inside one iteration
 agent, _, _ = bench.build_agent("cuda:0")
 B = 4096
@@ -19,7 +20,7 @@ with torch.no_grad():
     agent.sample(prior, solver="ddpm", n_samples=B, sample_steps=3, temperature=0.5)      # warm: plans, modules
 torch.cuda.synchronize()
 plan = next(iter(agent._engine_plans.values()))
-n_tc = sum(1 for op in plan.program.ops if op.kind == 0 and op.u.conv.math == 1)
+n_tc = sum(1 for op in plan.program.ops if op.kind == 0 and op.u.conv.math in (1, 2))
 SLOTS = 64
 buf = torch.zeros(1024 * SLOTS, dtype=torch.int64, device="cuda")
 for tgt in targets:
@@ -30,7 +31,7 @@ for tgt in targets:
     torch.cuda.synchronize()
     grid = lib.cds_debug_trace(None, 0, -1)
     t = buf.cpu().view(-1, SLOTS)[:grid].numpy()
-    convs = [op for op in plan.program.ops if op.kind == 0 and op.u.conv.math == 1]
+    convs = [op for op in plan.program.ops if op.kind == 0 and op.u.conv.math in (1, 2)]
     c = convs[tgt].u.conv
     print(f"== tc launch {tgt}: L {c.L_in}->{c.L_out} C {c.C_in}->{c.C_out} k{c.taps} gn{c.groups} grid {grid}")
     g0 = t[:, 0].min()

@@ -203,7 +203,24 @@ def run_update(u, it):
     xmax = _arr(u.x_max, (u.row,), (1,)) if u.x_max else None
     slot_stride = u.noise_slot_stride if u.noise_slot_stride > 0 else n
     z = _arr(u.noise + 4 * slot * slot_stride, (u.batch, u.row), (u.row, 1)) if slot >= 0 else None
-    if kind == 5:
+    if kind in (6, 7):                      # CDS_UPD_EDM / CDS_UPD_EDM_HEUN
+        d_theta = k0 * x + k1 * pr
+        if u.final_clip:
+            if xmin is not None:
+                d_theta = np.maximum(d_theta, xmin)
+            if xmax is not None:
+                d_theta = np.minimum(d_theta, xmax)
+        slope = (x - d_theta) / sigma
+        if kind == 6:
+            out = x - slope * k2
+            if k4 != 0 and u.xhat_prev and u.aux:
+                _arr(u.xhat_prev, (u.batch, u.row), (u.row, 1))[...] = x
+                _arr(u.aux, (u.batch, u.row), (u.row, 1))[...] = slope
+        else:
+            hist = _arr(u.xhat_prev, (u.batch, u.row), (u.row, 1))
+            aux = _arr(u.aux, (u.batch, u.row), (u.row, 1))
+            out = hist - (aux + slope) / f(2) * k2
+    elif kind == 5:
         out = k0 * x + k1 * pr
         if u.final_clip:
             if xmin is not None:

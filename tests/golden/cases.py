@@ -103,6 +103,21 @@ def sampler_cases():
     return out
 
 
+def edm_cases():
+    """ContinuousEDM.sample cases: both solvers x {plain, clip + fix_mask + Diffusion-X, two-branch CFG, warm start}."""
+    out = {}
+    for sv in ("euler", "heun"):
+        out[f"edm_{sv}_plain"] = dict(net="janner_tiny", solver=sv, steps=5, fix_mask=None, clip=False, w_cfg=0.0, cond=None,
+                                      temperature=1.0)
+        out[f"edm_{sv}_mask_clip_dx"] = dict(net="janner_tiny", solver=sv, steps=4, fix_mask="first_row", clip=True, w_cfg=1.0,
+                                             cond="emb", temperature=0.5, diffusion_x=2)
+        out[f"edm_{sv}_cfg2branch"] = dict(net="dql_tiny", solver=sv, steps=6, fix_mask=None, clip=True, w_cfg=1.7, cond="obs",
+                                           temperature=1.0)
+    out["edm_heun_warm"] = dict(net="janner_tiny", solver="heun", steps=4, fix_mask="first_row", clip=False, w_cfg=0.0, cond=None,
+                                temperature=1.0, warm=0.4)
+    return out
+
+
 def sampler_inputs(spec: dict, seed: int = 1):
     """prior / condition / masks for a sampler case (deterministic)."""
     g = torch.Generator().manual_seed(seed)

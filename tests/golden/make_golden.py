@@ -24,6 +24,7 @@ import cleandiffuser.nn_diffusion as ref_nn  # noqa: E402
 import cleandiffuser.nn_condition as ref_cond  # noqa: E402
 from cleandiffuser.diffusion import ContinuousDiffusionSDE, DiscreteDiffusionSDE  # noqa: E402
 from cleandiffuser.diffusion.consistency_model import ContinuousConsistencyModel  # noqa: E402
+from cleandiffuser.diffusion.newedm import ContinuousEDM  # noqa: E402
 from cleandiffuser.utils import (SUPPORTED_NOISE_SCHEDULES, SUPPORTED_SAMPLING_STEP_SCHEDULE,  # noqa: E402
                                  SUPPORTED_TIMESTEP_EMBEDDING, SinusoidalEmbedding)
 
@@ -133,9 +134,33 @@ def gen_consistency():
     print("consistency.npz", len(out))
 
 
+def gen_edm():
+    out = {}
+    for name, spec in cases.edm_cases().items():
+        net, _ = build_net(cases.SAMPLER_NETS[spec["net"]])
+        inp = cases.sampler_inputs(spec)
+        agent = ContinuousEDM(net, build_condition(spec), fix_mask=inp["fix_mask"], x_max=inp["x_max"], x_min=inp["x_min"],
+                              device="cpu")
+        agent.model_ema.eval()
+        kw = dict(solver=spec["solver"], n_samples=cases.SAMPLER_BATCH, sample_steps=spec["steps"], use_ema=True,
+                  temperature=spec["temperature"], condition_cfg=inp["cond"], w_cfg=spec["w_cfg"],
+                  diffusion_x_sampling_steps=spec.get("diffusion_x", 0))
+        if inp["warm"] is not None:
+            kw.update(warm_start_reference=inp["warm"], warm_start_forward_level=spec["warm"])
+        tape = NoiseTape()
+        with tape.active(), torch.no_grad():
+            x0, log = agent.sample(inp["prior"], **kw)
+        out[name + "/x0"] = x0.numpy()
+        for j, z in enumerate(tape.draws):
+            out[f"{name}/z{j}"] = z.numpy()
+        out[name + "/n_draws"] = np.array(len(tape.draws))
+    np.savez_compressed(os.path.join(HERE, "edm.npz"), **out)
+    print("edm.npz", len(out))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
-    gen_tables()
-    gen_nets()
-    gen_samplers()
-    gen_consistency()
+    only = sys.argv[1:]
+    for fn in (gen_tables, gen_nets, gen_samplers, gen_consistency, gen_edm):
+        if not only or fn.__name__[4:] in only:
+            fn()
