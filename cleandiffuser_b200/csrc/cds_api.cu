@@ -442,6 +442,25 @@ int cds_plan_run(cds_plan* p, int32_t first, int32_t count, void* stream, int32_
   return CDS_OK;
 }
 
+int cds_plan_run_range(cds_plan* p, int32_t iter, int32_t op_first, int32_t op_count, void* stream) {
+  if (!p || !p->finalized) return fail(CDS_ERR_STATE, "plan_run_range before finalize");
+  if (iter < 0 || iter >= p->n_iters) return fail(CDS_ERR_INVALID, "plan_run_range: iteration %d outside [0, %d)", iter, p->n_iters);
+  if (op_first < 0 || op_count < 0 || op_first + op_count > (int)p->steps.size())
+    return fail(CDS_ERR_INVALID, "plan_run_range: operators [%d, %d) outside [0, %d)", op_first, op_first + op_count, (int)p->steps.size());
+  if (p->n_branches > 1) return fail(CDS_ERR_UNSUPPORTED, "plan_run_range: programs with parallel branches run whole iterations only");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CDS_ON_DEVICE(p->device);
+  cds::set_iter_kernel<<<1, 1, 0, st>>>(p->d_iter, iter);
+  CDS_CUDA(cudaGetLastError());
+  for (int i = op_first; i < op_first + op_count; ++i) {
+    const Step& s = p->steps[i];
+    if ((s.op.flags & CDS_OPF_ONCE) || s.skip) continue;
+    int rc = launch(s, p->d_iter, p->sm_count, st, nullptr);
+    if (rc != CDS_OK) return rc;
+  }
+  return CDS_OK;
+}
+
 int cds_plan_profile(cds_plan* p, int32_t iter, void* stream, float* ms_per_op, int32_t n_ops) {
   if (!p || !p->finalized) return fail(CDS_ERR_STATE, "plan_profile before finalize");
   if (!ms_per_op || n_ops != (int)p->steps.size()) return fail(CDS_ERR_INVALID, "plan_profile: n_ops != %d", (int)p->steps.size());

@@ -166,10 +166,24 @@ class BaseDiffusionSDE(DiffusionModel):
 
         if engine_ok:
             from ..engine import runtime
+            guide = None
+            if self.classifier is not None and w_cg != 0.0:
+                # classifier guidance on the engine, step by step: the engine evaluates the denoiser, this callback adds the
+                # guidance term to the prediction in place (same tensor expression as classifier_guidance above), the engine
+                # applies the update.  The classifier's forward + input gradient stay PyTorch autograd.
+                def guide(n, i, x_t, pred):
+                    t = self._t_vector(n_samples, step_values[i])
+                    with torch.enable_grad():
+                        _, grad = self.classifier.gradients(x_t.clone(), t, condition_vec_cg)
+                    with torch.no_grad():
+                        if self.predict_noise:
+                            pred.copy_(pred - w_cg * sigmas[i] * grad)
+                        else:
+                            pred.copy_(pred + w_cg * ((sigmas[i] ** 2) / alphas[i]) * grad)
             out = runtime.try_sample(self, model=model, xt=xt, prior=prior, solver=solver,
                                      sample_steps=sample_steps, order=order, step_values=step_values,
                                      alphas=alphas, sigmas=sigmas, hs=hs, stds=stds,
-                                     cond_emb=condition_vec_cfg, w_cfg=w_cfg, n_samples=n_samples)
+                                     cond_emb=condition_vec_cfg, w_cfg=w_cfg, n_samples=n_samples, guide=guide)
             if out is not None:
                 return out
 
@@ -189,8 +203,6 @@ class BaseDiffusionSDE(DiffusionModel):
     def _engine_candidate(self, requires_grad, preserve_history, w_cg, warm_start_reference):
         """Cheap host-side screen; the detailed backbone/shape screen lives in engine/runtime.py."""
         if requires_grad or preserve_history:
-            return False
-        if self.classifier is not None and w_cg != 0.0:
             return False
         from ..engine import runtime
         return runtime._device_ok(torch.device(self.device))

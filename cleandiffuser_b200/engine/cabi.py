@@ -99,7 +99,7 @@ _lib = None
 
 # every symbol include/cds.h declares (tests check that the built library exports all of them)
 EXPORTS = ["cds_version", "cds_op_size", "cds_conv_tc_supported", "cds_last_error", "cds_device_sm_count", "cds_plan_create", "cds_plan_destroy",
-           "cds_plan_append", "cds_plan_finalize", "cds_plan_run", "cds_plan_profile", "cds_plan_launches_per_iter",
+           "cds_plan_append", "cds_plan_finalize", "cds_plan_run", "cds_plan_run_range", "cds_plan_profile", "cds_plan_launches_per_iter",
            "cds_run_op", "cds_debug_trace"]
 
 
@@ -127,6 +127,7 @@ def load():
     lib.cds_plan_append.argtypes = [C.c_void_p, C.POINTER(Op), C.c_int32]
     lib.cds_plan_finalize.argtypes = [C.c_void_p, C.c_int32]
     lib.cds_plan_run.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+    lib.cds_plan_run_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.cds_plan_profile.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     lib.cds_plan_launches_per_iter.argtypes = [C.c_void_p]
     lib.cds_run_op.argtypes = [C.c_int, C.POINTER(Op), C.c_int32, C.c_void_p]
@@ -161,6 +162,10 @@ class Plan:
 
     def run(self, first: int, count: int, stream: int, use_graph: bool = True):
         check(self._lib.cds_plan_run(self._h, int(first), int(count), C.c_void_p(stream), 1 if use_graph else 0))
+
+    def run_range(self, it: int, op_first: int, op_count: int, stream: int):
+        """operators [op_first, op_first + op_count) of iteration ``it`` with direct launches (the single-step entry)"""
+        check(self._lib.cds_plan_run_range(self._h, int(it), int(op_first), int(op_count), C.c_void_p(stream)))
 
     def profile(self, it: int, stream: int, n_ops: int):
         ms = (C.c_float * n_ops)()

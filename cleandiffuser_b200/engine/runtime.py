@@ -176,6 +176,8 @@ class SamplerPlan:
                 xin_ptr_t = self.xin
             xview = View(xin_ptr_t, L, Cn, offset=xin_off)
             pred = lower_denoiser(p, net, xview, x_shape, cfg_mode != 0, sub if cfg_mode == 2 else 0)
+            if K == 1:                 # the prediction buffer, for host callbacks between denoiser and update (guidance)
+                self.pred = pred.t if (pred.offset == 0 and pred.lstride == pred.C and pred.bstride == pred.L * pred.C) else None
 
             op = cabi.Op()
             op.kind = cabi.OP_UPDATE
@@ -252,6 +254,30 @@ class SamplerPlan:
         self.handle.run(first, self.n_iters - first if count is None else count, stream, use_graph)
         STATS["launches"] = self.handle.launches_per_iter() * self.n_iters + 1
 
+    def run_guided(self, t_all, cond_emb, xt, noise_slots, guide, t_key=None):
+        """The loop with a host callback between the denoiser and the update of every iteration (classifier guidance,
+        diffusionsde.py:153-173): per iteration the denoiser operators are enqueued through the single-step entry
+        (cds_plan_run_range), ``guide(n, x_t, pred)`` edits the prediction in place with ordinary PyTorch ops on the same stream,
+        then the update operator runs.  ``noise_slots[n]`` = 1 + tape slot of iteration n's draw, 0 = none."""
+        assert self.n_branches == 1 and self.pred is not None
+        ops = self.program.ops
+        upd = max(i for i, op in enumerate(ops) if op.kind == cabi.OP_UPDATE)
+        assert upd == len(ops) - 1, "the update must be the program's last operator"
+        self.fill_tables(t_all, cond_emb, t_key)
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
+        x_view = self.x.view(self.batch, *self.x_shape)
+        pred_view = self.pred.view(-1, *self.x_shape)[:self.batch]
+        self.handle.run(0, 0, stream, False)                       # the CDS_OPF_ONCE operators (x_t hand-over cast)
+        for n in range(self.n_iters):
+            slot = int(noise_slots[n]) - 1
+            if slot >= 0:
+                with torch.no_grad():
+                    _draw_noise(self.noise[slot], xt)
+            self.handle.run_range(n, 0, upd, stream)
+            guide(n, x_view, pred_view)
+            self.handle.run_range(n, upd, 1, stream)
+        STATS["launches"] = (self.handle.launches_per_iter() + 2) * self.n_iters + 1
+
     def run_chunked(self, t_all, cond_emb, xt, noise_rows, use_graph=True, t_key=None):
         """The whole loop, with the noise tape refilled between chunks when it is shorter than the number of draws
         (``noise_rows[n]`` = does iteration n draw?).  The draws are taken in loop order, so a seeded run consumes the
@@ -324,7 +350,9 @@ def _cond_rows(cfg_mode, cond_emb):
 
 
 def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_values, alphas, sigmas, hs, stds,
-               cond_emb, w_cfg, n_samples):
+               cond_emb, w_cfg, n_samples, guide=None):
+    """``guide``: optional host callback ``guide(n, i, x_t, pred)`` (n = iteration, i = its loop index) run between the denoiser
+    and the update of every iteration (classifier guidance); the loop then runs step by step instead of as a replayed graph."""
     if _backend() == "torch":
         return None
     device = _device_of(agent)
@@ -337,6 +365,9 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
     batch, x_shape = xt.shape[0], tuple(xt.shape[1:])
     if n_samples != batch:
         return _fallback("n_samples != prior.shape[0]")
+    if guide is not None and cfg_mode == 2:
+        # the update operator combines the two CFG branches itself; a guidance term would have to enter after that combine
+        return _fallback("classifier guidance together with two-branch classifier-free guidance")
 
     # ---- per-iteration scalars (host, reference op order); identical requests reuse the table (building it costs ~10 ms
     # of Python scalar arithmetic for 100 steps -- more than a tenth of a whole cfg2 sample() on the engine) ---------------
@@ -410,8 +441,15 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
         idx = torch.as_tensor(order, dtype=torch.long)
         t_all = t_cpu[idx].to(device)      # int64 (discrete) or float32 (continuous), one entry per iteration
     # the loop's draws: same calls, same order, same shapes as the reference loop's (diffusionsde.py:548,571,...)
-    plan.run_chunked(t_all, cond_emb, xt, (table[:, S.R_NOISE] > 0).tolist(), use_graph=os.environ.get("CDS_GRAPH", "1") != "0",
-                     t_key=(t_cpu.numpy().tobytes(), tuple(order)))
+    t_key = (t_cpu.numpy().tobytes(), tuple(order))
+    if guide is not None:
+        if plan.n_branches != 1 or getattr(plan, "pred", None) is None:
+            return _fallback("guided sampling needs a single-branch program with a dense prediction buffer")
+        slots = plan.coef[:, S.R_NOISE].cpu().tolist()              # tape slot per iteration as the update kernel sees it
+        plan.run_guided(t_all, cond_emb, xt, slots, lambda n, x, p: guide(n, order[n], x, p), t_key=t_key)
+    else:
+        plan.run_chunked(t_all, cond_emb, xt, (table[:, S.R_NOISE] > 0).tolist(),
+                         use_graph=os.environ.get("CDS_GRAPH", "1") != "0", t_key=t_key)
     STATS["engine_calls"] += 1
     return plan.x.clone()
 

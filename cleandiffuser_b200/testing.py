@@ -77,3 +77,33 @@ class NoiseTape:
             yield self
         finally:
             torch.randn_like = self._orig
+
+
+class ToyClassifier:
+    """A small deterministic stand-in with the reference's classifier surface (cleandiffuser/classifier/base.py:9-79:
+    ``model`` / ``model_ema`` / ``logp`` / ``gradients`` / ``train`` / ``eval``) for guided-sampling tests and goldens:
+    log p(c | x_t, t) = MLP([flatten(x_t), 0.01 t]) with synthetic weights.  The real classifiers (CumRewClassifier over
+    HalfJannerUNet1d ...) live in the reference and are used through the overlay; they are not part of this package."""
+
+    def __init__(self, x_shape, device="cpu", seed=5):
+        d = int(np.prod(x_shape))
+        net = torch.nn.Sequential(torch.nn.Linear(d + 1, 16), torch.nn.Tanh(), torch.nn.Linear(16, 1))
+        self.model = load_synth(net, seed).to(device)
+        self.model_ema = self.model
+        self.device = device
+
+    def train(self):
+        self.model.train()
+
+    def eval(self):
+        self.model.eval()
+
+    def logp(self, x, noise, c=None):
+        t = noise.to(torch.float32).reshape(-1, 1) * 0.01
+        return self.model_ema(torch.cat([torch.flatten(x, 1), t], 1))
+
+    def gradients(self, x, noise, c=None):
+        x.requires_grad_()
+        logp = self.logp(x, noise, c)
+        grad = torch.autograd.grad([logp.sum()], [x])[0]
+        return logp.detach(), grad.detach()

@@ -219,6 +219,13 @@ int cds_plan_finalize(cds_plan* plan, int32_t n_iters);
  * programmatic dependent launch (the next kernel's prologue and weight prefetch overlap the previous kernel's tail);
  * CDS_PDL=0 in the environment switches that off. */
 int cds_plan_run(cds_plan* plan, int32_t first, int32_t count, void* stream, int32_t use_graph);
+/* Single-step entry ("cds_step"): enqueue operators [op_first, op_first + op_count) of the program (indices into the appended
+ * operator list; CDS_OPF_ONCE operators inside the range are skipped) for iteration `iter` with direct launches -- the device
+ * iteration counter is set to `iter` first.  This is how a host callback is interleaved with the loop (classifier guidance,
+ * diffusionsde.py:153-173: the denoiser operators run, PyTorch adds the guidance term to the prediction in place, then the
+ * update operator runs); `cds_plan_run(plan, first, 0, ...)` runs the CDS_OPF_ONCE operators alone, and
+ * `cds_plan_run(plan, i, 1, ...)` is the whole iteration i. */
+int cds_plan_run_range(cds_plan* plan, int32_t iter, int32_t op_first, int32_t op_count, void* stream);
 /* Run iteration `iter` once with direct launches, bracketing every operator with CUDA events on `stream`;
  * ms_per_op[i] receives the device time of operator i (n_ops entries; CDS_OPF_ONCE operators are run and timed first).
  * Synchronises `stream`.  For bench.py's live per-kernel roofline; note that it advances x_t like a normal iteration. */

@@ -289,3 +289,24 @@ def run_program(ops, n_iters, first=0):
                     run_cast(op.u.cast)
                 else:
                     raise ValueError(op.kind)
+
+
+class Handle:
+    """Stand-in for ``cabi.Plan`` that executes the program on this interpreter (tests patch ``runtime._make_handle``)."""
+
+    def __init__(self, ops, n_iters):
+        self.ops, self.n_iters = list(ops), n_iters
+
+    def run(self, first, count, stream, use_graph=True):
+        run_program(self.ops, count, first)
+
+    def run_range(self, it, op_first, op_count, stream):
+        """cds_plan_run_range: operators [op_first, op_first + op_count) of iteration ``it`` (CDS_OPF_ONCE ones skipped)"""
+        keep = [op for op in self.ops[op_first:op_first + op_count] if not (op.flags & cabi.OPF_ONCE)]
+        run_program(keep, 1, it)
+
+    def launches_per_iter(self):
+        return len(self.ops)
+
+    def close(self):
+        pass

@@ -118,6 +118,19 @@ def edm_cases():
     return out
 
 
+def guided_cases():
+    """Classifier-guided sampling (diffusionsde.py:153-173, :597-606) with cleandiffuser_b200.testing.ToyClassifier attached:
+    the Diffuser pattern (x0-prediction, DDPM, fix_mask, w_cg = 0.3) and eps-prediction with a condition branch."""
+    return {
+        "cg_disc_ddpm_x0": dict(kind="discrete", net="janner_tiny", solver="ddpm", predict_noise=False, T=10, steps=10,
+                                fix_mask="first_row", clip=False, w_cfg=0.0, cond=None, temperature=0.5, w_cg=0.3),
+        "cg_disc_ddim_eps_clip": dict(kind="discrete", net="janner_tiny", solver="ddim", predict_noise=True, T=20, steps=5,
+                                      fix_mask="first_row", clip=True, w_cfg=0.0, cond=None, temperature=1.0, w_cg=0.7),
+        "cg_cont_2M_eps_cond": dict(kind="continuous", net="janner_tiny", solver="ode_dpmsolver++_2M", predict_noise=True, steps=5,
+                                    fix_mask=None, clip=True, w_cfg=1.0, cond="emb", temperature=0.5, schedule="linear", w_cg=0.4),
+    }
+
+
 def sampler_inputs(spec: dict, seed: int = 1):
     """prior / condition / masks for a sampler case (deterministic)."""
     g = torch.Generator().manual_seed(seed)

@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, "/root/reference")
 
 import cases  # noqa: E402
-from cleandiffuser_b200.testing import NoiseTape, state_checksum, synth_state_dict  # noqa: E402
+from cleandiffuser_b200.testing import NoiseTape, ToyClassifier, state_checksum, synth_state_dict  # noqa: E402
 
 import cleandiffuser.nn_diffusion as ref_nn  # noqa: E402
 import cleandiffuser.nn_condition as ref_cond  # noqa: E402
@@ -134,6 +134,37 @@ def gen_consistency():
     print("consistency.npz", len(out))
 
 
+def gen_guided():
+    out = {}
+    for name, spec in cases.guided_cases().items():
+        ncase = cases.SAMPLER_NETS[spec["net"]]
+        net, _ = build_net(ncase)
+        inp = cases.sampler_inputs(spec)
+        common = dict(nn_condition=build_condition(spec), fix_mask=inp["fix_mask"], x_max=inp["x_max"], x_min=inp["x_min"],
+                      predict_noise=spec["predict_noise"], device="cpu", noise_schedule=spec.get("schedule", "cosine"),
+                      classifier=ToyClassifier(ncase["x"]))
+        if spec["kind"] == "discrete":
+            agent = DiscreteDiffusionSDE(net, diffusion_steps=spec["T"], **common)
+            sched = "uniform"
+        else:
+            agent = ContinuousDiffusionSDE(net, **common)
+            sched = "uniform_continuous"
+        agent.model_ema.eval()
+        tape = NoiseTape()
+        with tape.active():
+            x0, log = agent.sample(inp["prior"], solver=spec["solver"], n_samples=cases.SAMPLER_BATCH, sample_steps=spec["steps"],
+                                   sample_step_schedule=sched, use_ema=True, temperature=spec["temperature"],
+                                   condition_cfg=inp["cond"], w_cfg=spec["w_cfg"], w_cg=spec["w_cg"])
+        out[name + "/x0"] = x0.detach().numpy()
+        if log.get("log_p") is not None:
+            out[name + "/log_p"] = log["log_p"].detach().numpy()
+        for j, z in enumerate(tape.draws):
+            out[f"{name}/z{j}"] = z.numpy()
+        out[name + "/n_draws"] = np.array(len(tape.draws))
+    np.savez_compressed(os.path.join(HERE, "guided.npz"), **out)
+    print("guided.npz", len(out))
+
+
 def gen_edm():
     out = {}
     for name, spec in cases.edm_cases().items():
@@ -161,6 +192,6 @@ def gen_edm():
 if __name__ == "__main__":
     torch.set_num_threads(1)
     only = sys.argv[1:]
-    for fn in (gen_tables, gen_nets, gen_samplers, gen_consistency, gen_edm):
+    for fn in (gen_tables, gen_nets, gen_samplers, gen_consistency, gen_edm, gen_guided):
         if not only or fn.__name__[4:] in only:
             fn()

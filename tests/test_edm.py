@@ -55,19 +55,6 @@ def test_edm_torch_path_matches_reference(golden, name, monkeypatch):
     np.testing.assert_allclose(x0.numpy(), golden["edm"][name + "/x0"], rtol=1e-5, atol=2e-4)
 
 
-class EmuHandle:
-    def __init__(self, ops, n_iters):
-        self.ops = list(ops)
-
-    def run(self, first, count, stream, use_graph=True):
-        emulator.run_program(self.ops, count, first)
-
-    def launches_per_iter(self):
-        return len(self.ops)
-
-    def close(self):
-        pass
-
 
 @pytest.mark.parametrize("math", ["fp32", "tf32"])
 @pytest.mark.parametrize("name", NAMES)
@@ -75,7 +62,7 @@ def test_lowered_edm_program(golden, name, math, monkeypatch):
     """The engine program of ContinuousEDM.sample (PREP -> denoiser -> CDS_UPD_EDM / _HEUN per network evaluation) on the
     numpy interpreter of the ABI."""
     monkeypatch.setattr(runtime, "_device_ok", lambda device: True)
-    monkeypatch.setattr(runtime, "_make_handle", lambda device, ops, n: EmuHandle(ops, n))
+    monkeypatch.setattr(runtime, "_make_handle", lambda device, ops, n: emulator.Handle(ops, n))
     monkeypatch.setenv("CDS_BACKEND", "cuda")
     monkeypatch.setenv("CDS_MATH", math)
     spec = cases.edm_cases()[name]

@@ -15,24 +15,11 @@ from cleandiffuser_b200.nn_condition import IdentityCondition
 from cleandiffuser_b200.testing import NoiseTape
 
 
-class EmuHandle:
-    def __init__(self, ops, n_iters):
-        self.ops, self.n_iters = list(ops), n_iters
-
-    def run(self, first, count, stream, use_graph=True):
-        emulator.run_program(self.ops, count, first)
-
-    def launches_per_iter(self):
-        return len(self.ops)
-
-    def close(self):
-        pass
-
 
 @pytest.fixture(autouse=True)
 def _emulate(monkeypatch):
     monkeypatch.setattr(runtime, "_device_ok", lambda device: True)
-    monkeypatch.setattr(runtime, "_make_handle", lambda device, ops, n: EmuHandle(ops, n))
+    monkeypatch.setattr(runtime, "_make_handle", lambda device, ops, n: emulator.Handle(ops, n))
     monkeypatch.setenv("CDS_BACKEND", "cuda")       # any fallback to the PyTorch loop is a failure here
     monkeypatch.setenv("CDS_MATH", "fp32")
 

@@ -25,19 +25,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "cleandiffuser")), reason="reference tree not present")
 
 
-class EmuHandle:
-    def __init__(self, ops, n_iters):
-        self.ops = list(ops)
-
-    def run(self, first, count, stream, use_graph=True):
-        emulator.run_program(self.ops, count, first)
-
-    def launches_per_iter(self):
-        return len(self.ops)
-
-    def close(self):
-        pass
-
 
 @pytest.fixture()
 def ref(monkeypatch):
@@ -49,7 +36,7 @@ def ref(monkeypatch):
     import cleandiffuser
     assert os.path.realpath(cleandiffuser.__file__).startswith(os.path.realpath(REF))
     monkeypatch.setattr(runtime, "_device_ok", lambda device: True)
-    monkeypatch.setattr(runtime, "_make_handle", lambda device, ops, n: EmuHandle(ops, n))
+    monkeypatch.setattr(runtime, "_make_handle", lambda device, ops, n: emulator.Handle(ops, n))
     monkeypatch.setenv("CDS_BACKEND", "cuda")            # any fallback to the PyTorch loop raises
     yield cleandiffuser
     for k in [k for k in sys.modules if k == "cleandiffuser" or k.startswith("cleandiffuser.")]:
