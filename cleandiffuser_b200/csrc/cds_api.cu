@@ -200,6 +200,7 @@ int preload_kernels() {
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<32>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<64>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_mma_hd32_kernel));
+  CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_mma_tf32_hd32_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::solver_update_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cm_prep_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cast_pad_kernel));

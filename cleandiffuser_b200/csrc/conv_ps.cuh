@@ -27,6 +27,8 @@ namespace cds {
 
 struct ConvPsParams {
   CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
+  CUtensorMap tm_out;             // output as a TMA-store target: box {16 channels, 1 position, 32 trajectories} (one epilogue warp's
+  int out_tma;                    // lanes x 16 columns), staged in shared memory; valid when out_tma != 0
   int batch, C_out, taps, pad;
   int kchunks, kchunks2;          // channel chunks of the main conv / of the shortcut conv
   int n_tiles;                    // column tiles per trajectory tile (C_out / N)
@@ -101,6 +103,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
     ptx::prefetch_tensormap(&p.tm_a);
     ptx::prefetch_tensormap(&p.tm_b);
     if (HAS_RES) { ptx::prefetch_tensormap(&p.tm_a2); ptx::prefetch_tensormap(&p.tm_b2); }
+    if (p.out_tma) ptx::prefetch_tensormap(&p.tm_out);
   }
   if (warp == kPsWarpMma) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
   ptx::tc_fence_before_sync();
@@ -314,8 +317,39 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
         o[4 * k + 2] = mish_fma(fmaf(fmaf(v[4 * k + 2] + bb.z, ga, gc), gm.z, be.z), addv[4 * k + 2]);
         o[4 * k + 3] = mish_fma(fmaf(fmaf(v[4 * k + 3] + bb.w, ga, gc), gm.w, be.w), addv[4 * k + 3]);
       }
-      if (valid) store_row<16>(p.out, (int64_t)b * p.out_bstride + (int64_t)lp * p.out_lstride + n_off + n0, kActDtype, o);
+      if (p.out_tma) {
+        // 32 trajectories (lanes) x 16 columns of position lp through shared memory and ONE bulk store: a warp-level st.global
+        // would touch 32 cache lines per instruction.  The operand ring is idle once the accumulators are complete (one tile
+        // per CTA), its first 2 KB (fp32) / 1 KB (bf16) per warp serve as staging rows in the swizzle of tm_out.
+        uint8_t* const stg = smem_al + warp * 2048;
+        if (lane == 0) ptx::bulk_wait_group_read<0>();
+        __syncwarp();
+        if constexpr (TF32) {
+          uint8_t* const sr = stg + lane * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(sr + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                make_float4(round_tf32(o[4 * k]), round_tf32(o[4 * k + 1]), round_tf32(o[4 * k + 2]), round_tf32(o[4 * k + 3]));
+        } else {
+          uint8_t* const sr = stg + lane * 32;
+          const int sw = (lane >> 2) & 1;
+          uint32_t w[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]); w[k] = *reinterpret_cast<uint32_t*>(&h2); }
+          *reinterpret_cast<uint4*>(sr + ((0 ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(sr + ((1 ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_3d(&p.tm_out, stg, n_off + n0, lp, b0 + 32 * q);
+          ptx::bulk_commit_group();
+        }
+      } else if (valid) {
+        store_row<16>(p.out, (int64_t)b * p.out_bstride + (int64_t)lp * p.out_lstride + n_off + n0, kActDtype, o);
+      }
     }
+    if (lane == 0) ptx::bulk_wait_group<0>();        // the bulk stores are complete before the CTA retires
     if (threadIdx.x == 0) { CDS_TRACE(11, clock64()); CDS_TRACE(5, 1LL); }
     ptx::tc_fence_before_sync();
   }
@@ -406,6 +440,21 @@ inline bool conv_ps_prepare(const cds_conv_op& c, ConvPsLaunch* out) {
   p.gn_gamma = c.gn_gamma; p.gn_beta = c.gn_beta; p.gn_eps = c.gn_eps;
   p.res = c.res; p.res_bstride = c.res_bstride; p.res_lstride = c.res_lstride; p.res_bias = c.res_bias;
   p.out = c.out; p.out_bstride = c.out_bstride; p.out_lstride = c.out_lstride;
+  {
+    const int oes = tf32 ? 4 : 2;
+    p.out_tma = 0;
+    PFN_encodeTiled enc = get_encode_tiled();
+    const bool ok = ((uintptr_t)c.out % 16) == 0 && ((int64_t)c.out_lstride * oes) % 16 == 0 && ((int64_t)c.out_bstride * oes) % 16 == 0 &&
+                    !getenv("CDS_NO_TMA_STORE");
+    cuuint64_t gdim[3] = {(cuuint64_t)c.C_out, (cuuint64_t)c.L_out, (cuuint64_t)c.batch};
+    cuuint64_t gstr[2] = {(cuuint64_t)c.out_lstride * oes, (cuuint64_t)c.out_bstride * oes};
+    cuuint32_t bx[3] = {16u, 1u, 32u};
+    cuuint32_t es[3] = {1u, 1u, 1u};
+    if (ok && enc && enc(&p.tm_out, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.out, gdim, gstr, bx, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, tf32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      p.out_tma = 1;
+  }
   L.grid = dim3((unsigned)(((c.batch + 127) / 128) * p.n_tiles));
   return true;
 }

@@ -40,6 +40,10 @@ constexpr int kTcMaxStages = 10;
 
 struct ConvTcParams {
   CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
+  // output as a TMA-store target: box {16 channels, L positions, 32/L trajectories} = the 32 tile rows one epilogue warp owns
+  // x 16 columns, staged in shared memory (SWIZZLE_64B for 4-byte / SWIZZLE_32B for 2-byte elements).  Valid when out_tma != 0.
+  CUtensorMap tm_out;
+  int out_tma;
   int batch, L, log2L, C_out, taps, pad;   // L = output positions per tile-trajectory; C_out = channels per phase
   int num_tiles;                  // ceil(batch*L / 128); CTAs are persistent and stride over the tiles
   int phases;                     // 2: columns [0,C_out) / [C_out,2C_out) are output positions 2l / 2l+1 (transposed conv)
@@ -168,7 +172,8 @@ struct ConvTcCfg {
   // at least 3, at most kTcMaxStages.  A tile is taps x C_in/KC k-blocks (5..20): only a ring that holds more than one tile
   // lets the TMA producer run ahead of the tile whose accumulator the epilogue is still draining -- with 4 stages and
   // 5 k-blocks per tile every tile paid one exposed L2 round trip (~1 us) on the narrow layers.
-  static constexpr int kRingBudget = (N <= 128 ? 100 : 200) * 1024;
+  // (2 CTAs/SM: 227 KB - 2 x (22 KB static: per-column constants, 16 KB of epilogue store staging, barriers) - 2 x 1 KB reserved)
+  static constexpr int kRingBudget = (N <= 128 ? 88 : 184) * 1024;
   static constexpr int kStagesFit = kRingBudget / kStageBytes;
   static constexpr int kStages = kStagesFit < 3 ? 3 : (kStagesFit > kTcMaxStages ? kTcMaxStages : kStagesFit);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
@@ -257,6 +262,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   // per-column constants of the epilogue, staged once per CTA while the main loop runs:
   // 0 bias  1 GN gamma  2 GN beta  3 FiLM scale  4 FiLM shift  5 shortcut bias   (iteration-indexed "step" parts)
   __shared__ __align__(16) float s_col[6][Cfg::kCols];
+  // epilogue store staging: every epilogue warp owns 32 rows x 16 columns (2 KB of fp32 / 1 KB of bf16), written in the
+  // swizzle of p.tm_out and handed to the TMA unit as one bulk store -- a warp-level st.global of its 32 rows would touch 32
+  // different cache lines per instruction (measured: the LSU serialises them, the store's source registers stay locked and the
+  // epilogue stalls on them), the bulk store writes whole sectors and costs the warp 4 conflict-free st.shared
+  __shared__ __align__(1024) uint8_t s_stage[kTcEpiThreads / 32][2048];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // operand ring, 1024-byte aligned (swizzle atoms)
@@ -277,6 +287,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     ptx::prefetch_tensormap(&p.tm_a);
     ptx::prefetch_tensormap(&p.tm_b);
     if (HAS_RES) { ptx::prefetch_tensormap(&p.tm_a2); ptx::prefetch_tensormap(&p.tm_b2); }
+    if (p.out_tma) ptx::prefetch_tensormap(&p.tm_out);
   }
   if (warp == 9) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
   ptx::tc_fence_before_sync();
@@ -423,7 +434,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     // scheduler at ~0.2 IPC each), so instructions per tile are what counts: the option dispatch happens ONCE per kernel (the
     // tile loop lives inside the specialisation), addresses are strength-reduced to one multiply-add per tile, dtypes are fixed.
     const bool fast_ok = N >= 32 && p.n_col_tiles <= 1 && has_gn && p.act == CDS_ACT_MISH && film != 2 && p.phases == 1 && io_vec &&
-                         p.out_dtype == kActDtype && (!add_res || act_readable(p.res_dtype)) && p.res_batch_mod == 0;
+                         p.out_dtype == kActDtype && (!add_res || act_readable(p.res_dtype)) && p.res_batch_mod == 0 && p.out_tma;
     auto fast_tiles = [&](auto film_tag, auto res_tag) {
       constexpr bool SHIFT = decltype(film_tag)::value == 1;
       constexpr bool RES = decltype(res_tag)::value;
@@ -436,9 +447,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       const float eps = p.gn_eps;
       const int L_ = p.L, log2L_ = p.log2L, batch_ = p.batch;
       using ET = std::conditional_t<TF32, float, __nv_bfloat16>;     // activation element
-      ET* const out_l = reinterpret_cast<ET*>(p.out) + (int64_t)l * p.out_lstride;
       const ET* const res_l = RES ? reinterpret_cast<const ET*>(p.res) + (int64_t)l * p.res_lstride : nullptr;
-      const int64_t out_bs = p.out_bstride, res_bs = p.res_bstride;
+      uint8_t* const stg = &s_stage[warp][0];                         // this warp's 32 rows x 16 columns
+      uint8_t* const stg_row = stg + lane * (16 * (int)sizeof(ET));
+      const int traj_q = (32 * q) >> p.log2L;                         // first trajectory of this warp's rows inside the tile
+      const int64_t res_bs = p.res_bstride;
       const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it % Cfg::kAccBufs;
@@ -447,7 +460,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         const int b = (tile / SPLIT) * T_ + tb;
         const bool valid = b < batch_;
         const uint32_t t_row = t_lane + (uint32_t)(buf * Cfg::kColsPerTile);
-        ET* const out_row = out_l + (int64_t)b * out_bs + n_off;
+        const int traj0 = (tile / SPLIT) * T_ + traj_q;
         const ET* const res_row_p = RES ? res_l + (int64_t)b * res_bs + n_off : nullptr;
         ptx::mbar_wait(&tmem_full_bar[buf], use & 1);
         ptx::tc_fence_after_sync();
@@ -513,6 +526,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
               }
             }
             uint32_t packed[8];
+            // the warp's staging rows are free again once its previous bulk store has READ them
+            if (lane == 0) ptx::bulk_wait_group_read<0>();
+            __syncwarp();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float4 gm = reinterpret_cast<const float4*>(cb + 1 * Cfg::kCols + 16 * h)[k];
@@ -523,7 +539,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
               const float o2 = mish_fma(fmaf(fmaf(v[16 * h + 4 * k + 2], ga[g], gc[g]), gm.z, be.z), addv[4 * k + 2]);
               const float o3 = mish_fma(fmaf(fmaf(v[16 * h + 4 * k + 3], ga[g], gc[g]), gm.w, be.w), addv[4 * k + 3]);
               if constexpr (TF32) {
-                if (valid) reinterpret_cast<float4*>(out_row + n0 + 16 * h)[k] =
+                // 16-byte chunk k of this row's 64 staged bytes, SWIZZLE_64B: chunk index ^= address bits [7:8] = (row >> 1) & 3
+                *reinterpret_cast<float4*>(stg_row + ((k ^ ((lane >> 1) & 3)) << 4)) =
                     make_float4(round_tf32(o0), round_tf32(o1), round_tf32(o2), round_tf32(o3));
               } else {
                 __nv_bfloat162 p01 = __floats2bfloat162_rn(o0, o1), p23 = __floats2bfloat162_rn(o2, o3);
@@ -531,12 +548,16 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
                 packed[2 * k + 1] = *reinterpret_cast<uint32_t*>(&p23);
               }
             }
-            if constexpr (!TF32) {
-              if (valid) {
-                uint4* op = reinterpret_cast<uint4*>(out_row + n0 + 16 * h);
-                op[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                op[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-              }
+            if constexpr (!TF32) {     // 32 staged bytes per row, SWIZZLE_32B: chunk index ^= address bit 7 = (row >> 2) & 1
+              const int sw = (lane >> 2) & 1;
+              *reinterpret_cast<uint4*>(stg_row + ((0 ^ sw) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+              *reinterpret_cast<uint4*>(stg_row + ((1 ^ sw) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+            ptx::fence_proxy_async();                       // generic-proxy writes -> visible to the TMA unit
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_3d(&p.tm_out, stg, n_off + n0 + 16 * h, 0, traj0);
+              ptx::bulk_commit_group();
             }
           }
         }
@@ -569,6 +590,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       const int batch_ = p.batch, phases_ = p.phases, C_out_ = p.C_out;
       const int64_t out_bs = p.out_bstride, out_ls = p.out_lstride;
       const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+      const bool use_tma = p.out_tma != 0 && phases_ == 1;           // (two-phase transposed convs interleave positions: direct stores)
+      uint8_t* const stg = &s_stage[warp][0];
+      const int traj_q = (32 * q) >> p.log2L;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it % Cfg::kAccBufs;
         const uint32_t use = (uint32_t)(it / Cfg::kAccBufs);
@@ -600,7 +624,36 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
             v[4 * k] = tc_act<ACT>(ACT, v[4 * k] + bb.x); v[4 * k + 1] = tc_act<ACT>(ACT, v[4 * k + 1] + bb.y);
             v[4 * k + 2] = tc_act<ACT>(ACT, v[4 * k + 2] + bb.z); v[4 * k + 3] = tc_act<ACT>(ACT, v[4 * k + 3] + bb.w);
           }
-          if (valid) {
+          if (use_tma) {
+            // through the warp's staging rows and one bulk store (see s_stage); rows beyond the batch are clipped by the TMA unit
+            if (lane == 0) ptx::bulk_wait_group_read<0>();
+            __syncwarp();
+            if constexpr (OUT_BF16) {
+              uint32_t w[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) { __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]); w[k] = *reinterpret_cast<uint32_t*>(&h2); }
+              uint8_t* const sr = stg + lane * 32;
+              const int sw = (lane >> 2) & 1;
+              *reinterpret_cast<uint4*>(sr + ((0 ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(sr + ((1 ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+              uint8_t* const sr = stg + lane * 64;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float4 o4;
+                if constexpr (OUT_DT == CDS_TF32)
+                  o4 = make_float4(round_tf32(v[4 * k]), round_tf32(v[4 * k + 1]), round_tf32(v[4 * k + 2]), round_tf32(v[4 * k + 3]));
+                else o4 = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                *reinterpret_cast<float4*>(sr + ((k ^ ((lane >> 1) & 3)) << 4)) = o4;
+              }
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_3d(&p.tm_out, stg, c0, 0, (tile / nct) * T_ + traj_q);
+              ptx::bulk_commit_group();
+            }
+          } else if (valid) {
             const int64_t oo = (int64_t)b * out_bs + (int64_t)(l * phases_ + phase) * out_ls + c0;
             if constexpr (OUT_BF16) {
               uint32_t w[8];
@@ -887,6 +940,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     if (threadIdx.x == 0) CDS_TRACE(5, (long long)it);
   }
 
+  // bulk stores issued by the epilogue warps' lane 0 must be complete (shared memory read AND global writes performed) before
+  // the CTA retires
+  if (warp < kTcEpiThreads / 32 && lane == 0) ptx::bulk_wait_group<0>();
   __syncthreads();
   if (warp == 9) {
     ptx::tc_fence_after_sync();
@@ -1063,6 +1119,25 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
     uint64_t s2[1] = {(uint64_t)c.res_C};
     uint32_t b2[2] = {(uint32_t)ke, (uint32_t)L.n};
     if (!encode_act_map(&p.tm_b2, c.res_w, 2, d2, s2, b2, kc, tf32)) return false;
+  }
+  {
+    // output as a TMA-store target (the fast epilogue lanes stage 32 rows x 16 columns per warp and bulk-store them): needs whole
+    // 16-column groups, 16-byte aligned rows, one phase, at most 32 positions per trajectory
+    const int oes = c.out_dtype == CDS_BF16 ? 2 : 4;
+    const bool ok = c.phases == 1 && c.C_out % 16 == 0 && Lp <= 32 && ((uintptr_t)c.out % 16) == 0 &&
+                    ((int64_t)c.out_lstride * oes) % 16 == 0 && ((int64_t)c.out_bstride * oes) % 16 == 0 && !getenv("CDS_NO_TMA_STORE");
+    p.out_tma = 0;
+    if (ok) {
+      PFN_encodeTiled enc = get_encode_tiled();
+      cuuint64_t gdim[3] = {(cuuint64_t)c.C_out, (cuuint64_t)Lp, (cuuint64_t)c.batch};
+      cuuint64_t gstr[2] = {(cuuint64_t)c.out_lstride * oes, (cuuint64_t)c.out_bstride * oes};
+      cuuint32_t bx[3] = {16u, (cuuint32_t)Lp, (cuuint32_t)(32 / Lp)};
+      cuuint32_t es[3] = {1u, 1u, 1u};
+      if (enc && enc(&p.tm_out, oes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c.out, gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, oes == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        p.out_tma = 1;
+    }
   }
   p.batch = c.batch; p.L = Lp; p.log2L = ilog2(Lp); p.C_out = c.C_out; p.taps = c.taps; p.pad = c.pad;
   p.phases = c.phases;

@@ -251,6 +251,30 @@ def test_wide_chiunet_layers_lower_to_tensor_core_ops(monkeypatch):
     assert len(wide) >= 6 and all(c.math == cabi.MATH_BF16_TC for c in wide)
 
 
+def test_dit_tf32_program_keeps_attention_on_tensor_cores(monkeypatch):
+    """TF32 programs: DiT1d's Linear layers are TF32 tensor-core operators over fp32 tokens; q/k/v are written TF32-rounded
+    (cds_dtype CDS_TF32), which selects the mma.sync tf32 attention kernel (head_dim 32, L <= 128) instead of the fp32 one."""
+    monkeypatch.setenv("CDS_MATH", "tf32")
+    from cleandiffuser_b200.engine import cabi
+    from cleandiffuser_b200.engine.lower import Program, View, lower_denoiser
+    from cleandiffuser_b200.nn_diffusion import DiT1d
+    from cleandiffuser_b200.testing import load_synth
+    net = load_synth(DiT1d(29, emb_dim=128, d_model=320, n_heads=10, depth=2, timestep_emb_type="fourier"), seed=0).eval()
+    B, L = 3, 100
+    p = Program(torch.device("cpu"), B, 1, cabi.MATH_TF32_TC)
+    lower_denoiser(p, net, View(p.buf(B, L, 29), L, 29), (L, 29), True, 0)
+    tc = [op.u.conv for op in p.ops if op.kind == cabi.OP_CONV and op.u.conv.math == cabi.MATH_TF32_TC]
+    assert sorted((c.C_in, c.C_out) for c in tc) == sorted([(320, 960), (320, 320), (320, 1280), (1280, 320)] * 2 + [(32, 320), (320, 29)])
+    attn = [op.u.attn for op in p.ops if op.kind == cabi.OP_ATTN]
+    assert len(attn) == 2 and all(a.qkv_dtype == cabi.TF32 and a.out_dtype == cabi.TF32 for a in attn)
+    g = torch.Generator().manual_seed(2)
+    x, cond, t = torch.randn(B, L, 29, generator=g), torch.randn(B, 128, generator=g), torch.tensor([0.37])
+    with torch.no_grad():
+        want = net(x, t.expand(B), cond).numpy()
+    err = np.abs(runtime.engine_forward(net, x, t, cond).numpy() - want)
+    assert err.max() < 2e-2 and err.mean() < 2e-3, (float(err.max()), float(err.mean()))
+
+
 def test_dit_linear_layers_lower_to_flattened_tensor_core_ops(monkeypatch):
     """DiT1d on a tensor-core program: QKV / out-proj / MLP Linear layers become tensor-core operators over the token stream
     flattened to rows*L length-1 sequences (L = 100 is not a tile-friendly length), per-trajectory gates follow through
