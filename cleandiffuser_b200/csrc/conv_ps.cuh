@@ -29,6 +29,10 @@ struct ConvPsParams {
   CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
   CUtensorMap tm_out;             // output as a TMA-store target: box {16 channels, 1 position, 32 trajectories} (one epilogue warp's
   int out_tma;                    // lanes x 16 columns), staged in shared memory; valid when out_tma != 0
+  // > 1: the n_tiles column-tile CTAs of a trajectory tile form a thread-block cluster of this size and share the activation
+  // tiles -- CTA r fetches input position(s) l = r (mod cluster) once and MULTICASTS them into the shared memory of all of them
+  // (each activation byte crosses the L2 -> SM fabric once per trajectory tile instead of once per column tile)
+  int cluster;
   int batch, C_out, taps, pad;
   int kchunks, kchunks2;          // channel chunks of the main conv / of the shortcut conv
   int n_tiles;                    // column tiles per trajectory tile (C_out / N)
@@ -94,8 +98,12 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
   const uint32_t main_bytes = (uint32_t)(P * Cfg::kATile + p.taps * Cfg::kBTile);
   const uint32_t res_bytes = (uint32_t)(P * Cfg::kATile + Cfg::kBTile);
 
+  const int cs = p.cluster;                           // cluster size (1 = no multicast)
+  const uint32_t crank = cs > 1 ? ptx::cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    // a stage is free again when the MMAs of EVERY CTA of the cluster have consumed it (peers multicast into it)
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], (uint32_t)cs); }
     ptx::mbar_init(&tmem_full_bar, 1);
     ptx::fence_barrier_init();
   }
@@ -108,6 +116,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
   if (warp == kPsWarpMma) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (cs > 1) ptx::cluster_sync();                    // every CTA's barriers exist before a peer can signal them
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_holder;
   if (threadIdx.x == 0) { CDS_TRACE(2, clock64()); ptx::grid_dep_launch_dependents(); }
@@ -143,8 +152,10 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
         }
         uint8_t* sa = smem_al + s * Cfg::kStageBytes;
         for (int l = 0; l < P; ++l) {
-          if (is_main) ptx::tma_load_3d(sa + l * Cfg::kATile, &p.tm_a, &full_bar[s], c * KE, l, a_b0);
-          else ptx::tma_load_3d(sa + l * Cfg::kATile, &p.tm_a2, &full_bar[s], (c - n_main) * KE, l, r_b0);
+          const void* tm = is_main ? (const void*)&p.tm_a : (const void*)&p.tm_a2;
+          const int ck = is_main ? c * KE : (c - n_main) * KE, bb = is_main ? a_b0 : r_b0;
+          if (cs == 1) ptx::tma_load_3d(sa + l * Cfg::kATile, tm, &full_bar[s], ck, l, bb);
+          else if ((uint32_t)(l % cs) == crank) ptx::tma_load_3d_mc(sa + l * Cfg::kATile, tm, &full_bar[s], ck, l, bb, cmask);
         }
       }
       CDS_TRACE(8, clock64());
@@ -198,7 +209,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
                              (uint32_t)(c > n_main || k > 0));
           }
         }
-        ptx::umma_commit(&empty_bar[s]);
+        if (cs > 1) ptx::umma_commit_mc(&empty_bar[s], cmask); else ptx::umma_commit(&empty_bar[s]);
       }
       ptx::umma_commit(&tmem_full_bar);
     }
@@ -355,6 +366,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
   }
 
   __syncthreads();
+  if (cs > 1) ptx::cluster_sync();                    // no CTA retires while a peer may still multicast into it / signal its barriers
   if (warp == kPsWarpMma) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -456,6 +468,9 @@ inline bool conv_ps_prepare(const cds_conv_op& c, ConvPsLaunch* out) {
       p.out_tma = 1;
   }
   L.grid = dim3((unsigned)(((c.batch + 127) / 128) * p.n_tiles));
+  // column-tile CTAs of a trajectory tile are consecutive blocks: one cluster per trajectory tile.  Opt-in (CDS_MULTICAST=1):
+  // measured slower than unicast on B200 (see conv_tc_prepare)
+  { const char* mc = getenv("CDS_MULTICAST"); p.cluster = (p.n_tiles == 4 && kPsPositions % 4 == 0 && mc && mc[0] == '1') ? 4 : 1; }
   return true;
 }
 
@@ -479,10 +494,15 @@ cudaError_t conv_ps_launch_t(const ConvPsLaunch& L, const int* iter_ptr, cudaStr
   prm.trace = conv_tc_trace_hook((int)L.grid.x);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = L.grid; cfg.blockDim = dim3(kPsThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+  if (prm.cluster > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)prm.cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, conv_ps_kernel<kPsKC, N, kPsPositions, HAS_RES, TF32>, prm, iter_ptr);
 }
 template <int N, bool HAS_RES, bool TF32>

@@ -44,6 +44,12 @@ struct ConvTcParams {
   // x 16 columns, staged in shared memory (SWIZZLE_64B for 4-byte / SWIZZLE_32B for 2-byte elements).  Valid when out_tma != 0.
   CUtensorMap tm_out;
   int out_tma;
+  // SPLIT > 1 kernels: the SPLIT column-tile CTAs of a row tile form a thread-block cluster (cluster = SPLIT, else 1) and share
+  // the activation tiles: CTA r fetches trajectories [r*T/SPLIT, (r+1)*T/SPLIT) of the tile (tm_a_mc / tm_a2_mc: the same
+  // tensors with that smaller box) and MULTICASTS them into every CTA's stage -- the A bytes cross the L2 -> SM fabric once per
+  // row tile instead of once per column tile.
+  CUtensorMap tm_a_mc, tm_a2_mc;
+  int cluster;
   int batch, L, log2L, C_out, taps, pad;   // L = output positions per tile-trajectory; C_out = channels per phase
   int num_tiles;                  // ceil(batch*L / 128); CTAs are persistent and stride over the tiles
   int phases;                     // 2: columns [0,C_out) / [C_out,2C_out) are output positions 2l / 2l+1 (transposed conv)
@@ -278,8 +284,12 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   const int n_kb_main = p.taps * p.kchunks;
   const int n_kb = n_kb_main + (HAS_RES ? p.kchunks2 : 0);
 
+  const int cs = SPLIT > 1 ? p.cluster : 1;           // cluster size (1 = no multicast)
+  const uint32_t crank = cs > 1 ? ptx::cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    // a stage is free again when the MMAs of EVERY CTA of the cluster have consumed it (peers multicast into it)
+    for (int s = 0; s < kTcStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], (uint32_t)cs); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], kTcEpiThreads / 32); }
     ptx::fence_barrier_init();
   }
@@ -288,10 +298,12 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     ptx::prefetch_tensormap(&p.tm_b);
     if (HAS_RES) { ptx::prefetch_tensormap(&p.tm_a2); ptx::prefetch_tensormap(&p.tm_b2); }
     if (p.out_tma) ptx::prefetch_tensormap(&p.tm_out);
+    if (cs > 1) { ptx::prefetch_tensormap(&p.tm_a_mc); if (HAS_RES) ptx::prefetch_tensormap(&p.tm_a2_mc); }
   }
   if (warp == 9) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (cs > 1) ptx::cluster_sync();                    // every CTA's barriers exist before a peer can signal them
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_holder;
   if (threadIdx.x == 0) CDS_TRACE(2, clock64());
@@ -339,11 +351,15 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         uint8_t* sb = sa + Cfg::kABytes;
         if (!HAS_RES || kb < n_kb_main) {
           const int tap = kb / p.kchunks, ck = kb - tap * p.kchunks;
-          ptx::tma_load_3d(sa, &p.tm_a, &full_bar[s], ck * KE, tap - p.pad, a_b0);
+          if (cs == 1) ptx::tma_load_3d(sa, &p.tm_a, &full_bar[s], ck * KE, tap - p.pad, a_b0);
+          else ptx::tma_load_3d_mc(sa + crank * (Cfg::kABytes / SPLIT), &p.tm_a_mc, &full_bar[s], ck * KE, tap - p.pad,
+                                   a_b0 + (int)crank * (T / SPLIT), cmask);
           if (!w_done) ptx::tma_load_2d(sb, &p.tm_b, &full_bar[s], ck * KE, tap * p.C_out * p.phases + n_off);
         } else {
           const int ck = kb - n_kb_main;
-          ptx::tma_load_3d(sa, &p.tm_a2, &full_bar[s], ck * KE, 0, r_b0);
+          if (cs == 1) ptx::tma_load_3d(sa, &p.tm_a2, &full_bar[s], ck * KE, 0, r_b0);
+          else ptx::tma_load_3d_mc(sa + crank * (Cfg::kABytes / SPLIT), &p.tm_a2_mc, &full_bar[s], ck * KE, 0,
+                                   r_b0 + (int)crank * (T / SPLIT), cmask);
           if (!w_done) ptx::tma_load_2d(sb, &p.tm_b2, &full_bar[s], ck * KE, n_off);
         }
       }
@@ -378,7 +394,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
           // advancing 16 bf16 / 8 tf32 (32 B) along K inside the swizzle span = +2 in the (addr >> 4) field
           ptx::umma<TF32>(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (first_of_acc && k == 0) ? 0u : 1u);
         }
-        ptx::umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
+        // frees the smem slot once these MMAs have read it (in every CTA of the cluster when the slot is filled by multicast)
+        if (cs > 1) ptx::umma_commit_mc(&empty_bar[s], cmask); else ptx::umma_commit(&empty_bar[s]);
       }
       ptx::umma_commit(&tmem_full_bar[buf]);      // this tile's accumulators complete
       }
@@ -590,7 +607,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       const int batch_ = p.batch, phases_ = p.phases, C_out_ = p.C_out;
       const int64_t out_bs = p.out_bstride, out_ls = p.out_lstride;
       const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
-      const bool use_tma = p.out_tma != 0 && phases_ == 1;           // (two-phase transposed convs interleave positions: direct stores)
+      // out_tma: 1 = {C, L, batch} view (one phase), 2 = {C, phase, L, batch} view of a two-phase transposed conv's output
+      const int use_tma = p.out_tma;
       uint8_t* const stg = &s_stage[warp][0];
       const int traj_q = (32 * q) >> p.log2L;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -650,7 +668,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              ptx::tma_store_3d(&p.tm_out, stg, c0, 0, (tile / nct) * T_ + traj_q);
+              if (use_tma == 2) ptx::tma_store_4d(&p.tm_out, stg, c0, phase, 0, (tile / nct) * T_ + traj_q);
+              else ptx::tma_store_3d(&p.tm_out, stg, c0, 0, (tile / nct) * T_ + traj_q);
               ptx::bulk_commit_group();
             }
           } else if (valid) {
@@ -944,6 +963,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   // the CTA retires
   if (warp < kTcEpiThreads / 32 && lane == 0) ptx::bulk_wait_group<0>();
   __syncthreads();
+  if (cs > 1) ptx::cluster_sync();                    // no CTA retires while a peer may still multicast into it / signal its barriers
   if (warp == 9) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -1109,12 +1129,27 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
     uint32_t box[2] = {(uint32_t)ke, (uint32_t)L.n};
     if (!encode_act_map(&p.tm_b, c.w, 2, dims, str, box, kc, tf32)) return false;
   }
+  // Opt-in (CDS_MULTICAST=1).  Measured on B200 (cfg2, batch 4096): 636 vs 615 us per iteration in TF32, 474 vs 452 in bf16 --
+  // what binds the main loop is the bytes INGESTED into each SM's shared memory (TMA fill + MMA operand reads, ~128 B/clk/SM),
+  // which multicast does not reduce, while the lock-step of the cluster costs a little.
+  { const char* mc = getenv("CDS_MULTICAST"); p.cluster = (L.split > 1 && T % L.split == 0 && mc && mc[0] == '1') ? L.split : 1; }
+  if (p.cluster > 1) {      // the activation tensor again, with the box of ONE cluster CTA's share of the tile's trajectories
+    uint64_t dims[3] = {(uint64_t)c.C_in, (uint64_t)c.L_in, in_b};
+    uint64_t str[2] = {(uint64_t)c.in_lstride, (uint64_t)c.in_bstride};
+    uint32_t box[3] = {(uint32_t)ke, (uint32_t)(Lp * c.stride), (uint32_t)(T / L.split)};
+    uint32_t es[3] = {1u, (uint32_t)c.stride, 1u};
+    if (!encode_act_map(&p.tm_a_mc, c.in, 3, dims, str, box, kc, tf32, es)) return false;
+  }
   if (L.has_res) {
     const uint64_t r_b = c.res_batch_mod > 0 ? (uint64_t)c.res_batch_mod : (uint64_t)c.batch;
     uint64_t dims[3] = {(uint64_t)c.res_C, (uint64_t)Lp, r_b};
     uint64_t str[2] = {(uint64_t)c.res_in_lstride, (uint64_t)c.res_in_bstride};
     uint32_t box[3] = {(uint32_t)ke, (uint32_t)Lp, (uint32_t)T};
     if (!encode_act_map(&p.tm_a2, c.res_in, 3, dims, str, box, kc, tf32)) return false;
+    if (p.cluster > 1) {
+      uint32_t boxp[3] = {(uint32_t)ke, (uint32_t)Lp, (uint32_t)(T / L.split)};
+      if (!encode_act_map(&p.tm_a2_mc, c.res_in, 3, dims, str, boxp, kc, tf32)) return false;
+    }
     uint64_t d2[2] = {(uint64_t)c.res_C, (uint64_t)c.C_out};
     uint64_t s2[1] = {(uint64_t)c.res_C};
     uint32_t b2[2] = {(uint32_t)ke, (uint32_t)L.n};
@@ -1124,19 +1159,32 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
     // output as a TMA-store target (the fast epilogue lanes stage 32 rows x 16 columns per warp and bulk-store them): needs whole
     // 16-column groups, 16-byte aligned rows, one phase, at most 32 positions per trajectory
     const int oes = c.out_dtype == CDS_BF16 ? 2 : 4;
-    const bool ok = c.phases == 1 && c.C_out % 16 == 0 && Lp <= 32 && ((uintptr_t)c.out % 16) == 0 &&
+    const bool ok = (c.phases == 1 || c.phases == 2) && c.C_out % 16 == 0 && Lp <= 32 && ((uintptr_t)c.out % 16) == 0 &&
                     ((int64_t)c.out_lstride * oes) % 16 == 0 && ((int64_t)c.out_bstride * oes) % 16 == 0 && !getenv("CDS_NO_TMA_STORE");
     p.out_tma = 0;
     if (ok) {
       PFN_encodeTiled enc = get_encode_tiled();
-      cuuint64_t gdim[3] = {(cuuint64_t)c.C_out, (cuuint64_t)Lp, (cuuint64_t)c.batch};
-      cuuint64_t gstr[2] = {(cuuint64_t)c.out_lstride * oes, (cuuint64_t)c.out_bstride * oes};
-      cuuint32_t bx[3] = {16u, (cuuint32_t)Lp, (cuuint32_t)(32 / Lp)};
-      cuuint32_t es[3] = {1u, 1u, 1u};
-      if (enc && enc(&p.tm_out, oes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c.out, gdim, gstr, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, oes == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-        p.out_tma = 1;
+      const CUtensorMapDataType dt = oes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+      const CUtensorMapSwizzle sw = oes == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
+      if (c.phases == 1) {
+        cuuint64_t gdim[3] = {(cuuint64_t)c.C_out, (cuuint64_t)Lp, (cuuint64_t)c.batch};
+        cuuint64_t gstr[2] = {(cuuint64_t)c.out_lstride * oes, (cuuint64_t)c.out_bstride * oes};
+        cuuint32_t bx[3] = {16u, (cuuint32_t)Lp, (cuuint32_t)(32 / Lp)};
+        cuuint32_t es[3] = {1u, 1u, 1u};
+        if (enc && enc(&p.tm_out, dt, 3, c.out, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+          p.out_tma = 1;
+      } else {
+        // two-phase transposed conv: tile row (trajectory, l) writes output position 2l + phase -> the output seen as
+        // {C, phase, L, batch} with strides {lstride, 2 lstride, bstride}; a store box covers ONE phase of its 32 rows
+        cuuint64_t gdim[4] = {(cuuint64_t)c.C_out, 2u, (cuuint64_t)Lp, (cuuint64_t)c.batch};
+        cuuint64_t gstr[3] = {(cuuint64_t)c.out_lstride * oes, (cuuint64_t)c.out_lstride * 2 * oes, (cuuint64_t)c.out_bstride * oes};
+        cuuint32_t bx[4] = {16u, 1u, (cuuint32_t)Lp, (cuuint32_t)(32 / Lp)};
+        cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+        if (enc && enc(&p.tm_out, dt, 4, c.out, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+          p.out_tma = 2;
+      }
     }
   }
   p.batch = c.batch; p.L = Lp; p.log2L = ilog2(Lp); p.C_out = c.C_out; p.taps = c.taps; p.pad = c.pad;
@@ -1198,14 +1246,21 @@ cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStr
   unsigned cap = (unsigned)resident;
   if (L.max_ctas_per_sm > 0 && (unsigned)(L.max_ctas_per_sm * sm_count) < cap) cap = (unsigned)(L.max_ctas_per_sm * sm_count);
   dim3 grid(L.grid.x < cap ? L.grid.x : cap);
+  const unsigned cl = L.prm.cluster > 1 ? (unsigned)L.prm.cluster : 1u;
+  if (cl > 1) grid.x -= grid.x % cl;                 // whole clusters: the CTAs of a cluster walk the same row tiles in lockstep
   ConvTcParams prm = L.prm;
   prm.trace = conv_tc_trace_hook((int)grid.x);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+  if (cl > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = cl; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, conv_tc_kernel<KC, N, HAS_RES, SPLIT, TF32>, prm, iter_ptr);
 }
 // touch the kernel once (module load) so that nothing lazy happens inside a stream capture

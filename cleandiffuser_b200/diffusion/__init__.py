@@ -2,4 +2,5 @@ from .basic import DiffusionModel
 from .sde import BaseDiffusionSDE, DiscreteDiffusionSDE, ContinuousDiffusionSDE
 from .consistency import ContinuousConsistencyModel
 from .edm import ContinuousEDM
+from .legacy import DDPM
 from .solvers import SUPPORTED_SOLVERS

@@ -350,8 +350,11 @@ def _cond_rows(cfg_mode, cond_emb):
 
 
 def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_values, alphas, sigmas, hs, stds,
-               cond_emb, w_cfg, n_samples, guide=None):
-    """``guide``: optional host callback ``guide(n, i, x_t, pred)`` (n = iteration, i = its loop index) run between the denoiser
+               cond_emb, w_cfg, n_samples, guide=None, table=None):
+    """``table``: optional ready-made ``(coefficient rows [n_iters, ROW], number of noise slots, int64/float32 time per iteration)``
+    for samplers that are "the same update kernel with another coefficient table" (the legacy DDPM class, RectifiedFlow's Euler
+    step): ``solver`` / ``alphas`` / ``sigmas`` / ``hs`` / ``stds`` / ``step_values`` are then unused.
+    ``guide``: optional host callback ``guide(n, i, x_t, pred)`` (n = iteration, i = its loop index) run between the denoiser
     and the update of every iteration (classifier guidance); the loop then runs step by step instead of as a replayed graph."""
     if _backend() == "torch":
         return None
@@ -371,11 +374,18 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
 
     # ---- per-iteration scalars (host, reference op order); identical requests reuse the table (building it costs ~10 ms
     # of Python scalar arithmetic for 100 steps -- more than a tenth of a whole cfg2 sample() on the engine) ---------------
-    alphas_c, sigmas_c, hs_c, stds_c = (z.detach().float().cpu() for z in (alphas, sigmas, hs, stds))
-    t_cpu = step_values.detach().cpu()
-    sched_key = (solver, sample_steps, tuple(order), alphas_c.numpy().tobytes(), sigmas_c.numpy().tobytes(),
-                 hs_c.numpy().tobytes(), stds_c.numpy().tobytes(), t_cpu.numpy().tobytes())
-    cached = agent._engine_tables.get(sched_key) if hasattr(agent, "_engine_tables") else None
+    if table is not None:
+        rows_given, slots_given, t_given = table
+        t_cpu = t_given.detach().cpu()
+        order = list(range(rows_given.shape[0]))
+        sched_key = (solver, rows_given.numpy().tobytes(), t_cpu.numpy().tobytes())
+        cached = (rows_given, int(slots_given))
+    else:
+        alphas_c, sigmas_c, hs_c, stds_c = (z.detach().float().cpu() for z in (alphas, sigmas, hs, stds))
+        t_cpu = step_values.detach().cpu()
+        sched_key = (solver, sample_steps, tuple(order), alphas_c.numpy().tobytes(), sigmas_c.numpy().tobytes(),
+                     hs_c.numpy().tobytes(), stds_c.numpy().tobytes(), t_cpu.numpy().tobytes())
+        cached = agent._engine_tables.get(sched_key) if hasattr(agent, "_engine_tables") else None
     if cached is None:
         table = S.coeff_table(solver, order, sample_steps, alphas_c, sigmas_c, hs_c, stds_c, t_cpu.double())
         n_slots = 0
@@ -390,7 +400,7 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
         agent._engine_tables[sched_key] = (table, n_slots)
     else:
         table, n_slots = cached
-    keep_history = S.solver_keeps_history(solver)
+    keep_history = table is None and S.solver_keeps_history(solver)
     has_mask = isinstance(agent.fix_mask, torch.Tensor)
     has_min, has_max = agent.x_min is not None, agent.x_max is not None
     math = _math_mode()

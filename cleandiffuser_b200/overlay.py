@@ -26,6 +26,7 @@ _PATCHED: List[Tuple[object, str, object]] = []      # (module, attribute, origi
 _TARGETS: Dict[str, Tuple[str, ...]] = {
     "cleandiffuser.diffusion": ("DiscreteDiffusionSDE", "ContinuousDiffusionSDE", "ContinuousConsistencyModel", "ContinuousEDM"),
     "cleandiffuser.diffusion.newedm": ("ContinuousEDM",),
+    "cleandiffuser.diffusion.ddpm": ("DDPM",),
     "cleandiffuser.diffusion.diffusionsde": ("DiscreteDiffusionSDE", "ContinuousDiffusionSDE"),
     "cleandiffuser.diffusion.consistency_model": ("ContinuousConsistencyModel",),
 }

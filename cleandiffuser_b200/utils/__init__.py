@@ -1,6 +1,6 @@
 from .schedules import *  # noqa: F401,F403
 from .schedules import (SUPPORTED_NOISE_SCHEDULES, SUPPORTED_DISCRETIZATIONS,
-                        SUPPORTED_SAMPLING_STEP_SCHEDULE)
+                        SUPPORTED_SAMPLING_STEP_SCHEDULE, cosine_beta_schedule, linear_beta_schedule)
 from .embeddings import (PositionalEmbedding, UntrainablePositionalEmbedding, SinusoidalEmbedding,
                          FourierEmbedding, UntrainableFourierEmbedding, SUPPORTED_TIMESTEP_EMBEDDING)
 from .blocks import at_least_ndim, to_tensor, count_parameters, Mlp, GroupNorm1d

@@ -284,3 +284,33 @@ def sample_edm(net, prior, tape, *, steps, solver="euler", temperature=1.0, fix_
     if clip:
         x = x.clip(x_min, x_max)
     return x
+
+
+# ----------------------------------------------------------------------------- legacy DDPM (beta-schedule parameterisation)
+def sample_legacy_ddpm(net, prior, tape, *, T, beta, predict_noise=True, temperature=1.0, fix_mask=0., cond_emb=None, w_cfg=0.0,
+                       x_min=None, x_max=None, extra_steps=0):
+    """DDPM.sample / DDPM.sample_x, ddpm.py:168-253, :256-378 (no classifier); ``beta``: the fp32 beta schedule tensor [T]."""
+    alpha = 1 - beta
+    bar = torch.cumprod(alpha.clone(), 0)
+    n = prior.shape[0]
+    x = tape(prior) * temperature
+    x = x * (1. - fix_mask) + prior * fix_mask
+    for k, t in enumerate(list(range(T - 1, -1, -1)) + [0] * extra_steps):
+        ab = bar[t]
+        ab_prev = bar[t - 1] if t > 0 else torch.tensor(1.0)
+        a, b = alpha[t], beta[t]
+        pred = guided_prediction(net, x, torch.full((n,), t, dtype=torch.long), cond_emb, w_cfg)
+        if predict_noise:
+            if x_min is not None or x_max is not None:
+                hi = (x - ab.sqrt() * x_min) / (1 - ab).sqrt() if x_min is not None else None
+                lo = (x - ab.sqrt() * x_max) / (1 - ab).sqrt() if x_max is not None else None
+                pred = pred.clip(lo, hi)
+            x = 1 / a.sqrt() * (x - b / (1 - ab).sqrt() * pred)
+        else:
+            if x_min is not None or x_max is not None:
+                pred = pred.clip(x_min, x_max)
+            x = 1 / (1 - ab) * (a.sqrt() * (1 - ab_prev) * x + b * ab_prev.sqrt() * pred)
+        if t != 0 and k < T:
+            x = x + (b * (1 - ab_prev) / (1 - ab)).sqrt() * tape(x)
+        x = x * (1. - fix_mask) + prior * fix_mask
+    return x

@@ -118,6 +118,20 @@ def edm_cases():
     return out
 
 
+def legacy_cases():
+    """Legacy DDPM class (ddpm.py): ancestral sampling and Diffusion-X (sample_x), both parameterisations."""
+    return {
+        "ddpm_eps_mask_clip": dict(net="janner_tiny", predict_noise=True, T=10, fix_mask="first_row", clip=True, w_cfg=1.0, cond="emb",
+                                   temperature=0.5, extra=0, beta_schedule="cosine"),
+        "ddpm_x0_linear": dict(net="janner_tiny", predict_noise=False, T=8, fix_mask=None, clip=True, w_cfg=0.0, cond=None,
+                               temperature=1.0, extra=0, beta_schedule="linear"),
+        "ddpm_x_eps_extra": dict(net="dql_tiny", predict_noise=True, T=6, fix_mask=None, clip=True, w_cfg=1.0, cond="obs",
+                                 temperature=1.0, extra=3, beta_schedule="cosine"),
+        "ddpm_x_x0_cfg2branch": dict(net="dql_tiny", predict_noise=False, T=6, fix_mask=None, clip=False, w_cfg=1.6, cond="obs",
+                                     temperature=1.0, extra=2, beta_schedule="cosine"),
+    }
+
+
 def guided_cases():
     """Classifier-guided sampling (diffusionsde.py:153-173, :597-606) with cleandiffuser_b200.testing.ToyClassifier attached:
     the Diffuser pattern (x0-prediction, DDPM, fix_mask, w_cg = 0.3) and eps-prediction with a condition branch."""

@@ -165,6 +165,31 @@ def gen_guided():
     print("guided.npz", len(out))
 
 
+def gen_legacy():
+    from cleandiffuser.diffusion.ddpm import DDPM
+    out = {}
+    for name, spec in cases.legacy_cases().items():
+        net, _ = build_net(cases.SAMPLER_NETS[spec["net"]])
+        inp = cases.sampler_inputs(spec)
+        agent = DDPM(net, build_condition(spec), fix_mask=inp["fix_mask"], x_max=inp["x_max"], x_min=inp["x_min"],
+                     predict_noise=spec["predict_noise"], diffusion_steps=spec["T"], beta_schedule=spec["beta_schedule"], device="cpu")
+        agent.model_ema.eval()
+        kw = dict(n_samples=cases.SAMPLER_BATCH, sample_steps=spec["T"], use_ema=True, temperature=spec["temperature"],
+                  condition_cfg=inp["cond"], w_cfg=spec["w_cfg"])
+        tape = NoiseTape()
+        with tape.active(), torch.no_grad():
+            if spec["extra"]:
+                x0, log = agent.sample_x(inp["prior"], extra_sample_steps=spec["extra"], **kw)
+            else:
+                x0, log = agent.sample(inp["prior"], **kw)
+        out[name + "/x0"] = x0.numpy()
+        for j, z in enumerate(tape.draws):
+            out[f"{name}/z{j}"] = z.numpy()
+        out[name + "/n_draws"] = np.array(len(tape.draws))
+    np.savez_compressed(os.path.join(HERE, "legacy.npz"), **out)
+    print("legacy.npz", len(out))
+
+
 def gen_edm():
     out = {}
     for name, spec in cases.edm_cases().items():
@@ -192,6 +217,6 @@ def gen_edm():
 if __name__ == "__main__":
     torch.set_num_threads(1)
     only = sys.argv[1:]
-    for fn in (gen_tables, gen_nets, gen_samplers, gen_consistency, gen_edm, gen_guided):
+    for fn in (gen_tables, gen_nets, gen_samplers, gen_consistency, gen_edm, gen_guided, gen_legacy):
         if not only or fn.__name__[4:] in only:
             fn()
