@@ -3,4 +3,5 @@ from .sde import BaseDiffusionSDE, DiscreteDiffusionSDE, ContinuousDiffusionSDE
 from .consistency import ContinuousConsistencyModel
 from .edm import ContinuousEDM
 from .legacy import DDPM
+from .rectifiedflow import DiscreteRectifiedFlow, ContinuousRectifiedFlow
 from .solvers import SUPPORTED_SOLVERS

@@ -350,10 +350,12 @@ def _cond_rows(cfg_mode, cond_emb):
 
 
 def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_values, alphas, sigmas, hs, stds,
-               cond_emb, w_cfg, n_samples, guide=None, table=None):
+               cond_emb, w_cfg, n_samples, guide=None, table=None, clip_in_loop=True, predict_noise=None):
     """``table``: optional ready-made ``(coefficient rows [n_iters, ROW], number of noise slots, int64/float32 time per iteration)``
     for samplers that are "the same update kernel with another coefficient table" (the legacy DDPM class, RectifiedFlow's Euler
     step): ``solver`` / ``alphas`` / ``sigmas`` / ``hs`` / ``stds`` / ``step_values`` are then unused.
+    ``clip_in_loop=False``: the sampler clips only its final sample (RectifiedFlow); ``predict_noise``: overrides
+    ``agent.predict_noise`` (classes without that attribute).
     ``guide``: optional host callback ``guide(n, i, x_t, pred)`` (n = iteration, i = its loop index) run between the denoiser
     and the update of every iteration (classifier guidance); the loop then runs step by step instead of as a replayed graph."""
     if _backend() == "torch":
@@ -402,7 +404,8 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
         table, n_slots = cached
     keep_history = table is None and S.solver_keeps_history(solver)
     has_mask = isinstance(agent.fix_mask, torch.Tensor)
-    has_min, has_max = agent.x_min is not None, agent.x_max is not None
+    has_min, has_max = (agent.x_min is not None and clip_in_loop), (agent.x_max is not None and clip_in_loop)
+    pn = bool(agent.predict_noise) if predict_noise is None else bool(predict_noise)
     math = _math_mode()
     row_elems = 1
     for s_ in x_shape:
@@ -410,12 +413,12 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
     # noise tape: all draws of the loop up front when they fit the budget, else as many slots as fit (the loop then runs in
     # chunks with the tape refilled in between -- O(budget) memory instead of O(sample_steps x batch x row))
     tape_slots = min(n_slots, max(1, _tape_budget_bytes() // (4 * batch * row_elems))) if n_slots > 0 else 0
-    key = ("sde", id(net), batch, x_shape, len(order), tape_slots, cfg_mode, bool(agent.predict_noise), has_mask,
+    key = ("sde", id(net), batch, x_shape, len(order), tape_slots, cfg_mode, pn, has_mask,
            has_min, has_max, keep_history, math, float(w_cfg) if cfg_mode == 2 else 0.0)
 
     def factory():
         plan = SamplerPlan(device, net, batch, x_shape, len(order), tape_slots, cfg_mode=cfg_mode,
-                           predict_noise=agent.predict_noise, has_mask=has_mask, has_min=has_min, has_max=has_max,
+                           predict_noise=pn, has_mask=has_mask, has_min=has_min, has_max=has_max,
                            keep_history=keep_history, math=math)
         plan.build(w_cfg)
         return plan

@@ -24,9 +24,11 @@ _PATCHED: List[Tuple[object, str, object]] = []      # (module, attribute, origi
 
 # reference module -> names rebound there
 _TARGETS: Dict[str, Tuple[str, ...]] = {
-    "cleandiffuser.diffusion": ("DiscreteDiffusionSDE", "ContinuousDiffusionSDE", "ContinuousConsistencyModel", "ContinuousEDM"),
+    "cleandiffuser.diffusion": ("DiscreteDiffusionSDE", "ContinuousDiffusionSDE", "ContinuousConsistencyModel", "ContinuousEDM",
+                                "DiscreteRectifiedFlow", "ContinuousRectifiedFlow"),
     "cleandiffuser.diffusion.newedm": ("ContinuousEDM",),
     "cleandiffuser.diffusion.ddpm": ("DDPM",),
+    "cleandiffuser.diffusion.rectifiedflow": ("DiscreteRectifiedFlow", "ContinuousRectifiedFlow"),
     "cleandiffuser.diffusion.diffusionsde": ("DiscreteDiffusionSDE", "ContinuousDiffusionSDE"),
     "cleandiffuser.diffusion.consistency_model": ("ContinuousConsistencyModel",),
 }

@@ -132,6 +132,20 @@ def legacy_cases():
     }
 
 
+def rf_cases():
+    """Rectified flow (rectifiedflow.py): discrete and continuous time, CFG regimes, Diffusion-X repeats, warm start, final clip."""
+    return {
+        "rf_disc_plain": dict(kind="discrete", net="janner_tiny", T=20, steps=5, fix_mask="first_row", clip=False, w_cfg=0.0, cond=None,
+                              temperature=0.5),
+        "rf_disc_cond_clip_dx": dict(kind="discrete", net="dql_tiny", T=30, steps=4, fix_mask=None, clip=True, w_cfg=1.0, cond="obs",
+                                     temperature=1.0, diffusion_x=2, step_schedule="quad"),
+        "rf_cont_cfg2branch": dict(kind="continuous", net="janner_tiny", steps=6, fix_mask="first_row", clip=True, w_cfg=2.0, cond="emb",
+                                   temperature=1.0),
+        "rf_cont_warm": dict(kind="continuous", net="janner_tiny", steps=4, fix_mask=None, clip=False, w_cfg=0.0, cond=None,
+                             temperature=1.0, warm=0.4),
+    }
+
+
 def guided_cases():
     """Classifier-guided sampling (diffusionsde.py:153-173, :597-606) with cleandiffuser_b200.testing.ToyClassifier attached:
     the Diffuser pattern (x0-prediction, DDPM, fix_mask, w_cg = 0.3) and eps-prediction with a condition branch."""

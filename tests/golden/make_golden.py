@@ -190,6 +190,34 @@ def gen_legacy():
     print("legacy.npz", len(out))
 
 
+def gen_rf():
+    from cleandiffuser.diffusion.rectifiedflow import ContinuousRectifiedFlow, DiscreteRectifiedFlow
+    out = {}
+    for name, spec in cases.rf_cases().items():
+        net, _ = build_net(cases.SAMPLER_NETS[spec["net"]])
+        inp = cases.sampler_inputs(spec)
+        common = dict(nn_condition=build_condition(spec), fix_mask=inp["fix_mask"], x_max=inp["x_max"], x_min=inp["x_min"], device="cpu")
+        if spec["kind"] == "discrete":
+            agent, sched = DiscreteRectifiedFlow(net, diffusion_steps=spec["T"], **common), spec.get("step_schedule", "uniform")
+        else:
+            agent, sched = ContinuousRectifiedFlow(net, **common), spec.get("step_schedule", "uniform_continuous")
+        agent.model_ema.eval()
+        kw = dict(n_samples=cases.SAMPLER_BATCH, sample_steps=spec["steps"], sample_step_schedule=sched, use_ema=True,
+                  temperature=spec["temperature"], condition_cfg=inp["cond"], w_cfg=spec["w_cfg"],
+                  diffusion_x_sampling_steps=spec.get("diffusion_x", 0))
+        if inp["warm"] is not None:
+            kw.update(warm_start_reference=inp["warm"], warm_start_forward_level=spec["warm"])
+        tape = NoiseTape()
+        with tape.active(), torch.no_grad():
+            x0, log = agent.sample(inp["prior"], **kw)
+        out[name + "/x0"] = x0.numpy()
+        for j, z in enumerate(tape.draws):
+            out[f"{name}/z{j}"] = z.numpy()
+        out[name + "/n_draws"] = np.array(len(tape.draws))
+    np.savez_compressed(os.path.join(HERE, "rf.npz"), **out)
+    print("rf.npz", len(out))
+
+
 def gen_edm():
     out = {}
     for name, spec in cases.edm_cases().items():
@@ -217,6 +245,6 @@ def gen_edm():
 if __name__ == "__main__":
     torch.set_num_threads(1)
     only = sys.argv[1:]
-    for fn in (gen_tables, gen_nets, gen_samplers, gen_consistency, gen_edm, gen_guided, gen_legacy):
+    for fn in (gen_tables, gen_nets, gen_samplers, gen_consistency, gen_edm, gen_guided, gen_legacy, gen_rf):
         if not only or fn.__name__[4:] in only:
             fn()
