@@ -597,10 +597,16 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     // DiT1d's QKV and GELU Linear layers).  Same idea as the fast lane: dispatch once, strength-reduced addressing, fixed dtype.
     const bool plain_ok = N >= 32 && !HAS_RES && !has_gn && film == 0 && !smp && !add_res && io_vec && p.res_batch_mod == 0 &&
                           (p.act == CDS_ACT_NONE || p.act == CDS_ACT_GELU_TANH);
-    auto plain_tiles = [&](auto act_tag, auto bf16_tag) {
+    // ... and its "gated" form: out = (acc + bias) * gate(trajectory, column) + residual -- DiT1d's attention out-projection and
+    // second MLP Linear (dit.py:33-36: x + gate * f(...)), fp32 residual stream, per-trajectory gate row
+    const bool gated_ok = N >= 32 && !HAS_RES && !has_gn && p.act == CDS_ACT_NONE && p.scale.sample && !p.scale.step && !has_shift &&
+                          !p.bias.sample && add_res && p.res_dtype != CDS_BF16 && p.out_dtype != CDS_BF16 && io_vec && p.phases == 1 &&
+                          p.res_batch_mod == 0 && p.out_tma == 1 && ((uintptr_t)p.scale.sample % 16 == 0) && (p.scale.sample_stride % 4 == 0);
+    auto plain_tiles = [&](auto act_tag, auto bf16_tag, auto gated_tag) {
       constexpr int ACT = decltype(act_tag)::value;
       constexpr int OUT_DT = decltype(bf16_tag)::value;            // cds_dtype of the output
       constexpr bool OUT_BF16 = OUT_DT == CDS_BF16;
+      constexpr bool GATED = decltype(gated_tag)::value;
       const int T_ = 128 >> p.log2L;
       const int tb = m >> p.log2L, l = m & (p.L - 1);
       const int nct = SPLIT > 1 ? SPLIT : p.n_col_tiles;
@@ -641,6 +647,24 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
             const float4 bb = b4[k];
             v[4 * k] = tc_act<ACT>(ACT, v[4 * k] + bb.x); v[4 * k + 1] = tc_act<ACT>(ACT, v[4 * k + 1] + bb.y);
             v[4 * k + 2] = tc_act<ACT>(ACT, v[4 * k + 2] + bb.z); v[4 * k + 3] = tc_act<ACT>(ACT, v[4 * k + 3] + bb.w);
+          }
+          if constexpr (GATED) {
+            const int bs = p.sample_div > 1 ? b / p.sample_div : b;
+            float4 g4[4], r4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { g4[k] = make_float4(0.f, 0.f, 0.f, 0.f); r4[k] = g4[k]; }
+            if (valid) {
+              const float4* gp = reinterpret_cast<const float4*>(p.scale.sample + (int64_t)bs * p.scale.sample_stride + c0);
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + (int64_t)b * p.res_bstride +
+                                                                 (int64_t)l * p.res_lstride + c0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { g4[k] = __ldg(gp + k); r4[k] = rp[k]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              v[4 * k] = fmaf(v[4 * k], g4[k].x, r4[k].x); v[4 * k + 1] = fmaf(v[4 * k + 1], g4[k].y, r4[k].y);
+              v[4 * k + 2] = fmaf(v[4 * k + 2], g4[k].z, r4[k].z); v[4 * k + 3] = fmaf(v[4 * k + 3], g4[k].w, r4[k].w);
+            }
           }
           if (use_tma) {
             // through the warp's staging rows and one bulk store (see s_stage); rows beyond the batch are clipped by the TMA unit
@@ -699,17 +723,20 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       }
     };
     if constexpr (N >= 32 && !HAS_RES) {
-      if (plain_ok && it == 0) {
-        using G = std::integral_constant<int, CDS_ACT_GELU_TANH>;
-        using Z = std::integral_constant<int, CDS_ACT_NONE>;
-        using DF = std::integral_constant<int, CDS_F32>;
-        using DB = std::integral_constant<int, CDS_BF16>;
-        using DT = std::integral_constant<int, CDS_TF32>;
-        const int od = p.out_dtype;
+      using G = std::integral_constant<int, CDS_ACT_GELU_TANH>;
+      using Z = std::integral_constant<int, CDS_ACT_NONE>;
+      using DF = std::integral_constant<int, CDS_F32>;
+      using DB = std::integral_constant<int, CDS_BF16>;
+      using DT = std::integral_constant<int, CDS_TF32>;
+      const int od = p.out_dtype;
+      if (gated_ok && it == 0) {
+        if (od == CDS_TF32) plain_tiles(Z{}, DT{}, std::true_type{}); else plain_tiles(Z{}, DF{}, std::true_type{});
+      } else if (plain_ok && it == 0) {
+        using NG = std::false_type;
         if (p.act == CDS_ACT_GELU_TANH) {
-          if (od == CDS_BF16) plain_tiles(G{}, DB{}); else if (od == CDS_TF32) plain_tiles(G{}, DT{}); else plain_tiles(G{}, DF{});
+          if (od == CDS_BF16) plain_tiles(G{}, DB{}, NG{}); else if (od == CDS_TF32) plain_tiles(G{}, DT{}, NG{}); else plain_tiles(G{}, DF{}, NG{});
         } else {
-          if (od == CDS_BF16) plain_tiles(Z{}, DB{}); else if (od == CDS_TF32) plain_tiles(Z{}, DT{}); else plain_tiles(Z{}, DF{});
+          if (od == CDS_BF16) plain_tiles(Z{}, DB{}, NG{}); else if (od == CDS_TF32) plain_tiles(Z{}, DT{}, NG{}); else plain_tiles(Z{}, DF{}, NG{});
         }
       }
     }

@@ -18,7 +18,7 @@ __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b)
 
 // per-iteration scalars of the update (one row of the coefficient table)
 struct UpdRow {
-  float alpha, sigma, k0, k1, k2, k3, k4;
+  float alpha, sigma, k0, k1, k2, k3, k4, xw, dw;
   int kind;
   const float* noise;          // this iteration's noise slot or NULL
 };
@@ -27,6 +27,7 @@ __device__ __forceinline__ UpdRow load_upd_row(const cds_update_op& p, int iter)
   UpdRow r;
   r.alpha = row[CDS_ROW_ALPHA]; r.sigma = row[CDS_ROW_SIGMA];
   r.k0 = row[CDS_ROW_K0]; r.k1 = row[CDS_ROW_K1]; r.k2 = row[CDS_ROW_K2]; r.k3 = row[CDS_ROW_K3]; r.k4 = row[CDS_ROW_K4];
+  r.xw = row[CDS_ROW_XW]; r.dw = row[CDS_ROW_DW];
   r.kind = (int)row[CDS_ROW_KIND];
   const int slot = (int)row[CDS_ROW_NOISE] - 1;
   const int64_t slot_stride = p.noise_slot_stride > 0 ? p.noise_slot_stride : (int64_t)p.batch * p.row;
@@ -49,7 +50,7 @@ __device__ __forceinline__ float solver_update_value(const cds_update_op& p, con
       if (p.x_min) d_theta = fmaxf(d_theta, p.x_min[e]);
       if (p.x_max) d_theta = fminf(d_theta, p.x_max[e]);
     }
-    const float slope = div_(sub_(x, d_theta), sigma);
+    const float slope = r.xw != 0.f ? sub_(mul_(r.xw, x), mul_(r.dw, d_theta)) : div_(sub_(x, d_theta), sigma);
     if (r.kind == CDS_UPD_EDM) {
       out = sub_(x, mul_(slope, r.k2));
       if (xhat_out) *xhat_out = x;
@@ -200,14 +201,69 @@ static __global__ void __launch_bounds__(256) cm_prep_kernel(const cds_prep_op p
 }
 
 // one warp per token row: LayerNorm (biased variance, no affine) then x*(1+scale)+shift.  8 B / element (6 with bf16 out).
-// Rows of up to 32*kLnRegs channels are held in registers: ONE pass over global memory (two-pass variance on the registers).
+// Rows of up to 128*kLnVec channels with C % 4 == 0 (DiT1d: 320) are held in registers as float4s: ONE pass over global memory
+// with 16-byte loads / stores (two-pass variance on the registers), two rows in flight per warp iteration; other shapes take
+// the scalar path.
 constexpr int kLnRegs = 16;
+constexpr int kLnVec = 4;               // float4s per lane: rows of up to 512 channels
+__device__ __forceinline__ void ln_store4(const cds_lnmod_op& p, int64_t off, float4 v) {
+  if (p.out_dtype == CDS_BF16) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = u;
+  } else {
+    if (p.out_dtype == CDS_TF32) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = v;
+  }
+}
 static __global__ void __launch_bounds__(256) ln_modulate_kernel(const cds_lnmod_op p) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t n_rows = (int64_t)p.batch * p.L;
-  const bool in_regs = p.C <= 32 * kLnRegs;
   const float inv_c = 1.f / (float)p.C;
+  const bool vec = (p.C % 4 == 0) && p.C <= 128 * kLnVec && ((uintptr_t)p.in % 16 == 0) && ((uintptr_t)p.out % 16 == 0) &&
+                   ((uintptr_t)p.shift % 16 == 0) && ((uintptr_t)p.scale % 16 == 0) && (p.mod_bstride % 4 == 0);
+  if (vec) {
+    const int n4 = p.C >> 2;                                  // float4s per row
+    const int64_t warp0 = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * warps_per_block;
+    for (int64_t r = warp0; r < n_rows; r += nwarps) {
+      const float4* src = reinterpret_cast<const float4*>(p.in + r * p.C);
+      const int b = (int)(r / p.L);
+      const float4* sh = reinterpret_cast<const float4*>(p.shift + (int64_t)b * p.mod_bstride);
+      const float4* sc = reinterpret_cast<const float4*>(p.scale + (int64_t)b * p.mod_bstride);
+      float4 x[kLnVec];
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < kLnVec; ++k) {
+        const int c4 = lane + 32 * k;
+        x[k] = c4 < n4 ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (x[k].x + x[k].y) + (x[k].z + x[k].w);
+      }
+      const float mean = warp_sum(s) * inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < kLnVec; ++k) {
+        if (lane + 32 * k < n4) {
+          const float d0 = x[k].x - mean, d1 = x[k].y - mean, d2 = x[k].z - mean, d3 = x[k].w - mean;
+          q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(q) * inv_c + p.eps);
+#pragma unroll
+      for (int k = 0; k < kLnVec; ++k) {
+        const int c4 = lane + 32 * k;
+        if (c4 < n4) {
+          const float4 a = __ldg(sc + c4), d = __ldg(sh + c4);
+          float4 o;
+          o.x = fmaf((x[k].x - mean) * rstd, 1.f + a.x, d.x); o.y = fmaf((x[k].y - mean) * rstd, 1.f + a.y, d.y);
+          o.z = fmaf((x[k].z - mean) * rstd, 1.f + a.z, d.z); o.w = fmaf((x[k].w - mean) * rstd, 1.f + a.w, d.w);
+          ln_store4(p, r * p.C + 4 * c4, o);
+        }
+      }
+    }
+    return;
+  }
+  const bool in_regs = p.C <= 32 * kLnRegs;
   for (int64_t r = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_rows;
        r += (int64_t)gridDim.x * warps_per_block) {
     const float* src = p.in + r * p.C;

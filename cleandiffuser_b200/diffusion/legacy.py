@@ -1,4 +1,6 @@
-"""The legacy ``DDPM`` class (beta-schedule parameterisation) that all ``dp_*`` / ``dbc_*`` pipelines construct.
+"""The legacy ``DDPM`` and ``EDM`` classes that the ``dp_*`` / ``dbc_*`` pipelines construct.
+
+``DDPM``: beta-schedule parameterisation.
 
 Same constructor / ``add_noise`` / ``loss`` / ``update`` / ``update_classifier`` / ``predict_function`` / ``sample`` /
 ``sample_x`` surface as cleandiffuser/diffusion/ddpm.py (:17-72 ctor, :81-112 training, :117-165 prediction, :168-253
@@ -47,7 +49,9 @@ class DDPM(DiffusionModel):
         self.beta = torch.tensor(beta, device=self.device, dtype=torch.float32)
         self.alpha = 1 - self.beta
         self.bar_alpha = torch.cumprod(self.alpha.clone(), 0)
-        self.x_max, self.x_min = x_max, x_min
+        # (the reference keeps the bounds where the caller put them and fails on a CUDA model with CPU bounds; moved here)
+        self.x_max = x_max.to(device) if isinstance(x_max, torch.Tensor) else x_max
+        self.x_min = x_min.to(device) if isinstance(x_min, torch.Tensor) else x_min
 
     @property
     def clip_pred(self):
@@ -218,3 +222,179 @@ class DDPM(DiffusionModel):
         (ddpm.py:256-378)."""
         return self._sample_impl(prior, n_samples, sample_steps, extra_sample_steps, use_ema, temperature, condition_cfg,
                                  mask_cfg, w_cfg, condition_cg, w_cg, requires_grad, preserve_history)
+
+
+# ======================================================================================================================
+class EDM(DiffusionModel):
+    """The legacy ``EDM`` class of the ``dbc_*`` pipelines (cleandiffuser/diffusion/edm.py: ``EDMArchetecture`` :15-355 with the
+    ``EDM`` parameterisation :358-428): Karras preconditioning, sigma(t) = t, scale 1, Euler / Heun over a DESCENDING sigma grid
+    ``sigma_0 = sigma_max ... sigma_N = sigma_min``, no clipping, slope ``x_weight x - D_weight D`` with both weights ``1/sigma``.
+
+    On the engine this is the ContinuousEDM program (``CDS_OP_PREP`` -> denoiser -> ``CDS_UPD_EDM`` / ``CDS_UPD_EDM_HEUN``) with
+    the slope weights passed explicitly (``CDS_ROW_XW`` / ``CDS_ROW_DW``) so that the arithmetic is the reference's."""
+
+    def __init__(self, nn_diffusion, nn_condition=None, fix_mask=None, loss_weight=None, classifier=None,
+                 grad_clip_norm: Optional[float] = None, diffusion_steps: int = 1000, ema_rate: float = 0.995,
+                 optim_params: Optional[dict] = None, sigma_data: float = 0.5, sigma_min: float = 0.002, sigma_max: float = 80.,
+                 rho: float = 7., P_mean: float = -1.2, P_std: float = 1.2, device: Union[torch.device, str] = "cpu"):
+        super().__init__(nn_diffusion, nn_condition, fix_mask, loss_weight, classifier, grad_clip_norm,
+                         diffusion_steps, ema_rate, optim_params, device)
+        self.sigma_data, self.sigma_min, self.sigma_max, self.rho = sigma_data, sigma_min, sigma_max, rho
+        self.P_mean, self.P_std = P_mean, P_std
+        self.sample_steps = None
+        self.sigma_s = self.t_s = self.scale_s = self.dot_sigma_s = self.dot_scale_s = None
+        self.x_weight_s = self.D_weight_s = None
+        self.x_min = self.x_max = None                      # (no clipping in this class; the engine looks the attributes up)
+
+    # ---- the EDM parameterisation (edm.py:400-428) ------------------------------------------------------------
+    def set_sample_steps(self, N: int):
+        self.sample_steps = N
+        ramp = torch.arange(N + 1, device=self.device) / N
+        self.sigma_s = (self.sigma_max ** (1 / self.rho) + ramp * (self.sigma_min ** (1 / self.rho) - self.sigma_max ** (1 / self.rho))) ** self.rho
+        self.t_s = self.sigma_s
+        self.scale_s = torch.ones_like(self.sigma_s)
+        self.dot_sigma_s = torch.ones_like(self.sigma_s)
+        self.dot_scale_s = torch.zeros_like(self.sigma_s)
+        self.x_weight_s = (self.dot_sigma_s / self.sigma_s + self.dot_scale_s / self.scale_s)
+        self.D_weight_s = self.dot_sigma_s / self.sigma_s * self.scale_s
+
+    def c_skip(self, sigma):
+        return self.sigma_data ** 2 / (self.sigma_data ** 2 + sigma ** 2)
+
+    def c_out(self, sigma):
+        return sigma * self.sigma_data / (self.sigma_data ** 2 + sigma ** 2).sqrt()
+
+    def c_in(self, sigma):
+        return 1 / (self.sigma_data ** 2 + sigma ** 2).sqrt()
+
+    def c_noise(self, sigma):
+        return 0.25 * sigma.log()
+
+    def loss_weighting(self, sigma):
+        return (self.sigma_data ** 2 + sigma ** 2) / ((sigma * self.sigma_data) ** 2)
+
+    def sample_noise_distribution(self, N):
+        return (torch.randn(N, device=self.device) * self.P_std + self.P_mean).exp()
+
+    def sample_scale_distribution(self, N):
+        return torch.ones(N, device=self.device)
+
+    def D(self, x, sigma, condition=None, use_ema=False):
+        net = (self.model_ema if use_ema else self.model)["diffusion"]
+        c_noise = at_least_ndim(self.c_noise(sigma).squeeze(), 1)
+        return self.c_skip(sigma) * x + self.c_out(sigma) * net(self.c_in(sigma) * x, c_noise, condition)
+
+    # ---- training (edm.py:88-116) -----------------------------------------------------------------------------
+    def loss(self, x0, condition=None):
+        sigma = at_least_ndim(self.sample_noise_distribution(x0.shape[0]), x0.dim())
+        eps = torch.randn_like(x0) * sigma * (1. - self.fix_mask)
+        cond = self.model["condition"](condition) if condition is not None else None
+        err = self.loss_weighting(sigma) * (self.D(x0 + eps, sigma, cond) - x0) ** 2
+        return (err * self.loss_weight).mean()
+
+    def update(self, x0, condition=None, **kwargs):
+        self.optimizer.zero_grad()
+        loss = self.loss(x0, condition)
+        loss.backward()
+        grad_norm = nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clip_norm) \
+            if self.grad_clip_norm else None
+        self.optimizer.step()
+        self._weights_epoch += 1
+        self.ema_update()
+        return {"loss": loss.item(), "grad_norm": grad_norm}
+
+    def update_classifier(self, x0, condition):
+        sigma = at_least_ndim(self.sample_noise_distribution(x0.shape[0]), x0.dim())
+        eps = torch.randn_like(x0) * sigma * (1. - self.fix_mask)
+        return self.classifier.update(x0 + eps, at_least_ndim(self.c_noise(sigma).squeeze(), 1), condition)
+
+    # ---- sampling (edm.py:118-355) ----------------------------------------------------------------------------
+    def dot_x(self, x, i, use_ema=False, condition_vec_cfg=None, w_cfg: float = 0.0, condition_vec_cg=None, w_cg: float = 1.0):
+        b = x.shape[0]
+        sigma = at_least_ndim(self.sigma_s[i].repeat(b), x.dim())
+        unscale = 1. / self.scale_s[i] * (1. - self.fix_mask) + self.fix_mask
+        with torch.no_grad():
+            if w_cfg != 0.0 and w_cfg != 1.0:
+                rep = [2] + [1] * (x.dim() - 1)
+                both = self.D((x * unscale).repeat(*rep), sigma.repeat(*rep),
+                              torch.cat([condition_vec_cfg, torch.zeros_like(condition_vec_cfg)], 0), use_ema)
+                D = w_cfg * both[:b] + (1. - w_cfg) * both[b:]
+            elif w_cfg == 0.0:
+                D = self.D(x * unscale, sigma, None, use_ema)
+            else:
+                D = self.D(x * unscale, sigma, condition_vec_cfg, use_ema)
+        log_p = None
+        if self.classifier is not None and w_cg != 0.0 and condition_vec_cg is not None:
+            log_p, grad = self.classifier.gradients(x * unscale, at_least_ndim(self.c_noise(sigma).squeeze(), 1), condition_vec_cg)
+            D = D + w_cg * self.scale_s[i] * (sigma ** 2) * grad
+        slope = self.x_weight_s[i] * x - self.D_weight_s[i] * D
+        return slope * (1. - self.fix_mask), {"log_p": log_p}
+
+    def _reimpose(self, x, prior):
+        return x if prior is None else x * (1. - self.fix_mask) + prior * self.fix_mask
+
+    def _sample_impl(self, prior, n_samples, sample_steps, extra_sample_steps, use_ema, solver, condition_cfg, mask_cfg, w_cfg,
+                     condition_cg, w_cg, preserve_history):
+        if sample_steps != self.sample_steps:
+            self.set_sample_steps(sample_steps)
+        N = self.sample_steps
+        model = self.model_ema if use_ema else self.model
+        cvec = model["condition"](condition_cfg, mask_cfg) if condition_cfg is not None else None
+        xt = torch.randn_like(prior, device=self.device) * self.sigma_s[0] * self.scale_s[0]
+        xt = xt * (1. - self.fix_mask) + prior * self.fix_mask
+        x_history = None
+        if preserve_history:
+            x_history = np.empty((n_samples, N + 1, *xt.shape))
+            x_history[:, 0] = xt.cpu().numpy()
+
+        heun_at = [solver == "heun" and i != N - 1 and bool(self.sigma_s[i + 1] > 0.005) for i in range(N)]
+        guided = self.classifier is not None and w_cg != 0.0 and condition_cg is not None
+        from ..engine import runtime
+        if not (preserve_history or guided) and runtime._device_ok(torch.device(self.device)):
+            sig, xw, dw = (z.detach().float().cpu() for z in (self.sigma_s, self.x_weight_s, self.D_weight_s))
+            evals = []
+            for i in list(range(N)) + [N - 1] * extra_sample_steps:
+                dt = sig[i] - sig[i + 1]
+                heun = heun_at[i]                    # (never at i = N-1, hence never in the extra steps, which repeat it)
+                evals.append((sig[i], S.UPD_EDM, dt, 1.0 if heun else 0.0, xw[i], dw[i]))
+                if heun:
+                    evals.append((sig[i + 1], S.UPD_EDM_HEUN, dt, 0.0, xw[i + 1], dw[i + 1]))
+            out = runtime.try_sample_edm(self, model=model, xt=xt, prior=prior.to(self.device),
+                                         solver="heun" if any(heun_at) else "euler", sigmas=None, order=None, cond_emb=cvec,
+                                         w_cfg=w_cfg, n_samples=n_samples, evals=evals, clip=False)
+            if out is not None:
+                return out, {"log_p": None, "sample_history": None}
+
+        log = {"log_p": None}
+        for i in range(N):
+            d1, log = self.dot_x(xt, i, use_ema, cvec, w_cfg, condition_cg, w_cg)
+            dt = self.t_s[i] - self.t_s[i + 1]
+            nxt = self._reimpose(xt - d1 * dt, prior)
+            if heun_at[i]:
+                d2, log = self.dot_x(nxt, i + 1, use_ema, cvec, w_cfg, condition_cg, w_cg)
+                nxt = self._reimpose(xt - (d1 + d2) / 2. * dt, prior)
+            xt = nxt
+            if preserve_history:
+                x_history[:, i + 1] = xt.cpu().numpy()
+        if extra_sample_steps > 0:
+            dt = self.t_s[N - 1] - self.t_s[N]
+            for _ in range(extra_sample_steps):
+                d1, log = self.dot_x(xt, N - 1, use_ema, cvec, w_cfg, condition_cg, w_cg)
+                xt = self._reimpose(xt - d1 * dt, prior)
+        log["sample_history"] = x_history
+        if log["log_p"] is None and self.classifier is not None and condition_cg is not None:
+            with torch.no_grad():
+                log["log_p"] = self.classifier.logp(xt, at_least_ndim(self.c_noise(self.sigma_s[-1]).squeeze(), 1), condition_cg)
+        return xt, log
+
+    def sample(self, prior: Optional[torch.Tensor] = None, n_samples: int = 1, sample_steps: int = 5, use_ema: bool = True,
+               solver: str = "euler", condition_cfg=None, mask_cfg=None, w_cfg: float = 0.0, condition_cg=None, w_cg: float = 0.0,
+               preserve_history: bool = False, **kwargs):
+        return self._sample_impl(prior, n_samples, sample_steps, 0, use_ema, solver, condition_cfg, mask_cfg, w_cfg, condition_cg,
+                                 w_cg, preserve_history)
+
+    def sample_x(self, prior: Optional[torch.Tensor] = None, n_samples: int = 1, sample_steps: int = 5, extra_sample_steps: int = 8,
+                 use_ema: bool = True, solver: str = "euler", condition_cfg=None, mask_cfg=None, w_cfg: float = 0.0,
+                 condition_cg=None, w_cg: float = 0.0, preserve_history: bool = False, **kwargs):
+        return self._sample_impl(prior, n_samples, sample_steps, extra_sample_steps, use_ema, solver, condition_cfg, mask_cfg,
+                                 w_cfg, condition_cg, w_cg, preserve_history)

@@ -118,7 +118,8 @@ class DiscreteRectifiedFlow(_RectifiedFlow):
         super().__init__(nn_diffusion, nn_condition, fix_mask, loss_weight, classifier, grad_clip_norm,
                          diffusion_steps, ema_rate, optim_params, device)
         assert classifier is None, "Rectified Flow does not support classifier-guidance."
-        self.x_max, self.x_min = x_max, x_min
+        self.x_max = x_max.to(device) if isinstance(x_max, torch.Tensor) else x_max
+        self.x_min = x_min.to(device) if isinstance(x_min, torch.Tensor) else x_min
         if isinstance(discretization, str):
             fn = SUPPORTED_DISCRETIZATIONS.get(discretization, SUPPORTED_DISCRETIZATIONS["uniform"])
             self.t_diffusion = fn(diffusion_steps, 0.).to(device)
@@ -173,7 +174,8 @@ class ContinuousRectifiedFlow(_RectifiedFlow):
         super().__init__(nn_diffusion, nn_condition, fix_mask, loss_weight, classifier, grad_clip_norm,
                          0, ema_rate, optim_params, device)
         assert classifier is None, "Rectified Flow does not support classifier-guidance."
-        self.x_max, self.x_min = x_max, x_min
+        self.x_max = x_max.to(device) if isinstance(x_max, torch.Tensor) else x_max
+        self.x_min = x_min.to(device) if isinstance(x_min, torch.Tensor) else x_min
 
     def _sample_training_time(self, n):
         t = torch.rand((n,), device=self.device)

@@ -37,6 +37,7 @@ UPD_DDPM, UPD_DDIM, UPD_EPS, UPD_X, UPD_X2M, UPD_CM, UPD_EDM, UPD_EDM_HEUN = 0, 
 # row layout of the per-iteration coefficient table (floats)
 ROW = 12
 (R_ALPHA, R_SIGMA, R_K0, R_K1, R_K2, R_K3, R_K4, R_KIND, R_NOISE, R_T, R_SPARE0, R_SPARE1) = range(ROW)
+R_XW, R_DW = R_SPARE0, R_SPARE1          # EDM kinds: explicit slope weights (legacy EDM archetecture)
 
 
 def solver_draws_noise(solver: str) -> bool:

@@ -533,7 +533,7 @@ def try_sample_consistency(agent, *, model, xt, prior, sigmas, order, cond_emb, 
     return plan.x.clone()
 
 
-def try_sample_edm(agent, *, model, xt, prior, solver, sigmas, order, cond_emb, w_cfg, n_samples):
+def try_sample_edm(agent, *, model, xt, prior, solver, sigmas, order, cond_emb, w_cfg, n_samples, evals=None, clip=True):
     """ContinuousEDM.sample on the engine (newedm.py:395-431).  Every network evaluation is one engine iteration:
     ``euler``: one per reverse step; ``heun``: predictor + corrector (two evaluations) for every step but the last.
     ``sigmas``: the Karras grid (sample_steps + 1 entries, fp32), ``order``: the reverse steps i in loop order."""
@@ -549,10 +549,11 @@ def try_sample_edm(agent, *, model, xt, prior, solver, sigmas, order, cond_emb, 
     batch, x_shape = xt.shape[0], tuple(xt.shape[1:])
     if n_samples != batch:
         return _fallback("n_samples != prior.shape[0]")
-    sig = sigmas.detach().float().cpu()
     sd = agent.sigma_data
-    evals = []                                   # (sigma of the evaluation, kind, dt, predictor flag)
-    for i in order:
+    given = evals is not None                    # legacy EDM: the caller lists the evaluations (sigma, kind, dt, flag, xw, dw)
+    sig = sigmas.detach().float().cpu() if not given else None
+    evals = list(evals) if given else []         # (sigma of the evaluation, kind, dt, predictor flag[, x_weight, D_weight])
+    for i in ([] if given else order):
         dt = sig[i] - sig[i - 1]
         heun = solver == "heun" and i > 1
         evals.append((sig[i], S.UPD_EDM, dt, 1.0 if heun else 0.0))
@@ -561,7 +562,10 @@ def try_sample_edm(agent, *, model, xt, prior, solver, sigmas, order, cond_emb, 
             evals.append((sig[i - 1], S.UPD_EDM_HEUN, dt, 0.0))
     n_iters = len(evals)
     table = torch.zeros((n_iters, S.ROW), dtype=torch.float32)
-    for n, (s, kind, dt, pred_flag) in enumerate(evals):   # 0-d fp32 tensors, reference op order (newedm.py:128-148)
+    for n, ev in enumerate(evals):                         # 0-d fp32 tensors, reference op order (newedm.py:128-148)
+        s, kind, dt, pred_flag = ev[:4]
+        if len(ev) > 4:
+            table[n, S.R_XW], table[n, S.R_DW] = float(ev[4]), float(ev[5])
         table[n, S.R_K0] = float(sd ** 2 / (sd ** 2 + s ** 2))                  # c_skip
         table[n, S.R_K1] = float(s * sd / (sd ** 2 + s ** 2).sqrt())            # c_out
         table[n, S.R_K3] = float(1 / (sd ** 2 + s ** 2).sqrt())                 # c_in
@@ -571,7 +575,8 @@ def try_sample_edm(agent, *, model, xt, prior, solver, sigmas, order, cond_emb, 
         table[n, S.R_KIND] = float(kind)
         table[n, S.R_T] = float(0.25 * s.log())                                 # c_noise
     has_mask = isinstance(agent.fix_mask, torch.Tensor)
-    has_min, has_max = agent.x_min is not None, agent.x_max is not None
+    has_min = clip and getattr(agent, "x_min", None) is not None
+    has_max = clip and getattr(agent, "x_max", None) is not None
     math = _math_mode()
     heun = solver == "heun"
     key = ("edm", id(net), batch, x_shape, n_iters, cfg_mode, has_mask, has_min, has_max, heun, math,

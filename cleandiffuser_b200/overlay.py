@@ -28,6 +28,7 @@ _TARGETS: Dict[str, Tuple[str, ...]] = {
                                 "DiscreteRectifiedFlow", "ContinuousRectifiedFlow"),
     "cleandiffuser.diffusion.newedm": ("ContinuousEDM",),
     "cleandiffuser.diffusion.ddpm": ("DDPM",),
+    "cleandiffuser.diffusion.edm": ("EDM",),
     "cleandiffuser.diffusion.rectifiedflow": ("DiscreteRectifiedFlow", "ContinuousRectifiedFlow"),
     "cleandiffuser.diffusion.diffusionsde": ("DiscreteDiffusionSDE", "ContinuousDiffusionSDE"),
     "cleandiffuser.diffusion.consistency_model": ("ContinuousConsistencyModel",),

@@ -83,6 +83,8 @@ typedef enum cds_update_kind { CDS_UPD_DDPM = 0, CDS_UPD_DDIM = 1, CDS_UPD_EPS =
 /* per-iteration coefficient row (floats), one row per reverse iteration */
 enum { CDS_ROW_ALPHA = 0, CDS_ROW_SIGMA = 1, CDS_ROW_K0 = 2, CDS_ROW_K1 = 3, CDS_ROW_K2 = 4, CDS_ROW_K3 = 5,
        CDS_ROW_K4 = 6, CDS_ROW_KIND = 7, CDS_ROW_NOISE = 8 /* 1 + noise slot, 0 = no draw */, CDS_ROW_T = 9,
+       CDS_ROW_XW = 10, CDS_ROW_DW = 11 /* EDM kinds: when XW != 0 the slope is XW*x - DW*D (the legacy EDM archetecture's
+                                           x_weight / D_weight, edm.py:152) instead of (x - D)/SIGMA */,
        CDS_ROW_FLOATS = 12 };
 
 /* vec(b, c) = step[iter*step_stride + c] + sample[b*sample_stride + c] */

@@ -28,4 +28,4 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden():
     return {n: np.load(os.path.join(GOLDEN, n + ".npz"), allow_pickle=False)
-            for n in ("nets", "tables", "samplers", "consistency", "edm", "guided", "legacy", "rf")}
+            for n in ("nets", "tables", "samplers", "consistency", "edm", "guided", "legacy", "rf", "legacy_edm")}

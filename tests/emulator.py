@@ -210,7 +210,7 @@ def run_update(u, it):
                 d_theta = np.maximum(d_theta, xmin)
             if xmax is not None:
                 d_theta = np.minimum(d_theta, xmax)
-        slope = (x - d_theta) / sigma
+        slope = (f(row[10]) * x - f(row[11]) * d_theta) if row[10] != 0 else (x - d_theta) / sigma
         if kind == 6:
             out = x - slope * k2
             if k4 != 0 and u.xhat_prev and u.aux:

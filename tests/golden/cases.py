@@ -146,6 +146,15 @@ def rf_cases():
     }
 
 
+def legacy_edm_cases():
+    """Legacy EDM class (edm.py): Euler / Heun over the descending Karras grid, CFG regimes, fix_mask, sample_x extra steps."""
+    return {
+        "ledm_euler_plain": dict(net="janner_tiny", solver="euler", steps=5, fix_mask=None, w_cfg=0.0, cond=None, extra=0),
+        "ledm_heun_mask_cond": dict(net="janner_tiny", solver="heun", steps=6, fix_mask="first_row", w_cfg=1.0, cond="emb", extra=0),
+        "ledm_heun_cfg2branch_x": dict(net="dql_tiny", solver="heun", steps=4, fix_mask=None, w_cfg=1.5, cond="obs", extra=3),
+    }
+
+
 def guided_cases():
     """Classifier-guided sampling (diffusionsde.py:153-173, :597-606) with cleandiffuser_b200.testing.ToyClassifier attached:
     the Diffuser pattern (x0-prediction, DDPM, fix_mask, w_cg = 0.3) and eps-prediction with a condition branch."""

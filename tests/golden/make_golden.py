@@ -218,6 +218,30 @@ def gen_rf():
     print("rf.npz", len(out))
 
 
+def gen_legacy_edm():
+    from cleandiffuser.diffusion.edm import EDM
+    out = {}
+    for name, spec in cases.legacy_edm_cases().items():
+        net, _ = build_net(cases.SAMPLER_NETS[spec["net"]])
+        inp = cases.sampler_inputs(dict(spec, clip=False))
+        agent = EDM(net, build_condition(spec), fix_mask=inp["fix_mask"], device="cpu")
+        agent.model_ema.eval()
+        kw = dict(n_samples=cases.SAMPLER_BATCH, sample_steps=spec["steps"], use_ema=True, solver=spec["solver"],
+                  condition_cfg=inp["cond"], w_cfg=spec["w_cfg"])
+        tape = NoiseTape()
+        with tape.active(), torch.no_grad():
+            if spec["extra"]:
+                x0, log = agent.sample_x(inp["prior"], extra_sample_steps=spec["extra"], **kw)
+            else:
+                x0, log = agent.sample(inp["prior"], **kw)
+        out[name + "/x0"] = x0.numpy()
+        for j, z in enumerate(tape.draws):
+            out[f"{name}/z{j}"] = z.numpy()
+        out[name + "/n_draws"] = np.array(len(tape.draws))
+    np.savez_compressed(os.path.join(HERE, "legacy_edm.npz"), **out)
+    print("legacy_edm.npz", len(out))
+
+
 def gen_edm():
     out = {}
     for name, spec in cases.edm_cases().items():
@@ -245,6 +269,6 @@ def gen_edm():
 if __name__ == "__main__":
     torch.set_num_threads(1)
     only = sys.argv[1:]
-    for fn in (gen_tables, gen_nets, gen_samplers, gen_consistency, gen_edm, gen_guided, gen_legacy, gen_rf):
+    for fn in (gen_tables, gen_nets, gen_samplers, gen_consistency, gen_edm, gen_guided, gen_legacy, gen_rf, gen_legacy_edm):
         if not only or fn.__name__[4:] in only:
             fn()

@@ -104,3 +104,26 @@ def test_edm_on_the_cuda_engine(golden, name, math, monkeypatch):
         assert err.max() < 1e-3, float(err.max())
     else:
         assert err.max() < (0.1 if spec["w_cfg"] not in (0.0, 1.0) else 2e-2) and err.mean() < 4e-3, (float(err.max()), float(err.mean()))
+
+
+def test_consistency_distillation_from_an_edm_teacher():
+    """ContinuousConsistencyModel.prepare_distillation / update(loss_type="distillation") with a ContinuousEDM teacher
+    (consistency_model.py:200-239, :264-293; tutorials/sp_consistency_policy.py:216,290): the capability the EDM class unlocks."""
+    from cleandiffuser_b200.diffusion import ContinuousConsistencyModel
+    from cleandiffuser_b200.nn_condition import IdentityCondition
+    case = cases.NETS["chi_cm_fourier"]
+    net_t, _ = product_net(case)
+    net_s, _ = product_net(case, seed=1)
+    kw = dict(x_max=torch.ones(1, 8, 3), x_min=-torch.ones(1, 8, 3), device="cpu")
+    edm = ContinuousEDM(net_t, IdentityCondition(dropout=0.0), **kw)
+    log = edm.update(torch.randn(4, 8, 3) * 0.3, torch.randn(4, 2, 5))
+    assert np.isfinite(log["loss"])
+    cm = ContinuousConsistencyModel(net_s, IdentityCondition(dropout=0.0), **kw)
+    cm.prepare_distillation(edm, distillation_N=6)
+    for a, b in zip(cm.model.parameters(), edm.model.parameters()):
+        assert torch.equal(a, b)                                   # student initialised from the teacher
+    before = [p.clone() for p in cm.model.parameters()]
+    log = cm.update(torch.randn(4, 8, 3) * 0.3, torch.randn(4, 2, 5), loss_type="distillation")
+    assert np.isfinite(log["loss"]) and any(not torch.equal(a, b) for a, b in zip(before, cm.model.parameters()))
+    x0, _ = cm.sample(torch.zeros(4, 8, 3), n_samples=4, sample_steps=2, condition_cfg=torch.randn(4, 2, 5), w_cfg=1.0)
+    assert x0.shape == (4, 8, 3) and float(x0.abs().max()) <= 1.0

@@ -102,3 +102,83 @@ def test_legacy_ddpm_on_the_cuda_engine(golden, name, math, monkeypatch):
         assert err.max() < 1e-3, float(err.max())
     else:
         assert err.max() < 0.15 and err.mean() < 4e-3, (float(err.max()), float(err.mean()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the legacy EDM class (edm.py) of the dbc_* pipelines: goldens from the reference (make_golden.py::gen_legacy_edm)
+from cleandiffuser_b200.diffusion import EDM  # noqa: E402
+
+EDM_NAMES = list(cases.legacy_edm_cases())
+
+
+def build_edm(spec, device="cpu"):
+    net, _ = product_net(cases.SAMPLER_NETS[spec["net"]])
+    inp = cases.sampler_inputs(dict(spec, clip=False))
+    agent = EDM(net, product_condition(spec), fix_mask=inp["fix_mask"], device=device)
+    kw = dict(n_samples=cases.SAMPLER_BATCH, sample_steps=spec["steps"], use_ema=True, solver=spec["solver"],
+              condition_cfg=inp["cond"], w_cfg=spec["w_cfg"])
+    return agent, inp, kw
+
+
+def run_edm(agent, spec, prior, kw):
+    if spec["extra"]:
+        return agent.sample_x(prior, extra_sample_steps=spec["extra"], **kw)
+    return agent.sample(prior, **kw)
+
+
+@pytest.mark.parametrize("name", EDM_NAMES)
+def test_legacy_edm_torch_path_matches_reference(golden, name, monkeypatch):
+    monkeypatch.setenv("CDS_BACKEND", "torch")
+    spec = cases.legacy_edm_cases()[name]
+    agent, inp, kw = build_edm(spec)
+    tape = NoiseTape(tape_of(golden["legacy_edm"], name))
+    with tape.active(), torch.no_grad():
+        x0, _ = run_edm(agent, spec, inp["prior"], kw)
+    assert tape.pos == len(tape.draws)
+    np.testing.assert_allclose(x0.numpy(), golden["legacy_edm"][name + "/x0"], rtol=1e-5, atol=2e-4)
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+@pytest.mark.parametrize("name", EDM_NAMES)
+def test_legacy_edm_lowered_program(golden, name, math, monkeypatch):
+    monkeypatch.setattr(runtime, "_device_ok", lambda device: True)
+    monkeypatch.setattr(runtime, "_make_handle", lambda device, ops, n: emulator.Handle(ops, n))
+    monkeypatch.setenv("CDS_BACKEND", "cuda")
+    monkeypatch.setenv("CDS_MATH", math)
+    spec = cases.legacy_edm_cases()[name]
+    agent, inp, kw = build_edm(spec)
+    calls = runtime.STATS["engine_calls"]
+    tape = NoiseTape(tape_of(golden["legacy_edm"], name))
+    with tape.active(), torch.no_grad():
+        x0, _ = run_edm(agent, spec, inp["prior"], kw)
+    assert runtime.STATS["engine_calls"] == calls + 1 and tape.pos == len(tape.draws)
+    err = np.abs(x0.numpy() - golden["legacy_edm"][name + "/x0"])
+    ref = max(1.0, float(np.abs(golden["legacy_edm"][name + "/x0"]).mean()))
+    if math == "fp32":
+        assert err.max() / ref < 5e-4, float(err.max())
+    else:
+        assert err.max() / ref < 0.1 and err.mean() / ref < 4e-3, (float(err.max()), float(err.mean()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+@pytest.mark.parametrize("name", EDM_NAMES)
+def test_legacy_edm_on_the_cuda_engine(golden, name, math, monkeypatch):
+    monkeypatch.setenv("CDS_BACKEND", "cuda")
+    monkeypatch.setenv("CDS_MATH", math)
+    dev = "cuda:0"
+    spec = cases.legacy_edm_cases()[name]
+    agent, inp, kw = build_edm(spec, device=dev)
+    if kw.get("condition_cfg") is not None:
+        kw["condition_cfg"] = kw["condition_cfg"].to(dev)
+    calls = runtime.STATS["engine_calls"]
+    tape = NoiseTape(tape_of(golden["legacy_edm"], name))
+    with tape.active(), torch.no_grad():
+        x0, _ = run_edm(agent, spec, inp["prior"].to(dev), kw)
+    assert runtime.STATS["engine_calls"] == calls + 1
+    err = np.abs(x0.cpu().numpy() - golden["legacy_edm"][name + "/x0"])
+    ref = max(1.0, float(np.abs(golden["legacy_edm"][name + "/x0"]).mean()))
+    if math == "fp32":
+        assert err.max() / ref < 2e-3, float(err.max())
+    else:
+        assert err.max() / ref < 0.1 and err.mean() / ref < 4e-3, (float(err.max()), float(err.mean()))
