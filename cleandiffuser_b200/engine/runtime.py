@@ -376,7 +376,8 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
 
     # ---- per-iteration scalars (host, reference op order); identical requests reuse the table (building it costs ~10 ms
     # of Python scalar arithmetic for 100 steps -- more than a tenth of a whole cfg2 sample() on the engine) ---------------
-    if table is not None:
+    table_given = table is not None
+    if table_given:
         rows_given, slots_given, t_given = table
         t_cpu = t_given.detach().cpu()
         order = list(range(rows_given.shape[0]))
@@ -402,7 +403,7 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
         agent._engine_tables[sched_key] = (table, n_slots)
     else:
         table, n_slots = cached
-    keep_history = table is None and S.solver_keeps_history(solver)
+    keep_history = (not table_given) and S.solver_keeps_history(solver)
     has_mask = isinstance(agent.fix_mask, torch.Tensor)
     has_min, has_max = (agent.x_min is not None and clip_in_loop), (agent.x_max is not None and clip_in_loop)
     pn = bool(agent.predict_noise) if predict_noise is None else bool(predict_noise)
