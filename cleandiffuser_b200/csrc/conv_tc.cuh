@@ -50,6 +50,10 @@ struct ConvTcParams {
   // row tile instead of once per column tile.
   CUtensorMap tm_a_mc, tm_a2_mc;
   int cluster;
+  // identity residual as a TMA-load source with the box of tm_out: the fast lane prefetches the next 32 rows x 16 columns of the
+  // residual into per-warp staging rows while it works on the current ones (valid when res_tma != 0; tiles of N <= 64 only)
+  CUtensorMap tm_res;
+  int res_tma;
   int batch, L, log2L, C_out, taps, pad;   // L = output positions per tile-trajectory; C_out = channels per phase
   int num_tiles;                  // ceil(batch*L / 128); CTAs are persistent and stride over the tiles
   int phases;                     // 2: columns [0,C_out) / [C_out,2C_out) are output positions 2l / 2l+1 (transposed conv)
@@ -178,8 +182,10 @@ struct ConvTcCfg {
   // at least 3, at most kTcMaxStages.  A tile is taps x C_in/KC k-blocks (5..20): only a ring that holds more than one tile
   // lets the TMA producer run ahead of the tile whose accumulator the epilogue is still draining -- with 4 stages and
   // 5 k-blocks per tile every tile paid one exposed L2 round trip (~1 us) on the narrow layers.
-  // (2 CTAs/SM: 227 KB - 2 x (22 KB static: per-column constants, 16 KB of epilogue store staging, barriers) - 2 x 1 KB reserved)
-  static constexpr int kRingBudget = (N <= 128 ? 88 : 184) * 1024;
+  // (2 CTAs/SM: 227 KB - 2 x (22 KB static: per-column constants, 16 KB of epilogue store staging, barriers; + 16 KB of residual
+  // staging for the narrow tiles) - 2 x 1 KB reserved)
+  static constexpr bool kResStage = N <= 64;             // per-warp staging of TMA-prefetched identity residuals
+  static constexpr int kRingBudget = (N <= 64 ? 72 : (N <= 128 ? 88 : 184)) * 1024;
   static constexpr int kStagesFit = kRingBudget / kStageBytes;
   static constexpr int kStages = kStagesFit < 3 ? 3 : (kStagesFit > kTcMaxStages ? kTcMaxStages : kStagesFit);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
@@ -273,6 +279,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
   // different cache lines per instruction (measured: the LSU serialises them, the store's source registers stay locked and the
   // epilogue stalls on them), the bulk store writes whole sectors and costs the warp 4 conflict-free st.shared
   __shared__ __align__(1024) uint8_t s_stage[kTcEpiThreads / 32][2048];
+  __shared__ __align__(1024) uint8_t s_resb[Cfg::kResStage ? kTcEpiThreads / 32 : 1][Cfg::kResStage ? 2048 : 16];
+  __shared__ __align__(8) uint64_t res_bar[kTcEpiThreads / 32];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // operand ring, 1024-byte aligned (swizzle atoms)
@@ -291,6 +299,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     // a stage is free again when the MMAs of EVERY CTA of the cluster have consumed it (peers multicast into it)
     for (int s = 0; s < kTcStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], (uint32_t)cs); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], kTcEpiThreads / 32); }
+    for (int i = 0; i < kTcEpiThreads / 32; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 8 && lane == 0) {
@@ -299,6 +308,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     if (HAS_RES) { ptx::prefetch_tensormap(&p.tm_a2); ptx::prefetch_tensormap(&p.tm_b2); }
     if (p.out_tma) ptx::prefetch_tensormap(&p.tm_out);
     if (cs > 1) { ptx::prefetch_tensormap(&p.tm_a_mc); if (HAS_RES) ptx::prefetch_tensormap(&p.tm_a2_mc); }
+    if (p.res_tma) ptx::prefetch_tensormap(&p.tm_res);
   }
   if (warp == 9) ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_holder);
   ptx::tc_fence_before_sync();
@@ -469,6 +479,18 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       uint8_t* const stg_row = stg + lane * (16 * (int)sizeof(ET));
       const int traj_q = (32 * q) >> p.log2L;                         // first trajectory of this warp's rows inside the tile
       const int64_t res_bs = p.res_bstride;
+      // identity residual through TMA: this warp's 32 rows x 16 columns of the NEXT column group / tile are fetched into its
+      // staging rows while the current group is processed (the strided ld.global of a row-per-thread layout cost ~1 us per tile)
+      constexpr int kGroups = NH / 16;                                // 16-column groups per thread and tile
+      constexpr uint32_t kResBytes = 32u * 16u * (uint32_t)sizeof(ET);
+      const bool res_pf = RES && Cfg::kResStage && p.res_tma != 0;
+      uint8_t* const rstg = &s_resb[Cfg::kResStage ? warp : 0][0];
+      uint32_t res_phase = 0;
+      auto issue_res = [&](int tile_, int gi_) {                      // lane 0 only
+        ptx::mbar_expect_tx(&res_bar[warp], kResBytes);
+        ptx::tma_load_3d(rstg, &p.tm_res, &res_bar[warp], (tile_ % SPLIT) * N + col0 + 16 * gi_, 0, (tile_ / SPLIT) * T_ + traj_q);
+      };
+      if (res_pf && lane == 0 && (int)blockIdx.x < p.num_tiles) issue_res((int)blockIdx.x, 0);
       const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it % Cfg::kAccBufs;
@@ -513,7 +535,34 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
 #pragma unroll
               for (int j = 0; j < 16; ++j) addv[j] = 0.f;
             }
-            if constexpr (RES && TF32) {
+            if (RES && res_pf) {
+              // the prefetched rows (zero beyond the batch: TMA out-of-bound fill), de-swizzled like the store staging
+              ptx::mbar_wait(&res_bar[warp], res_phase);
+              res_phase ^= 1u;
+              const uint8_t* rr = rstg + lane * (16 * (int)sizeof(ET));
+              if constexpr (TF32) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float4 rv = *reinterpret_cast<const float4*>(rr + ((k ^ ((lane >> 1) & 3)) << 4));
+                  addv[4 * k] += rv.x; addv[4 * k + 1] += rv.y; addv[4 * k + 2] += rv.z; addv[4 * k + 3] += rv.w;
+                }
+              } else {
+                const int sw = (lane >> 2) & 1;
+                const uint4 u0 = *reinterpret_cast<const uint4*>(rr + ((0 ^ sw) << 4)), u1 = *reinterpret_cast<const uint4*>(rr + ((1 ^ sw) << 4));
+                const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  addv[2 * j] += __uint_as_float(w[j] << 16);
+                  addv[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+                }
+              }
+              __syncwarp();                                          // every lane has its values: the rows may be overwritten
+              if (lane == 0) {
+                const int gi = ch * (WC / 16) + h;
+                if (gi + 1 < kGroups) { ptx::fence_proxy_async(); issue_res(tile, gi + 1); }
+                else if (tile + (int)gridDim.x < p.num_tiles) { ptx::fence_proxy_async(); issue_res(tile + (int)gridDim.x, 0); }
+              }
+            } else if constexpr (RES && TF32) {
               if (valid) {
                 const float4* rp = reinterpret_cast<const float4*>(res_row_p + n0 + 16 * h);
 #pragma unroll
@@ -1214,6 +1263,22 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
       }
     }
   }
+  p.res_tma = 0;
+  if (c.res && !c.res_w && c.res_batch_mod == 0 && c.phases == 1 && c.C_out % 16 == 0 && Lp <= 32 && L.n <= 64 &&
+      c.res_dtype == (tf32 ? c.res_dtype : CDS_BF16) && (tf32 ? c.res_dtype != CDS_BF16 : true) && !getenv("CDS_NO_TMA_RES")) {
+    const int res_es = tf32 ? 4 : 2;
+    if (((uintptr_t)c.res % 16) == 0 && ((int64_t)c.res_lstride * res_es) % 16 == 0 && ((int64_t)c.res_bstride * res_es) % 16 == 0) {
+      PFN_encodeTiled enc = get_encode_tiled();
+      cuuint64_t gdim[3] = {(cuuint64_t)c.C_out, (cuuint64_t)Lp, (cuuint64_t)c.batch};
+      cuuint64_t gstr[2] = {(cuuint64_t)c.res_lstride * res_es, (cuuint64_t)c.res_bstride * res_es};
+      cuuint32_t bx[3] = {16u, (cuuint32_t)Lp, (cuuint32_t)(32 / Lp)};
+      cuuint32_t es[3] = {1u, 1u, 1u};
+      if (enc && enc(&p.tm_res, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(c.res), gdim,
+                     gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, tf32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        p.res_tma = 1;
+    }
+  }
   p.batch = c.batch; p.L = Lp; p.log2L = ilog2(Lp); p.C_out = c.C_out; p.taps = c.taps; p.pad = c.pad;
   p.phases = c.phases;
   p.kchunks = c.C_in / ke; p.kchunks2 = L.has_res ? c.res_C / ke : 0;
@@ -1256,7 +1321,9 @@ cudaError_t conv_tc_launch_t(const ConvTcLaunch& L, const int* iter_ptr, cudaStr
     // residency we design for: launch-bounds blocks, TMEM (kTmemCols of 512 columns per SM), 227 KB shared memory
     int want = Cfg::kMinBlocks;
     int by_tmem = 512 / (int)Cfg::kTmemCols;
-    int by_smem = (227 * 1024) / (Cfg::kSmemBytes + 8 * 1024);
+    // static shared memory: 16 KB store staging + 24 B/column of constants + barriers (+ 16 KB residual staging), 1 KB reserved
+    const int static_smem = 16 * 1024 + 24 * Cfg::kCols + 1024 + (Cfg::kResStage ? 16 * 1024 : 0) + 1024;
+    int by_smem = (227 * 1024) / (Cfg::kSmemBytes + static_smem);
     if (want > by_tmem) want = by_tmem;
     if (want > by_smem) want = by_smem;
     if (const char* cap = getenv("CDS_TC_MAXCTAS")) { int c = atoi(cap); if (c >= 1 && c < want) want = c; }

@@ -533,6 +533,55 @@ def lower_dql(p: Program, net: nn.Module, x: View, has_cond: bool, in_batch_mod:
     return p.conv(h, w_linear(fl.weight), out, bias=_const_vec(p.packed(lambda: fl.bias)))
 
 
+# =============================================================================== IDQLMlp
+def lower_idql(p: Program, net: nn.Module, x: View, has_cond: bool, in_batch_mod: int) -> View:
+    """idqlmlp.py:21-65.  affine_in over cat[x, time_mlp(t), obs] splits like DQLMlp's first Linear (per-iteration row +
+    per-trajectory row); each residual block is LayerNorm (affine folded into the LN+modulate operator: scale = gamma - 1,
+    shift = beta, broadcast over the batch) -> Linear + Mish -> Linear + identity residual.  Dropout is inactive in eval mode."""
+    if net.training and any(blk.net[0].p > 0 for blk in net.ln_resnet):
+        raise Unsupported("IDQLMlp in train mode (dropout)")
+    act_dim = x.C
+    lin_in = net.affine_in
+    e_dim = net.time_mlp[2].out_features
+    hidden = lin_in.out_features
+    step_tab, samp_tab = p.buf(p.n_iters, hidden), p.buf(p.rows, hidden)
+
+    def fill(ctx):
+        temb = net.time_mlp(net.map_noise(ctx.t_all))
+        step_tab.copy_(F.linear(temb, lin_in.weight[:, act_dim:act_dim + e_dim], lin_in.bias))
+        if has_cond:
+            samp_tab.copy_(F.linear(ctx.cond_rows, lin_in.weight[:, act_dim + e_dim:]))
+        else:
+            samp_tab.zero_()
+    p.per_call.append(fill)
+    f32 = torch.float32
+    h = View(p.buf(p.rows, 1, hidden), 1, hidden)                       # the residual stream stays exact fp32
+    p.conv(x, w_linear(lin_in.weight, slice(0, act_dim)), h, bias=_vec(step_tab, samp_tab), in_batch_mod=in_batch_mod)
+    for blk in net.ln_resnet:
+        ln, fc1, fc2 = blk.net[1], blk.net[2], blk.net[4]
+        if not ln.elementwise_affine:
+            raise Unsupported("LayerNorm without affine")
+        mod = p.buf(1, 2 * hidden)                                    # [gamma - 1 | beta]: LN(x) * (1 + scale) + shift
+        p.packers.append(lambda m=mod, l=ln: m.copy_(torch.cat([l.weight - 1., l.bias])[None]))
+        p.packers[-1]()
+        y = p.act(1, hidden)
+        op = cabi.Op()
+        op.kind = cabi.OP_LNMOD
+        m = op.u.lnmod
+        m.batch, m.L, m.C, m.eps = p.rows, 1, hidden, ln.eps
+        m.in_, m.out, m.out_dtype = h.ptr, y.ptr, y.dtype
+        m.scale, m.shift, m.mod_bstride = mod.data_ptr(), mod.data_ptr() + 4 * hidden, 0
+        p.ops.append(op)
+        mid = p.act(1, fc1.out_features)
+        p.conv(y, w_linear(fc1.weight), mid, bias=_const_vec(p.packed(lambda f=fc1: f.bias)), act=cabi.ACT_MISH)
+        h2 = View(p.buf(p.rows, 1, hidden), 1, hidden)
+        p.conv(mid, w_linear(fc2.weight), h2, bias=_const_vec(p.packed(lambda f=fc2: f.bias)), res=h)
+        h = h2
+    out = View(p.buf(p.rows, 1, act_dim), 1, act_dim)
+    fo = net.affine_out
+    return p.conv(h, w_linear(fo.weight), out, bias=_const_vec(p.packed(lambda: fo.bias)))
+
+
 # =============================================================================== DiT1d
 def lower_dit(p: Program, net: nn.Module, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
     d = net.d_model
@@ -622,4 +671,6 @@ def lower_denoiser(p: Program, net: nn.Module, x: View, x_shape, has_cond: bool,
         return lower_dit(p, net, x, x_shape[0], has_cond, in_batch_mod)
     if name == "DQLMlp" and len(x_shape) == 1:
         return lower_dql(p, net, x, has_cond, in_batch_mod)
+    if name == "IDQLMlp" and len(x_shape) == 1:
+        return lower_idql(p, net, x, has_cond, in_batch_mod)
     raise Unsupported(f"backbone {name} with x_shape {tuple(x_shape)}")

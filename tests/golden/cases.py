@@ -34,6 +34,10 @@ NETS = {
         cls="DiT1d", ctor=dict(in_dim=4, emb_dim=16, d_model=32, n_heads=1, depth=1),
         x=(7, 4), t="long", cond=None,
         oracle=dict(fn="dit1d", emb_dim=16, d_model=32, n_heads=1, depth=1)),
+    "idql_small": dict(
+        cls="IDQLMlp", ctor=dict(obs_dim=11, act_dim=3, emb_dim=32, hidden_dim=64, n_blocks=2),
+        x=(3,), t="long", cond=(11,),
+        oracle=dict(fn="idql_mlp", emb_dim=32, obs_dim=11, n_blocks=2)),
     "dql_cfg1": dict(
         cls="DQLMlp", ctor=dict(obs_dim=11, act_dim=3, emb_dim=64),
         x=(3,), t="long", cond=(11,),
