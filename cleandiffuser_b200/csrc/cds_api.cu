@@ -12,6 +12,7 @@
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
 #include "conv_ps.cuh"
+#include "attention_tma.cuh"
 #include "elementwise.cuh"
 
 namespace {
@@ -60,6 +61,7 @@ struct Step {            // one validated operator + its kernel choice
   bool skip = false;     // operator folded into another launch by a finalize-time peephole (none at present)
   bool ps = false;       // ... served by the position-sliced kernel (short sequences, conv_ps.cuh)
   cds::ConvPsLaunch psl;
+  cds::AttnTmaLaunch attl;   // TF32 attention: tensor maps of the persistent TMA-fed kernel (attention_tma.cuh)
 };
 
 int elementwise_grid(int64_t total, int sm_count) {
@@ -128,6 +130,8 @@ int validate(const cds_op& op, Step* out) {
       if ((size_t)a.L * hd * 8 > 200 * 1024) return fail(CDS_ERR_UNSUPPORTED, "attn: L=%d too long", a.L);
       if (a.qkv_dtype == CDS_BF16 && (hd != 32 || a.L > cds::kAttnMaxL || a.C % 8 != 0 || ((uintptr_t)a.qkv % 16) != 0))
         return fail(CDS_ERR_UNSUPPORTED, "attn: bf16 q/k/v needs head_dim 32, L <= %d, 16-byte aligned rows", cds::kAttnMaxL);
+      if (cds::attention_tma_eligible(a) && !cds::attention_tma_prepare(a, &out->attl))
+        return fail(CDS_ERR_CUDA, "attn: cuTensorMapEncodeTiled failed (L=%d C=%d)", a.L, a.C);
       return CDS_OK;
     }
     case CDS_OP_PREP: {
@@ -176,7 +180,8 @@ int launch(const Step& s, const int* iter_ptr, int sm_count, cudaStream_t st, in
       return CDS_OK;
     }
     case CDS_OP_ATTN:
-      CDS_CUDA(cds::attention_launch(s.op.u.attn, st));
+      if (s.attl.ok) CDS_CUDA(cds::attention_tma_launch(s.op.u.attn, s.attl, sm_count, st));
+      else CDS_CUDA(cds::attention_launch(s.op.u.attn, st));
       return CDS_OK;
     case CDS_OP_CAST: {
       const cds_cast_op& k = s.op.u.cast;
@@ -201,6 +206,7 @@ int preload_kernels() {
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<64>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_mma_hd32_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_mma_tf32_hd32_kernel));
+  CDS_CUDA(cudaFuncSetAttribute(cds::attention_tma_tf32_hd32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::solver_update_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cm_prep_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cast_pad_kernel));

@@ -192,7 +192,10 @@ struct ConvTcCfg {
   static constexpr int kCols = N * SPLIT;                                 // columns of the whole layer
   static constexpr int kColsPerTile = N * (HAS_RES ? 2 : 1);             // main (+ shortcut) accumulator
   static constexpr int kAccBufs = 2 * kColsPerTile <= 512 ? 2 : 1;       // double-buffered when TMEM allows
-  static constexpr uint32_t kTmemCols = (kAccBufs * kColsPerTile) < 32 ? 32 : (kAccBufs * kColsPerTile);
+  static constexpr uint32_t kTmemNeed = (uint32_t)(kAccBufs * kColsPerTile);
+  static constexpr uint32_t kTmemCols = kTmemNeed <= 32 ? 32 : (kTmemNeed <= 64 ? 64 : (kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512)));   // power of two
+  // GroupNorm lanes exist for the power-of-two tile widths only (the 160 / 192-wide tiles serve un-normalised Linear layers)
+  static constexpr bool kGnOk = (N & (N - 1)) == 0;
   static constexpr int kEpiSplit = N >= 32 ? 2 : 1;     // epilogue warps per TMEM lane quarter (column split)
   // designed CTAs per SM: 2 (102 registers per thread: the epilogue keeps 16-32 columns live).  3 CTAs (68 registers) were
   // measured on the narrow tiles: the spills cost more than the extra residency buys (471 -> 490 us per iteration).
@@ -634,7 +637,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
         if (threadIdx.x == 0 && it < 14) CDS_TRACE(11 + 4 * it, clock64());
       }
     };
-    if constexpr (N >= 32 && Cfg::kCols <= 256) {
+    if constexpr (N >= 32 && Cfg::kCols <= 256 && Cfg::kGnOk) {
       if (fast_ok) {
         using T1 = std::integral_constant<int, 1>;
         using T0 = std::integral_constant<int, 0>;
@@ -1014,12 +1017,14 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       using F1 = std::integral_constant<int, 1>;
       using F2 = std::integral_constant<int, 2>;
       if (has_gn) {
-        if (p.act == CDS_ACT_MISH) {
-          if (film == 0) run(T{}, A1{}, F0{});
-          else if (film == 1) run(T{}, A1{}, F1{});
-          else run(T{}, A1{}, F2{});
-        } else {
-          run(T{}, AX{}, F2{});
+        if constexpr (Cfg::kGnOk) {
+          if (p.act == CDS_ACT_MISH) {
+            if (film == 0) run(T{}, A1{}, F0{});
+            else if (film == 1) run(T{}, A1{}, F1{});
+            else run(T{}, A1{}, F2{});
+          } else {
+            run(T{}, AX{}, F2{});
+          }
         }
       } else {
         if (p.act == CDS_ACT_NONE && film == 0) run(F{}, A0{}, F0{});
@@ -1095,13 +1100,22 @@ inline int conv_tc_pick_kc(const cds_conv_op& c) {
 
 // GEMM width of the op: C_out*phases, or 16 for a narrow (C_out <= 16) 1x1 head whose missing weight rows the TMA
 // unit zero-fills (out-of-bound rows of the weight tensor); 0 = not a width the kernel is instantiated for
+// column-tile width for the runtime-tiled (un-normalised) layers of total width n (a multiple of 64): the widest instantiated
+// tile that divides it -- wide tiles re-load the activation tile less often (DiT1d: 1280 = 5 x 256, 960 = 5 x 192, 320 = 2 x 160)
+// (the 160 / 192-wide tiles are instantiated for 128-byte operand rows only: kc == 64)
+inline int conv_tc_runtime_tile(int n, int kc) {
+  if (n % 256 == 0) return 256;
+  if (kc == 64 && n % 192 == 0) return 192;
+  if (kc == 64 && n % 160 == 0) return 160;
+  return n % 128 == 0 ? 128 : 64;
+}
 inline int conv_tc_width(const cds_conv_op& c) {
   int n = c.C_out * c.phases;
   if (n == 32 || n == 64 || n == 128 || n == 256) return (c.phases == 1 || c.C_out % 16 == 0) ? n : 0;
   if ((n == 512 || n == 1024) && c.phases == 1) return n;      // wide layers: 2 / 4 CTAs of 256 columns (2-4 whole GroupNorm groups each)
   // un-normalised layers of any width that is a multiple of 64 (DiT1d's 320 / 960 / 1280-wide Linear layers): runtime column tiles
   if (n > 64 && n % 64 == 0 && c.groups == 0) {
-    const int tn = n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64);       // a column tile must not straddle the two phases
+    const int tn = conv_tc_runtime_tile(n, conv_tc_pick_kc(c));           // a column tile must not straddle the two phases
     if (c.phases == 1 || c.C_out % tn == 0) return n;
   }
   // narrow output heads (C_out <= 32, e.g. 14 / 29 state dims): N = 16 / 32 with the missing weight rows zero-filled by the TMA unit
@@ -1186,7 +1200,7 @@ inline bool conv_tc_prepare(const cds_conv_op& c, ConvTcLaunch* out) {
     L.n = n_total / L.split;
   } else {
     L.split = 1;
-    L.n = n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64);
+    L.n = conv_tc_runtime_tile(n_total, kc);
     col_tiles = n_total / L.n;
   }
   const uint64_t in_b = c.in_batch_mod > 0 ? (uint64_t)c.in_batch_mod : (uint64_t)c.batch;
@@ -1367,7 +1381,7 @@ cudaError_t conv_tc_preload_t() {
 // every (KC, N, SPLIT) the dispatcher can pick (each with and without the shortcut accumulator); X(kc, n, split)
 #define CDS_TC_VARIANTS(X)                                                                              \
   X(64, 16, 1) X(64, 32, 1) X(64, 64, 1) X(64, 128, 1) X(64, 256, 1) X(64, 32, 2) X(64, 64, 2) X(64, 128, 2) \
-  X(64, 256, 2) X(64, 256, 4)                                                                            \
+  X(64, 256, 2) X(64, 256, 4) X(64, 160, 1) X(64, 192, 1)                                                \
   X(32, 16, 1) X(32, 32, 1) X(32, 64, 1) X(32, 128, 1) X(32, 256, 1) X(32, 32, 2) X(32, 64, 2) X(32, 128, 2)
 
 #ifndef CDS_TC_INSTANTIATE

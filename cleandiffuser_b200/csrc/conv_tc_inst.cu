@@ -23,9 +23,9 @@ CDS_TC_INST(64, 16, 1) CDS_TC_INST(32, 16, 1) CDS_TC_INST(64, 256, 2)
 #elif CDS_TC_PART == 1
 CDS_TC_INST(64, 32, 1) CDS_TC_INST(32, 32, 1) CDS_TC_INST(64, 256, 4)
 #elif CDS_TC_PART == 2
-CDS_TC_INST(64, 64, 1) CDS_TC_INST(32, 64, 1)
+CDS_TC_INST(64, 64, 1) CDS_TC_INST(32, 64, 1) CDS_TC_INST(64, 160, 1)
 #elif CDS_TC_PART == 3
-CDS_TC_INST(64, 128, 1) CDS_TC_INST(32, 128, 1)
+CDS_TC_INST(64, 128, 1) CDS_TC_INST(32, 128, 1) CDS_TC_INST(64, 192, 1)
 #elif CDS_TC_PART == 4
 CDS_TC_INST(64, 256, 1) CDS_TC_INST(32, 32, 2)
 #elif CDS_TC_PART == 5
