@@ -652,13 +652,18 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
     // ... and its "gated" form: out = (acc + bias) * gate(trajectory, column) + residual -- DiT1d's attention out-projection and
     // second MLP Linear (dit.py:33-36: x + gate * f(...)), fp32 residual stream, per-trajectory gate row
     const bool gated_ok = N >= 32 && !HAS_RES && !has_gn && p.act == CDS_ACT_NONE && p.scale.sample && !p.scale.step && !has_shift &&
-                          !p.bias.sample && add_res && p.res_dtype != CDS_BF16 && p.out_dtype != CDS_BF16 && io_vec && p.phases == 1 &&
+                          !p.bias.sample && add_res && p.out_dtype != CDS_BF16 && io_vec && p.phases == 1 &&
                           p.res_batch_mod == 0 && p.out_tma == 1 && ((uintptr_t)p.scale.sample % 16 == 0) && (p.scale.sample_stride % 4 == 0);
-    auto plain_tiles = [&](auto act_tag, auto bf16_tag, auto gated_tag) {
+    // ... and its "table" form: out = acc + bias + table[row % period] -- DiT1d's x_proj + pos_emb (dit.py:118), fp32 table
+    const bool table_ok = N >= 32 && !HAS_RES && !has_gn && film == 0 && !smp && add_res && p.res_batch_mod > 0 && p.act == CDS_ACT_NONE &&
+                          p.res_dtype != CDS_BF16 && p.out_dtype != CDS_BF16 && io_vec && p.phases == 1 && p.out_tma == 1 &&
+                          ((uintptr_t)p.res % 16 == 0) && (p.res_bstride % 4 == 0) && (p.res_lstride % 4 == 0);
+    auto plain_tiles = [&](auto act_tag, auto bf16_tag, auto mode_tag) {
       constexpr int ACT = decltype(act_tag)::value;
       constexpr int OUT_DT = decltype(bf16_tag)::value;            // cds_dtype of the output
       constexpr bool OUT_BF16 = OUT_DT == CDS_BF16;
-      constexpr bool GATED = decltype(gated_tag)::value;
+      constexpr int MODE = decltype(mode_tag)::value;              // 0 plain, 1 gated + residual, 2 + periodic table
+      constexpr bool GATED = MODE == 1;
       const int T_ = 128 >> p.log2L;
       const int tb = m >> p.log2L, l = m & (p.L - 1);
       const int nct = SPLIT > 1 ? SPLIT : p.n_col_tiles;
@@ -707,15 +712,40 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
             for (int k = 0; k < 4; ++k) { g4[k] = make_float4(0.f, 0.f, 0.f, 0.f); r4[k] = g4[k]; }
             if (valid) {
               const float4* gp = reinterpret_cast<const float4*>(p.scale.sample + (int64_t)bs * p.scale.sample_stride + c0);
-              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + (int64_t)b * p.res_bstride +
-                                                                 (int64_t)l * p.res_lstride + c0);
+              const int64_t ro = (int64_t)b * p.res_bstride + (int64_t)l * p.res_lstride + c0;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) { g4[k] = __ldg(gp + k); r4[k] = rp[k]; }
+              for (int k = 0; k < 4; ++k) g4[k] = __ldg(gp + k);
+              if (p.res_dtype == CDS_BF16) {           // (bf16 programs: the modulated tokens are bf16, the stream fp32)
+                const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + ro);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  const uint4 u = rp[k];
+                  r4[2 * k] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                                          __uint_as_float(u.y & 0xffff0000u));
+                  r4[2 * k + 1] = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u), __uint_as_float(u.w << 16),
+                                              __uint_as_float(u.w & 0xffff0000u));
+                }
+              } else {
+                const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + ro);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r4[k] = rp[k];
+              }
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               v[4 * k] = fmaf(v[4 * k], g4[k].x, r4[k].x); v[4 * k + 1] = fmaf(v[4 * k + 1], g4[k].y, r4[k].y);
               v[4 * k + 2] = fmaf(v[4 * k + 2], g4[k].z, r4[k].z); v[4 * k + 3] = fmaf(v[4 * k + 3], g4[k].w, r4[k].w);
+            }
+          }
+          if constexpr (MODE == 2) {
+            if (valid) {
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) +
+                                                                 (int64_t)(b % p.res_batch_mod) * p.res_bstride + (int64_t)l * p.res_lstride + c0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 r = __ldg(rp + k);
+                v[4 * k] += r.x; v[4 * k + 1] += r.y; v[4 * k + 2] += r.z; v[4 * k + 3] += r.w;
+              }
             }
           }
           if (use_tma) {
@@ -781,10 +811,14 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
       using DB = std::integral_constant<int, CDS_BF16>;
       using DT = std::integral_constant<int, CDS_TF32>;
       const int od = p.out_dtype;
+      using M1 = std::integral_constant<int, 1>;
+      using M2 = std::integral_constant<int, 2>;
       if (gated_ok && it == 0) {
-        if (od == CDS_TF32) plain_tiles(Z{}, DT{}, std::true_type{}); else plain_tiles(Z{}, DF{}, std::true_type{});
+        if (od == CDS_TF32) plain_tiles(Z{}, DT{}, M1{}); else plain_tiles(Z{}, DF{}, M1{});
+      } else if (table_ok && it == 0) {
+        if (od == CDS_TF32) plain_tiles(Z{}, DT{}, M2{}); else plain_tiles(Z{}, DF{}, M2{});
       } else if (plain_ok && it == 0) {
-        using NG = std::false_type;
+        using NG = std::integral_constant<int, 0>;
         if (p.act == CDS_ACT_GELU_TANH) {
           if (od == CDS_BF16) plain_tiles(G{}, DB{}, NG{}); else if (od == CDS_TF32) plain_tiles(G{}, DT{}, NG{}); else plain_tiles(G{}, DF{}, NG{});
         } else {

@@ -216,6 +216,58 @@ __device__ __forceinline__ void ln_store4(const cds_lnmod_op& p, int64_t off, fl
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = v;
   }
 }
+// LPR lanes per row (32: one row per warp; 16: two rows per warp, each on a half-warp -- DiT1d's 320 channels are exactly
+// 16 lanes x 5 float4s, so no lane idles and twice as many rows are in flight), K float4s per lane
+template <int LPR, int K>
+__device__ __forceinline__ void ln_rows_vec(const cds_lnmod_op& p, int64_t n_rows, float inv_c) {
+  constexpr int RPW = 32 / LPR;                               // rows per warp
+  const int lane = threadIdx.x & 31, sub = lane / LPR, li = lane % LPR;
+  const int n4 = p.C >> 2;                                    // float4s per row
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r0 = warp0 * RPW; r0 < n_rows; r0 += nwarps * RPW) {
+    const int64_t r = r0 + sub;
+    const bool live = r < n_rows;
+    const int64_t rr = live ? r : n_rows - 1;                 // (idle half-warps shadow the last row: uniform shuffles, no store)
+    const float4* src = reinterpret_cast<const float4*>(p.in + rr * p.C);
+    const int b = (int)(rr / p.L);
+    const float4* sh = reinterpret_cast<const float4*>(p.shift + (int64_t)b * p.mod_bstride);
+    const float4* sc = reinterpret_cast<const float4*>(p.scale + (int64_t)b * p.mod_bstride);
+    float4 x[K];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int c4 = li + LPR * k;
+      x[k] = c4 < n4 ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (x[k].x + x[k].y) + (x[k].z + x[k].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (li + LPR * k < n4) {
+        const float d0 = x[k].x - mean, d1 = x[k].y - mean, d2 = x[k].z - mean, d3 = x[k].w - mean;
+        q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + p.eps);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int c4 = li + LPR * k;
+      if (c4 < n4 && live) {
+        const float4 a = __ldg(sc + c4), d = __ldg(sh + c4);
+        float4 o;
+        o.x = fmaf((x[k].x - mean) * rstd, 1.f + a.x, d.x); o.y = fmaf((x[k].y - mean) * rstd, 1.f + a.y, d.y);
+        o.z = fmaf((x[k].z - mean) * rstd, 1.f + a.z, d.z); o.w = fmaf((x[k].w - mean) * rstd, 1.f + a.w, d.w);
+        ln_store4(p, r * p.C + 4 * c4, o);
+      }
+    }
+  }
+}
+
 static __global__ void __launch_bounds__(256) ln_modulate_kernel(const cds_lnmod_op p) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -224,43 +276,10 @@ static __global__ void __launch_bounds__(256) ln_modulate_kernel(const cds_lnmod
   const bool vec = (p.C % 4 == 0) && p.C <= 128 * kLnVec && ((uintptr_t)p.in % 16 == 0) && ((uintptr_t)p.out % 16 == 0) &&
                    ((uintptr_t)p.shift % 16 == 0) && ((uintptr_t)p.scale % 16 == 0) && (p.mod_bstride % 4 == 0);
   if (vec) {
-    const int n4 = p.C >> 2;                                  // float4s per row
-    const int64_t warp0 = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * warps_per_block;
-    for (int64_t r = warp0; r < n_rows; r += nwarps) {
-      const float4* src = reinterpret_cast<const float4*>(p.in + r * p.C);
-      const int b = (int)(r / p.L);
-      const float4* sh = reinterpret_cast<const float4*>(p.shift + (int64_t)b * p.mod_bstride);
-      const float4* sc = reinterpret_cast<const float4*>(p.scale + (int64_t)b * p.mod_bstride);
-      float4 x[kLnVec];
-      float s = 0.f;
-#pragma unroll
-      for (int k = 0; k < kLnVec; ++k) {
-        const int c4 = lane + 32 * k;
-        x[k] = c4 < n4 ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        s += (x[k].x + x[k].y) + (x[k].z + x[k].w);
-      }
-      const float mean = warp_sum(s) * inv_c;
-      float q = 0.f;
-#pragma unroll
-      for (int k = 0; k < kLnVec; ++k) {
-        if (lane + 32 * k < n4) {
-          const float d0 = x[k].x - mean, d1 = x[k].y - mean, d2 = x[k].z - mean, d3 = x[k].w - mean;
-          q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
-        }
-      }
-      const float rstd = rsqrtf(warp_sum(q) * inv_c + p.eps);
-#pragma unroll
-      for (int k = 0; k < kLnVec; ++k) {
-        const int c4 = lane + 32 * k;
-        if (c4 < n4) {
-          const float4 a = __ldg(sc + c4), d = __ldg(sh + c4);
-          float4 o;
-          o.x = fmaf((x[k].x - mean) * rstd, 1.f + a.x, d.x); o.y = fmaf((x[k].y - mean) * rstd, 1.f + a.y, d.y);
-          o.z = fmaf((x[k].z - mean) * rstd, 1.f + a.z, d.z); o.w = fmaf((x[k].w - mean) * rstd, 1.f + a.w, d.w);
-          ln_store4(p, r * p.C + 4 * c4, o);
-        }
-      }
-    }
+    const int n4 = p.C >> 2;
+    if (n4 <= 16 * 3) ln_rows_vec<16, 3>(p, n_rows, inv_c);
+    else if (n4 <= 16 * 6 && n4 % 16 == 0) ln_rows_vec<16, 6>(p, n_rows, inv_c);
+    else ln_rows_vec<32, kLnVec>(p, n_rows, inv_c);
     return;
   }
   const bool in_regs = p.C <= 32 * kLnRegs;

@@ -582,6 +582,72 @@ def lower_idql(p: Program, net: nn.Module, x: View, has_cond: bool, in_batch_mod
     return p.conv(h, w_linear(fo.weight), out, bias=_const_vec(p.packed(lambda: fo.bias)))
 
 
+# =============================================================================== SfBCUNet
+def lower_sfbc(p: Program, net: nn.Module, x: View, has_cond: bool, in_batch_mod: int) -> View:
+    """sfbc_unet.py:9-82.  Every residual block is two fused operators:
+    ``h = silu(W1 x + b1) + linearc(c)`` (the conditioning enters as the post-activation shift: one row per iteration for the
+    time part, one per trajectory for the condition part, both evaluated once per call for all blocks) and
+    ``out = silu(W2 h + b2) + skip(x)`` (skip = the operator's shortcut GEMM, or an identity residual).
+    ``torch.cat([x, kept.pop()])`` costs nothing: the down block whose output is kept writes straight into the right-hand
+    channels of the up block's input buffer, the previous block into the left-hand ones."""
+    downs, ups = list(net.down_blocks), list(net.up_blocks)
+    blocks = downs + [net.mid_block] + ups
+    widths = [b.linearc.out_features for b in blocks]
+    offs = [sum(widths[:i]) for i in range(len(widths))]
+    total = sum(widths)
+    step_tab, samp_tab = p.buf(p.n_iters, total), p.buf(p.rows, total)
+
+    def fill(ctx):
+        wc = torch.cat([b.linearc.weight for b in blocks], 0)
+        bc = torch.cat([b.linearc.bias for b in blocks], 0)
+        step_tab.copy_(F.linear(net.t_layer(net.map_noise(ctx.t_all)), wc, bc))
+        if has_cond:
+            samp_tab.copy_(F.linear(ctx.cond_rows, wc))
+        else:
+            samp_tab.zero_()
+    p.per_call.append(fill)
+
+    n = len(downs)
+    # input buffers of the up blocks: [ x from below | kept down activation ]
+    cat_in = []
+    for j, b in enumerate(ups):
+        left = b.linear1[0].in_features - downs[n - 1 - j].linear1[0].out_features
+        cat_in.append((p.act(1, b.linear1[0].in_features), left))
+
+    def out_view(width, dest):
+        """Where a block's output goes: a fresh activation, or a channel range of an up block's input buffer."""
+        if dest is None:
+            return p.act(1, width)
+        buf, start = dest
+        return buf.channels(start, width)
+
+    def block(b, xin, o, dest, first=False):
+        width = b.linear1[0].out_features
+        h = p.act(1, width)
+        ibm = in_batch_mod if first else 0
+        p.conv(xin, w_linear(b.linear1[0].weight), h, bias=_const_vec(p.packed(lambda: b.linear1[0].bias)), act=cabi.ACT_SILU,
+               shift=_vec(step=step_tab, sample=samp_tab, col=o), in_batch_mod=ibm)
+        out = out_view(width, dest)
+        kw = dict(bias=_const_vec(p.packed(lambda: b.linear2[0].bias)), act=cabi.ACT_SILU, res_batch_mod=ibm)
+        if isinstance(b.skip, nn.Linear):
+            kw["res_conv"] = (xin, w_linear(b.skip.weight), lambda: b.skip.bias)
+        else:
+            kw["res"] = xin
+        return p.conv(h, w_linear(b.linear2[0].weight), out, **kw)
+
+    h = x
+    for i, b in enumerate(downs):
+        j = n - 1 - i                              # the up block that pops this activation (none for the first down block)
+        dest = (cat_in[j][0], cat_in[j][1]) if 0 <= j < len(ups) else None
+        h = block(b, h, offs[i], dest, first=(i == 0))
+    h = block(net.mid_block, h, offs[n], (cat_in[0][0], 0) if ups else None)
+    for j, b in enumerate(ups):
+        dest = (cat_in[j + 1][0], 0) if j + 1 < len(ups) else None
+        h = block(b, cat_in[j][0], offs[n + 1 + j], dest)
+    out = View(p.buf(p.rows, 1, x.C), 1, x.C)
+    return p.conv(h, w_linear(net.out_layer.weight), out, bias=_const_vec(p.packed(lambda: net.out_layer.bias)))
+
+
 # =============================================================================== DiT1d
 def lower_dit(p: Program, net: nn.Module, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
     d = net.d_model
@@ -671,6 +737,12 @@ def lower_denoiser(p: Program, net: nn.Module, x: View, x_shape, has_cond: bool,
         return lower_dit(p, net, x, x_shape[0], has_cond, in_batch_mod)
     if name == "DQLMlp" and len(x_shape) == 1:
         return lower_dql(p, net, x, has_cond, in_batch_mod)
+    if name == "DVInvMlp" and len(x_shape) == 1:
+        if not has_cond:
+            raise Unsupported("DVInvMlp needs a condition")         # the reference raises too (dvinvmlp.py:44)
+        return lower_dql(p, net, x, has_cond, in_batch_mod)         # same graph: cat[x, time_mlp(t), cond] -> 3 x (Linear + Mish) -> Linear
+    if name == "SfBCUNet" and len(x_shape) == 1:
+        return lower_sfbc(p, net, x, has_cond, in_batch_mod)
     if name == "IDQLMlp" and len(x_shape) == 1:
         return lower_idql(p, net, x, has_cond, in_batch_mod)
     raise Unsupported(f"backbone {name} with x_shape {tuple(x_shape)}")

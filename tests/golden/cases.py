@@ -38,6 +38,18 @@ NETS = {
         cls="IDQLMlp", ctor=dict(obs_dim=11, act_dim=3, emb_dim=32, hidden_dim=64, n_blocks=2),
         x=(3,), t="long", cond=(11,),
         oracle=dict(fn="idql_mlp", emb_dim=32, obs_dim=11, n_blocks=2)),
+    "dvinv_small": dict(
+        cls="DVInvMlp", ctor=dict(obs_dim=5, act_dim=3, emb_dim=16, hidden_dim=64),
+        x=(3,), t="long", cond=(10,),
+        oracle=dict(fn="dvinv_mlp", emb_dim=16)),
+    "sfbc_small": dict(
+        cls="SfBCUNet", ctor=dict(act_dim=3, emb_dim=32, hidden_dims=[64, 32, 32]),
+        x=(3,), t="float", cond=(32,),
+        oracle=dict(fn="sfbc_unet", emb_dim=32, n_layers=3)),
+    "sfbc_uncond": dict(
+        cls="SfBCUNet", ctor=dict(act_dim=6, emb_dim=16, hidden_dims=[32, 16]),
+        x=(6,), t="float", cond=None,
+        oracle=dict(fn="sfbc_unet", emb_dim=16, n_layers=2)),
     "dql_cfg1": dict(
         cls="DQLMlp", ctor=dict(obs_dim=11, act_dim=3, emb_dim=64),
         x=(3,), t="long", cond=(11,),

@@ -20,7 +20,7 @@ def _run_attn(qkv, heads, out_dtype):
     op.kind = cabi.OP_ATTN
     a = op.u.attn
     a.batch, a.L, a.C, a.heads = B, L, C3 // 3, heads
-    a.qkv = C.cast(qkv.data_ptr(), type(a.qkv))
+    a.qkv = qkv.data_ptr()
     a.out = out.data_ptr()
     a.out_dtype, a.qkv_dtype = out_dtype, cabi.TF32
     cabi.run_op(qkv.device.index or 0, op, 0, torch.cuda.current_stream().cuda_stream)
