@@ -206,7 +206,7 @@ int preload_kernels() {
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_f32_kernel<64>));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_mma_hd32_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_mma_tf32_hd32_kernel));
-  CDS_CUDA(cudaFuncSetAttribute(cds::attention_tma_tf32_hd32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  CDS_CUDA(cds::attention_tma_preload_all());
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::solver_update_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cm_prep_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cast_pad_kernel));
