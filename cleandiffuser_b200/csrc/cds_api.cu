@@ -13,6 +13,7 @@
 #include "conv_tc.cuh"
 #include "conv_ps.cuh"
 #include "attention_tma.cuh"
+#include "linear_ln.cuh"
 #include "elementwise.cuh"
 
 namespace {
@@ -62,6 +63,11 @@ struct Step {            // one validated operator + its kernel choice
   bool ps = false;       // ... served by the position-sliced kernel (short sequences, conv_ps.cuh)
   cds::ConvPsLaunch psl;
   cds::AttnTmaLaunch attl;   // TF32 attention: tensor maps of the persistent TMA-fed kernel (attention_tma.cuh)
+  // gated Linear directly followed by the LayerNorm+modulate that reads its output: ONE launch of linear_ln_kernel when both
+  // operators are in the executed range (the LNMOD step then carries fused_into_prev and is not launched)
+  bool fuse_ln = false;
+  bool fused_into_prev = false;
+  cds::LinLnLaunch lll;
 };
 
 int elementwise_grid(int64_t total, int sm_count) {
@@ -151,10 +157,11 @@ int validate(const cds_op& op, Step* out) {
   }
 }
 
-int launch(const Step& s, const int* iter_ptr, int sm_count, cudaStream_t st, int* advance = nullptr) {
+int launch(const Step& s, const int* iter_ptr, int sm_count, cudaStream_t st, int* advance = nullptr, bool fused = false) {
   switch (s.op.kind) {
     case CDS_OP_CONV:
-      if (s.ps) CDS_CUDA(cds::conv_ps_launch(s.psl, iter_ptr, st));
+      if (fused && s.fuse_ln) CDS_CUDA(cds::linear_ln_launch(s.lll, iter_ptr, sm_count, st));
+      else if (s.ps) CDS_CUDA(cds::conv_ps_launch(s.psl, iter_ptr, st));
       else if (s.tc) CDS_CUDA(cds::conv_tc_launch(s.tcl, iter_ptr, st));
       else CDS_CUDA(cds::conv_simt_launch(s.op.u.conv, s.conv_bn, iter_ptr, st));
       return CDS_OK;
@@ -207,6 +214,7 @@ int preload_kernels() {
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_mma_hd32_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::attention_mma_tf32_hd32_kernel));
   CDS_CUDA(cds::attention_tma_preload_all());
+  CDS_CUDA(cds::linear_ln_preload_all());
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::solver_update_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cm_prep_kernel));
   CDS_CUDA(cudaFuncGetAttributes(&a, cds::cast_pad_kernel));
@@ -338,6 +346,19 @@ int cds_plan_finalize(cds_plan* p, int32_t n_iters) {
     // the branches share the machine: one CTA per SM and kernel, so that kernels of different branches co-reside
     for (Step& s : p->steps) if (s.tc && !s.ps) s.tcl.max_ctas_per_sm = 1;
   }
+  // peephole: gated Linear + the LayerNorm that consumes it -> one launch (linear_ln.cuh)
+  if (p->n_branches == 1) {
+    for (size_t i = 0; i + 1 < p->steps.size(); ++i) {
+      Step& a = p->steps[i];
+      Step& b = p->steps[i + 1];
+      if (a.op.kind != CDS_OP_CONV || b.op.kind != CDS_OP_LNMOD || !a.tc || a.ps) continue;
+      if ((a.op.flags & CDS_OPF_ONCE) || (b.op.flags & CDS_OPF_ONCE)) continue;
+      if (!cds::linear_ln_eligible(a.op.u.conv, b.op.u.lnmod)) continue;
+      if (!cds::linear_ln_prepare(a.op.u.conv, b.op.u.lnmod, &a.lll)) continue;
+      a.fuse_ln = true;
+      b.fused_into_prev = true;
+    }
+  }
   p->finalized = true;
   return CDS_OK;
 }
@@ -367,8 +388,8 @@ static int enqueue_iteration(cds_plan* p, cudaStream_t st) {
     for (int i = 0; i < (int)p->steps.size(); ++i) if (!(p->steps[i].op.flags & CDS_OPF_ONCE)) last = i;
     for (int i = 0; i < (int)p->steps.size(); ++i) {
       const Step& s = p->steps[i];
-      if ((s.op.flags & CDS_OPF_ONCE) || s.skip) continue;
-      int rc = launch(s, p->d_iter, p->sm_count, st, (fused && i == last) ? p->d_iter : nullptr);
+      if ((s.op.flags & CDS_OPF_ONCE) || s.skip || s.fused_into_prev) continue;
+      int rc = launch(s, p->d_iter, p->sm_count, st, (fused && i == last) ? p->d_iter : nullptr, true);
       if (rc != CDS_OK) return rc;
     }
   } else {
@@ -462,7 +483,10 @@ int cds_plan_run_range(cds_plan* p, int32_t iter, int32_t op_first, int32_t op_c
   for (int i = op_first; i < op_first + op_count; ++i) {
     const Step& s = p->steps[i];
     if ((s.op.flags & CDS_OPF_ONCE) || s.skip) continue;
-    int rc = launch(s, p->d_iter, p->sm_count, st, nullptr);
+    // a fused pair runs as one launch only when the range holds both halves
+    if (s.fused_into_prev && i > op_first) continue;
+    const bool both = s.fuse_ln && i + 1 < op_first + op_count;
+    int rc = launch(s, p->d_iter, p->sm_count, st, nullptr, both);
     if (rc != CDS_OK) return rc;
   }
   return CDS_OK;
@@ -482,8 +506,8 @@ int cds_plan_profile(cds_plan* p, int32_t iter, void* stream, float* ms_per_op, 
       const bool once = (p->steps[i].op.flags & CDS_OPF_ONCE) != 0;
       if (once != (pass == 0)) continue;
       CDS_CUDA(cudaEventRecord(ev[2 * i], st));
-      if (!p->steps[i].skip) {
-        int rc = launch(p->steps[i], p->d_iter, p->sm_count, st);
+      if (!p->steps[i].skip && !p->steps[i].fused_into_prev) {
+        int rc = launch(p->steps[i], p->d_iter, p->sm_count, st, nullptr, true);
         if (rc != CDS_OK) return rc;
       }
       CDS_CUDA(cudaEventRecord(ev[2 * i + 1], st));
@@ -498,7 +522,7 @@ int cds_plan_profile(cds_plan* p, int32_t iter, void* stream, float* ms_per_op, 
 int cds_plan_launches_per_iter(const cds_plan* p) {
   if (!p) return 0;
   int n = advance_fused(p) ? 0 : 1;
-  for (const Step& s : p->steps) if (!(s.op.flags & CDS_OPF_ONCE) && !s.skip) ++n;
+  for (const Step& s : p->steps) if (!(s.op.flags & CDS_OPF_ONCE) && !s.skip && !s.fused_into_prev) ++n;
   return n;
 }
 

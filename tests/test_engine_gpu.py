@@ -356,3 +356,29 @@ def test_dit_full_size_on_tensor_cores(monkeypatch):
     lower_denoiser(p, net, View(p.buf(B, L, 29), L, 29), (L, 29), True, 0)
     assert sum(1 for op in p.ops if op.kind == cabi.OP_CONV and op.u.conv.math == cabi.MATH_BF16_TC) == 10
     assert all(op.u.attn.qkv_dtype == cabi.BF16 for op in p.ops if op.kind == cabi.OP_ATTN)
+
+
+@pytest.mark.parametrize("d_model,heads", [(320, 10), (256, 8)])
+def test_dit_fused_linear_layernorm_matches_the_two_launch_form(d_model, heads, monkeypatch):
+    """TF32 programs fuse `gated Linear -> LayerNorm + modulate` pairs into one launch at plan-finalize time (csrc/linear_ln.cuh);
+    CDS_FUSE_LN=0 keeps the two launches.  Same arithmetic up to summation order: the two forms must agree far inside the TF32
+    tolerance, and both must match the module's fp32 forward.  37 x 100 = 3700 token rows: ragged last 128-row tile."""
+    monkeypatch.setenv("CDS_MATH", "tf32")
+    from cleandiffuser_b200.nn_diffusion import DiT1d
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(3)
+    B, L = 37, 100
+    x, cond = torch.randn(B, L, 29, generator=g).to(DEV), torch.randn(B, 128, generator=g).to(DEV)
+    t = torch.tensor([0.37], device=DEV)
+    outs, launches = {}, {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("CDS_FUSE_LN", fuse)
+        net = load_synth(DiT1d(29, emb_dim=128, d_model=d_model, n_heads=heads, depth=2, timestep_emb_type="fourier"), seed=0).eval().to(DEV)
+        with torch.no_grad():
+            want = net(x, t.expand(B), cond)
+        outs[fuse] = runtime.engine_forward(net, x, t, cond)
+        err = (outs[fuse] - want).abs()
+        assert torch.isfinite(outs[fuse]).all()
+        assert err.max().item() < TF32_MAX and err.mean().item() < TF32_MEAN, (fuse, err.max().item(), err.mean().item())
+    d = (outs["1"] - outs["0"]).abs()
+    assert d.max().item() < 2e-3, d.max().item()
