@@ -10,13 +10,16 @@
 //     kernel's 160-wide column tiles re-stage it per tile), which is what the shared-memory-bound TF32 main loop cares about;
 //   * the separate LayerNorm launch (read X, write Y: 8 bytes per element of HBM traffic, ~230 us per call at cfg4's size)
 //     disappears: X never leaves the SM between the two.
-// Epilogue, 8 warps (TMEM lane quarter q = warp & 3, column half hh = warp >> 2), two passes over the thread's NH columns:
-//   1. x = (acc + bias) * gate + residual; x goes back into TMEM (tcgen05.st) and, through the warp's staging rows (two
-//      buffers) + one bulk tensor store per 16 columns, to X; row moments about a pivot (the row's first x: no cancellation),
-//      the two halves' (mean, M2) combine exactly in shared memory -> mean, rstd
-//   2. y = (x - mean) * rstd * (1 + scale) + shift -> Y (rounded to TF32 when Y feeds the next tensor-core Linear)
+// Epilogue, 8 warps (TMEM lane quarter q = warp & 3, column half hh = warp >> 2), two passes over the thread's NH columns; the
+// accumulator is released after the FIRST one, so the next tile's main loop overlaps the second:
+//   1. x = (acc + bias) * gate + residual.  The residual arrives by TMA, 16 columns x 32 rows per warp and request, one request
+//      ahead (a thread walking its own 1280-byte-pitch row with ld.global costs 13 us per tile: scripts/micro/store_patterns.cu
+//      v5 is the store-side twin of that pattern); x is computed IN PLACE in that buffer and bulk-stored from it to X; row moments
+//      about a pivot (the row's first x: no cancellation), the two halves' (mean, M2) combine exactly in shared memory
+//   2. the x chunks come back by TMA from the X just written (L2 hits; each request waits for the completion of that chunk's
+//      store): y = (x - mean) * rstd * (1 + scale) + shift, in place, bulk-stored to Y (rounded to TF32 when Y feeds a Linear)
 // The accumulator is single-buffered (2 NH <= 512 TMEM columns leave no room for a second one): the MMA of the next tile waits
-// for pass 2, the producer keeps prefetching operand stages meanwhile.
+// for pass 1 only, the producer keeps prefetching operand stages meanwhile.
 // Algorithmic HBM bytes per row: 4 K (A) + 4 C (R) + 4 C (X) + 4 C (Y);  flops per row: 2 K C.
 #pragma once
 #include "conv_tc.cuh"
@@ -25,9 +28,10 @@ namespace cds {
 
 constexpr int kLlThreads = 320;                      // warps 0-7 epilogue, 8 producer, 9 MMA + TMEM owner
 constexpr int kLlEpiThreads = 256;
+constexpr int kLlAhead = 4;                          // steps between the request of a per-trajectory vector chunk and its use
 
 struct LinLnParams {
-  CUtensorMap tm_a, tm_b, tm_x, tm_y;
+  CUtensorMap tm_a, tm_b, tm_x, tm_y, tm_r, tm_rp, tm_xl;   // tm_xl: X as a load source (pass 2 re-reads what pass 1 stored)   // tm_rp: the residual again, box {NH, 32}, for L2 prefetches
   int rows, K, C, L;                                 // L = tokens per trajectory
   const float* bias; int64_t bias_step_stride;       // bias row of iteration i = bias + i * stride
   const float* gate; int64_t gate_stride;            // per trajectory
@@ -50,7 +54,7 @@ struct LinLnCfg {
   static constexpr int kStageA = 128 * 128;                           // 128 rows x 32 fp32
   static constexpr int kStageB = 2 * NH * 128;                        // 2 NH weight rows x 32 fp32
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStaging = 8 * 2 * 2048;                       // per epilogue warp: two buffers of 32 rows x 16 fp32
+  static constexpr int kStaging = 8 * 3 * 2048;                       // per epilogue warp: three buffers of 32 rows x 16 fp32
   static constexpr int kSmemBytes = kStages * kStage + kStaging + 1024;
   static_assert(NH % 16 == 0 && NH >= 16 && NH <= 256, "column half");
   static_assert((NH * 128) % 1024 == 0, "the second weight half must start on a swizzle atom");
@@ -76,7 +80,8 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
   __shared__ __align__(8) uint64_t full_bar[Cfg::kStages], empty_bar[Cfg::kStages], tmem_full_bar, tmem_empty_bar;
   __shared__ uint32_t tmem_base_holder;
   __shared__ __align__(16) float s_bias[C];
-  __shared__ float s_red[2][2][128];
+  __shared__ float s_red[2][2][2][128];            // [tile parity][mean | M2][column half][row]
+  __shared__ __align__(8) uint64_t res_bar[8][3];
   const uint32_t base_u = (ptx::smem_u32(ll_smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = ll_smem_raw + (base_u - ptx::smem_u32(ll_smem_raw));
   uint8_t* s_stage = sm + Cfg::kStages * Cfg::kStage;
@@ -87,9 +92,10 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
     for (int s = 0; s < Cfg::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     ptx::mbar_init(&tmem_full_bar, 1);
     ptx::mbar_init(&tmem_empty_bar, 8);
+    for (int w = 0; w < 8; ++w) for (int j = 0; j < 3; ++j) ptx::mbar_init(&res_bar[w][j], 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&p.tm_a); ptx::prefetch_tensormap(&p.tm_b);
-    ptx::prefetch_tensormap(&p.tm_x); ptx::prefetch_tensormap(&p.tm_y);
+    ptx::prefetch_tensormap(&p.tm_x); ptx::prefetch_tensormap(&p.tm_y); ptx::prefetch_tensormap(&p.tm_r); ptx::prefetch_tensormap(&p.tm_xl);
   }
   if (warp == 9) ptx::tmem_alloc<kTmemCols>(&tmem_base_holder);
   ptx::tc_fence_before_sync();
@@ -144,117 +150,173 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
     const int m = 32 * q + lane;
     for (int i = threadIdx.x; i < C; i += kLlEpiThreads) s_bias[i] = p.bias[(int64_t)(*iter_ptr) * p.bias_step_stride + i];
     ptx::named_bar_sync(1, kLlEpiThreads);
-    uint8_t* const stg = s_stage + warp * 4096;
-    uint8_t* const sr = stg + lane * 64;
+    // three rotating 2 KB buffers per warp (32 rows x 16 fp32, SWIZZLE_64B).  Use number u works in buffer u % 3: in pass 1 the
+    // residual chunk is TMA-LOADED into it (requested one use ahead), x is computed in place and TMA-stored from it; in pass 2
+    // it is plain staging for Y.  A buffer is reloaded / rewritten only after the store issued three uses earlier has read it.
+    uint8_t* const stg = s_stage + warp * 6144;
     const int sw = (lane >> 1) & 3;
+    const uint32_t lane_off = (uint32_t)lane * 64u;
     const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(hh * NH);
     const float inv_c = 1.f / (float)C;
-    uint32_t t = 0, nst = 0;                           // tiles done, bulk stores issued by this warp (staging buffer = nst & 1)
+    uint64_t* const rbar = &res_bar[warp][0];
+    uint32_t t = 0, u = 0, par = 0;                    // tiles done, buffer uses, phase bit of each buffer's load barrier
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
       const int64_t grow = (int64_t)tile * 128 + m;
-      const bool valid = grow < p.rows;
-      const int64_t traj = (valid ? grow : (int64_t)p.rows - 1) / p.L;
-      const float* gate = p.gate + traj * p.gate_stride + hh * NH;
-      const float* res = p.res + (valid ? grow : 0) * p.res_stride + hh * NH;
+      const int row0 = tile * 128 + 32 * q;
+      // Per-trajectory vectors (gate in pass 1; scale, shift in pass 2).  A warp's 32 rows touch at most two trajectories (L >= 32):
+      // lanes 0-15 fetch 16 consecutive elements of the first one's vector, lanes 16-31 of the second one's -- ONE coalesced load
+      // per vector and step, issued kLlAhead steps before its use and handed out by shuffles.  (A thread loading its own copy made
+      // every 16-column step wait for an L2 / HBM round trip: ncu put 11 % of all stall samples on the first use of `scale`.)
+      const int64_t last_traj = ((int64_t)p.rows - 1) / p.L;
+      const int64_t traj_a = min((int64_t)row0 / p.L, last_traj);
+      const int64_t traj = min(grow / p.L, last_traj);
+      const int sel = traj != traj_a ? 16 : 0;          // which half of the warp holds this row's values
+      const int64_t traj_ld = (lane < 16) ? traj_a : min(traj_a + 1, last_traj);
+      const float* gate_ld = p.gate + traj_ld * p.gate_stride + hh * NH + (lane & 15);
+      const float* scp_ld = p.scale + traj_ld * p.mod_stride + hh * NH + (lane & 15);
+      const float* shp_ld = p.shift + traj_ld * p.mod_stride + hh * NH + (lane & 15);
+      float gq[kLlAhead], aq[kLlAhead], dq[kLlAhead];
+#pragma unroll
+      for (int j = 0; j < kLlAhead; ++j) aq[j] = dq[j] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kLlAhead; ++j) gq[j] = (j < NH / 16) ? __ldg(gate_ld + 16 * j) : 0.f;
+      if (lane == 0) {                                 // residual chunks 0..2: in flight while the main loop runs
+        ptx::bulk_wait_group_read<0>();
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (j < NH / 16) {
+            const uint32_t bj = (u + j) % 3;
+            ptx::mbar_expect_tx(&rbar[bj], 2048u);
+            ptx::tma_load_2d(stg + bj * 2048, &p.tm_r, &rbar[bj], hh * NH + 16 * j, row0);
+          }
+        }
+        // ... and the next tile's residual rows of this warp are pulled into L2 (they were written several launches ago)
+        const int nt = tile + (int)gridDim.x;
+        if (nt < p.num_tiles) ptx::tma_prefetch_2d(&p.tm_rp, hh * NH, nt * 128 + 32 * q);
+      }
       ptx::mbar_wait(&tmem_full_bar, t & 1u);
       ptx::tc_fence_after_sync();
-      // ---- pass 1: x = (acc + bias) * gate + residual -> TMEM, X; shifted row moments.  The residual / gate rows of chunk ch + 1
-      // are requested before chunk ch is processed (each thread walks its own row: the loads are latency-, not bandwidth-bound).
+      // ---- pass 1: x = (acc + bias) * gate + residual -> TMEM, X; shifted row moments
       float sh0 = 0.f, sd = 0.f, sdd = 0.f;            // pivot (the row's first x of this half), sum (x - pivot), sum (x - pivot)^2
-      float4 rn[4], gn[4];
-      {
-        const float4* g4 = reinterpret_cast<const float4*>(gate);
-        const float4* r4 = reinterpret_cast<const float4*>(res);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { gn[k] = __ldg(g4 + k); rn[k] = valid ? r4[k] : make_float4(0.f, 0.f, 0.f, 0.f); }
-      }
 #pragma unroll 1
-      for (int ch = 0; ch < NH / 16; ++ch) {
-        float4 r[4], g[4];
+      for (int ch = 0; ch < NH / 16; ++ch, ++u) {
+        const uint32_t b = u % 3;
+        uint8_t* const buf = stg + b * 2048;
+        const float gcur = gq[0];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { r[k] = rn[k]; g[k] = gn[k]; }
-        if (ch + 1 < NH / 16) {
-          const float4* g4 = reinterpret_cast<const float4*>(gate + 16 * (ch + 1));
-          const float4* r4 = reinterpret_cast<const float4*>(res + 16 * (ch + 1));
+        for (int j = 0; j + 1 < kLlAhead; ++j) gq[j] = gq[j + 1];
+        gq[kLlAhead - 1] = (ch + kLlAhead < NH / 16) ? __ldg(gate_ld + 16 * (ch + kLlAhead)) : 0.f;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { gn[k] = __ldg(g4 + k); rn[k] = valid ? r4[k] : make_float4(0.f, 0.f, 0.f, 0.f); }
+        for (int j = 0; j + 1 < kLlAhead; ++j) { aq[j] = aq[j + 1]; dq[j] = dq[j + 1]; }
+        if (ch + kLlAhead >= NH / 16) {                // pass 2's first kLlAhead chunks are requested by pass 1's last steps
+          const int j2 = ch + kLlAhead - NH / 16;
+          aq[kLlAhead - 1] = __ldg(scp_ld + 16 * j2); dq[kLlAhead - 1] = __ldg(shp_ld + 16 * j2);
         }
         float v[16];
         ptx::tmem_ld<16>(t_row + (uint32_t)(16 * ch), v);
+        ptx::mbar_wait(&rbar[b], (par >> b) & 1u);
+        par ^= 1u << b;
         const float4* b4 = reinterpret_cast<const float4*>(&s_bias[hh * NH + 16 * ch]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float4 bb = b4[k];
-          v[4 * k] = fmaf(v[4 * k] + bb.x, g[k].x, r[k].x); v[4 * k + 1] = fmaf(v[4 * k + 1] + bb.y, g[k].y, r[k].y);
-          v[4 * k + 2] = fmaf(v[4 * k + 2] + bb.z, g[k].z, r[k].z); v[4 * k + 3] = fmaf(v[4 * k + 3] + bb.w, g[k].w, r[k].w);
+          const float4 r = *reinterpret_cast<const float4*>(buf + lane_off + ((k ^ sw) << 4));
+          v[4 * k] = fmaf(v[4 * k] + bb.x, __shfl_sync(0xffffffffu, gcur, sel + 4 * k), r.x);
+          v[4 * k + 1] = fmaf(v[4 * k + 1] + bb.y, __shfl_sync(0xffffffffu, gcur, sel + 4 * k + 1), r.y);
+          v[4 * k + 2] = fmaf(v[4 * k + 2] + bb.z, __shfl_sync(0xffffffffu, gcur, sel + 4 * k + 2), r.z);
+          v[4 * k + 3] = fmaf(v[4 * k + 3] + bb.w, __shfl_sync(0xffffffffu, gcur, sel + 4 * k + 3), r.w);
         }
         if (ch == 0) sh0 = v[0];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const float d = v[j] - sh0; sd += d; sdd = fmaf(d, d, sdd); }
-        tmem_st16(t_row + (uint32_t)(16 * ch), v);
-        uint8_t* const srb = sr + (nst & 1u) * 2048;
-        if (lane == 0) ptx::bulk_wait_group_read<1>();          // the store issued two chunks ago has read this staging buffer
-        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 4; ++k) {                  // x over the residual it came from (same thread, same bytes)
           float4 o4;
           if (p.x_dtype == CDS_TF32) o4 = make_float4(round_tf32(v[4 * k]), round_tf32(v[4 * k + 1]), round_tf32(v[4 * k + 2]), round_tf32(v[4 * k + 3]));
           else o4 = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-          *reinterpret_cast<float4*>(srb + ((k ^ sw) << 4)) = o4;
+          *reinterpret_cast<float4*>(buf + lane_off + ((k ^ sw) << 4)) = o4;
+        }
+        if (ch >= 1 && ch + 2 < NH / 16 && lane == 0) {
+          // the buffer of the previous step is free once its X store has read it (issued a whole step ago): residual chunk
+          // ch + 2 goes there, two steps ahead of its use
+          const uint32_t bp = (u + 2) % 3;
+          ptx::bulk_wait_group_read<0>();
+          ptx::mbar_expect_tx(&rbar[bp], 2048u);
+          ptx::tma_load_2d(stg + bp * 2048, &p.tm_r, &rbar[bp], hh * NH + 16 * (ch + 2), row0);
         }
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          ptx::tma_store_2d(&p.tm_x, stg + (nst & 1u) * 2048, hh * NH + 16 * ch, tile * 128 + 32 * q);
+          ptx::tma_store_2d(&p.tm_x, buf, hh * NH + 16 * ch, row0);
           ptx::bulk_commit_group();
         }
-        ++nst;
       }
-      tmem_st_wait();
-      // this half's (mean, M2) from the shifted moments; the two halves combine exactly (Chan et al.): M2 = M2a + M2b + d^2 n / 2
-      {
-        const float mh = sd * (1.f / (float)NH);
-        s_red[0][hh][m] = sh0 + mh;
-        s_red[1][hh][m] = fmaf(-sd, mh, sdd);
-      }
-      ptx::named_bar_sync(1, kLlEpiThreads);
-      const float ma = s_red[0][0][m], mb = s_red[0][1][m];
-      const float mean = 0.5f * (ma + mb);
-      const float m2 = s_red[1][0][m] + s_red[1][1][m] + (mb - ma) * (mb - ma) * (0.5f * (float)NH);
-      const float rstd = rsqrtf(fmaxf(m2, 0.f) * inv_c + p.eps);
-      // (s_red is rewritten only in the next tile's pass 1, i.e. after every warp has arrived on tmem_empty_bar below)
-      // ---- pass 2: normalise, modulate -> Y
-      const float* scp = p.scale + traj * p.mod_stride + hh * NH;
-      const float* shp = p.shift + traj * p.mod_stride + hh * NH;
-#pragma unroll 1
-      for (int ch = 0; ch < NH / 16; ++ch) {
-        float v[16];
-        ptx::tmem_ld<16>(t_row + (uint32_t)(16 * ch), v);
-        const float4* a4 = reinterpret_cast<const float4*>(scp + 16 * ch);
-        const float4* d4 = reinterpret_cast<const float4*>(shp + 16 * ch);
-        uint8_t* const srb = sr + (nst & 1u) * 2048;
-        if (lane == 0) ptx::bulk_wait_group_read<1>();
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float4 a = __ldg(a4 + k), d = __ldg(d4 + k);
-          float4 o4;
-          o4.x = fmaf((v[4 * k] - mean) * rstd, 1.f + a.x, d.x); o4.y = fmaf((v[4 * k + 1] - mean) * rstd, 1.f + a.y, d.y);
-          o4.z = fmaf((v[4 * k + 2] - mean) * rstd, 1.f + a.z, d.z); o4.w = fmaf((v[4 * k + 3] - mean) * rstd, 1.f + a.w, d.w);
-          if (p.y_dtype == CDS_TF32) o4 = make_float4(round_tf32(o4.x), round_tf32(o4.y), round_tf32(o4.z), round_tf32(o4.w));
-          *reinterpret_cast<float4*>(srb + ((k ^ sw) << 4)) = o4;
-        }
-        ptx::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::tma_store_2d(&p.tm_y, stg + (nst & 1u) * 2048, hh * NH + 16 * ch, tile * 128 + 32 * q);
-          ptx::bulk_commit_group();
-        }
-        ++nst;
-      }
+      // the accumulator has been read: the MMA of the next tile may overwrite it while pass 2 runs
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar);
+      // this half's (mean, M2) from the shifted moments; the two halves combine exactly (Chan et al.): M2 = M2a + M2b + d^2 n / 2
+      {
+        const float mh = sd * (1.f / (float)NH);
+        s_red[t & 1][0][hh][m] = sh0 + mh;
+        s_red[t & 1][1][hh][m] = fmaf(-sd, mh, sdd);
+      }
+      // X chunks 0..2 come back (from L2) into the three buffers: their stores must have COMPLETED (written), every store must
+      // have read its buffer.  Committed groups of this thread at this point: ..., X(0) .. X(NCH-1).
+      if (lane == 0) {
+        ptx::bulk_wait_group_read<0>();
+        ptx::bulk_wait_group<NH / 16 - 3>();
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const uint32_t bj = (u + j) % 3;
+          ptx::mbar_expect_tx(&rbar[bj], 2048u);
+          ptx::tma_load_2d(stg + bj * 2048, &p.tm_xl, &rbar[bj], hh * NH + 16 * j, row0);
+        }
+      }
+      ptx::named_bar_sync(1, kLlEpiThreads);
+      const float ma = s_red[t & 1][0][0][m], mb = s_red[t & 1][0][1][m];
+      const float mean = 0.5f * (ma + mb);
+      const float m2 = s_red[t & 1][1][0][m] + s_red[t & 1][1][1][m] + (mb - ma) * (mb - ma) * (0.5f * (float)NH);
+      const float rstd = rsqrtf(fmaxf(m2, 0.f) * inv_c + p.eps);
+      // (s_red is double-buffered by tile parity: a warp may be a whole pass ahead of another one, never two tiles)
+      // ---- pass 2: x (re-read from X, 16 columns x 32 rows per request, two steps ahead) -> normalise, modulate in place -> Y
+#pragma unroll 1
+      for (int ch = 0; ch < NH / 16; ++ch, ++u) {
+        const uint32_t b = u % 3;
+        uint8_t* const buf = stg + b * 2048;
+        const float acur = aq[0], dcur = dq[0];
+#pragma unroll
+        for (int j = 0; j + 1 < kLlAhead; ++j) { aq[j] = aq[j + 1]; dq[j] = dq[j + 1]; }
+        if (ch + kLlAhead < NH / 16) { aq[kLlAhead - 1] = __ldg(scp_ld + 16 * (ch + kLlAhead)); dq[kLlAhead - 1] = __ldg(shp_ld + 16 * (ch + kLlAhead)); }
+        ptx::mbar_wait(&rbar[b], (par >> b) & 1u);
+        par ^= 1u << b;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 x = *reinterpret_cast<const float4*>(buf + lane_off + ((k ^ sw) << 4));
+          float4 o4;
+          o4.x = fmaf((x.x - mean) * rstd, 1.f + __shfl_sync(0xffffffffu, acur, sel + 4 * k), __shfl_sync(0xffffffffu, dcur, sel + 4 * k));
+          o4.y = fmaf((x.y - mean) * rstd, 1.f + __shfl_sync(0xffffffffu, acur, sel + 4 * k + 1), __shfl_sync(0xffffffffu, dcur, sel + 4 * k + 1));
+          o4.z = fmaf((x.z - mean) * rstd, 1.f + __shfl_sync(0xffffffffu, acur, sel + 4 * k + 2), __shfl_sync(0xffffffffu, dcur, sel + 4 * k + 2));
+          o4.w = fmaf((x.w - mean) * rstd, 1.f + __shfl_sync(0xffffffffu, acur, sel + 4 * k + 3), __shfl_sync(0xffffffffu, dcur, sel + 4 * k + 3));
+          if (p.y_dtype == CDS_TF32) o4 = make_float4(round_tf32(o4.x), round_tf32(o4.y), round_tf32(o4.z), round_tf32(o4.w));
+          *reinterpret_cast<float4*>(buf + lane_off + ((k ^ sw) << 4)) = o4;
+        }
+        if (ch >= 1 && ch + 2 < NH / 16 && lane == 0) {
+          // X chunk ch + 2 into the previous step's buffer: that step's Y store has read it; the X store of chunk ch + 2 is complete
+          // when at most (NCH - 1 - (ch + 2)) + ch = NCH - 3 younger groups are pending
+          const uint32_t bp = (u + 2) % 3;
+          ptx::bulk_wait_group_read<0>();
+          ptx::bulk_wait_group<NH / 16 - 3>();
+          ptx::mbar_expect_tx(&rbar[bp], 2048u);
+          ptx::tma_load_2d(stg + bp * 2048, &p.tm_xl, &rbar[bp], hh * NH + 16 * (ch + 2), row0);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&p.tm_y, buf, hh * NH + 16 * ch, row0);
+          ptx::bulk_commit_group();
+        }
+      }
     }
     if (lane == 0) ptx::bulk_wait_group<0>();
   }
@@ -283,7 +345,7 @@ inline bool linear_ln_eligible(const cds_conv_op& c, const cds_lnmod_op& l) {
   if (!c.bias.step || c.bias.sample) return false;
   if (!c.scale.sample || c.scale.step || c.shift.step || c.shift.sample) return false;
   if (!c.res || c.res_w || c.res_batch_mod != 0 || c.res_bstride % 4 != 0) return false;
-  if (c.sample_row_div < 1) return false;
+  if (c.sample_row_div < 32) return false;             // (a warp's 32 rows then span at most two trajectories)
   if (c.scale.sample_stride % 4 != 0 || ((uintptr_t)c.scale.sample % 16) || ((uintptr_t)c.res % 16) || ((uintptr_t)c.bias.step % 4)) return false;
   if (((uintptr_t)c.in % 16) || ((uintptr_t)c.w % 16) || ((uintptr_t)c.out % 16)) return false;
   // the LayerNorm that follows
@@ -321,6 +383,9 @@ inline bool linear_ln_prepare(const cds_conv_op& c, const cds_lnmod_op& l, LinLn
   if (!linear_ln_encode_2d(&p.tm_a, c.in, (uint64_t)c.C_in, (uint64_t)c.batch, (uint64_t)c.C_in * 4, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
   if (!linear_ln_encode_2d(&p.tm_b, c.w, (uint64_t)c.C_in, (uint64_t)c.C_out, (uint64_t)c.C_in * 4, 32, (uint32_t)L.nh, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
   if (!linear_ln_encode_2d(&p.tm_x, c.out, (uint64_t)c.C_out, (uint64_t)c.batch, (uint64_t)c.C_out * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
+  if (!linear_ln_encode_2d(&p.tm_r, c.res, (uint64_t)c.C_out, (uint64_t)c.batch, (uint64_t)c.res_bstride * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
+  if (!linear_ln_encode_2d(&p.tm_rp, c.res, (uint64_t)c.C_out, (uint64_t)c.batch, (uint64_t)c.res_bstride * 4, (uint32_t)L.nh, 32, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
+  p.tm_xl = p.tm_x;
   if (!linear_ln_encode_2d(&p.tm_y, l.out, (uint64_t)c.C_out, (uint64_t)c.batch, (uint64_t)c.C_out * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
   L.ok = true;
   return true;

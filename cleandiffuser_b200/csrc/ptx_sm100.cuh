@@ -80,6 +80,10 @@ __device__ __forceinline__ void cluster_sync() {
 // TMA store (tile mode, bulk-group completion): shared -> global box at the given coordinates; out-of-bound parts of the box
 // are clipped by the TMA unit.  The shared-memory source must have been written with the tensor map's swizzle and made
 // visible to the async proxy (fence_proxy_async) before the issue.
+// pull a box into L2 without a destination (no completion mechanism: a hint)
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_u32(smem_src)),
                "r"(c0), "r"(c1)
