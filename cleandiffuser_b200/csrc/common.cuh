@@ -47,6 +47,8 @@ __device__ __forceinline__ float apply_act(int act, float x) {
     case CDS_ACT_SILU: return act_silu(x);
     case CDS_ACT_GELU_TANH: return act_gelu_tanh(x);
     case CDS_ACT_MISH_SILU: return act_silu(act_mish(x));
+    case CDS_ACT_LEAKY_RELU: return x > 0.f ? x : 0.01f * x;
+    case CDS_ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.7071067811865476f));
     default: return x;
   }
 }

@@ -109,6 +109,8 @@ __device__ __forceinline__ float tc_act(int act, float x) {
       case CDS_ACT_GELU_TANH: { float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);   // 0.5 (1 + tanh(u)) = sigmoid(2u)
                                 return x * fast_sigmoid(2.f * u); }
       case CDS_ACT_MISH_SILU: { float m = fast_mish(x); return m * fast_sigmoid(m); }
+      case CDS_ACT_LEAKY_RELU: return x > 0.f ? x : 0.01f * x;
+      case CDS_ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.7071067811865476f));
       default: return x;
     }
   }

@@ -648,6 +648,71 @@ def lower_sfbc(p: Program, net: nn.Module, x: View, has_cond: bool, in_batch_mod
     return p.conv(h, w_linear(net.out_layer.weight), out, bias=_const_vec(p.packed(lambda: net.out_layer.bias)))
 
 
+# =============================================================================== PearceMlp
+def lower_pearce(p: Program, net: nn.Module, x: View, has_cond: bool, in_batch_mod: int) -> View:
+    """pearcemlp.py:35-79.  Every Linear over a concatenation splits by column blocks, like DQLMlp's first layer:
+      fcs[0]  W [x_e | t_e | cond]      = W_xe x_e  + (W_te map_noise(t) + b: one row per iteration) + (W_c cond: one row per trajectory)
+      fcs[k]  W [nn/1.414 | x | t]      = (W_h / c) v + (x W_x^T: one row per trajectory AND iteration, a small GEMM ahead of the
+                                          blocks, all three layers at once) + (w_t t + b: one row per iteration)
+    The residual chain ``nn_{k+1} = FC_k(nn_k / 1.414, ..) + nn_k / 1.414`` is carried as ``v_k = 1.414^(k-1) nn_k`` so that every
+    residual has coefficient one: ``v_{k+1} = 1.414^k FC_k + v_k`` (a constant output scale), the 1 / 1.414^k go into the packed
+    weights of the Linear that reads ``v_k``.  FCBlock = Linear + GroupNorm1d + exact GELU = one operator."""
+    act_dim, emb, To = x.C, net.emb_dim, net.To
+    fc0, fc1, fc2, head = net.fcs[0], net.fcs[1], net.fcs[2], net.fcs[3]
+    for fc in (fc0, fc1, fc2):
+        if not _is_groupnorm(fc.model[1]) or type(fc.model[2]).__name__ != "GELU" or getattr(fc.model[2], "approximate", "none") != "none":
+            raise Unsupported("PearceMlp FCBlock other than Linear -> GroupNorm1d -> GELU")
+    hidden = fc0.model[0].out_features
+    lins = [fc1.model[0], fc2.model[0], head]
+    s = 1.414
+    inv = [1.0 / s, 1.0 / (s * s), 1.0 / (s * s)]       # what the Linear reading v_1, v_2, v_3 folds into its weights
+    widths = [l.out_features for l in lins]
+    offs = [sum(widths[:i]) for i in range(3)]
+    xw = p.buf(p.rows, sum(widths))                                     # x W_x^T of the three layers
+    step0, samp0 = p.buf(p.n_iters, hidden), p.buf(p.rows, hidden)
+    steps = [p.buf(p.n_iters, w) for w in widths]
+
+    def fill(ctx):
+        w0 = fc0.model[0]
+        step0.copy_(F.linear(net.map_noise(ctx.t_all), w0.weight[:, emb:2 * emb], w0.bias))
+        if has_cond:
+            samp0.copy_(F.linear(torch.flatten(ctx.cond_rows, 1), w0.weight[:, 2 * emb:]))
+        else:
+            samp0.zero_()
+        tr = ctx.t_all.to(torch.float32)[:, None]
+        for lin, tab in zip(lins, steps):
+            tab.copy_(tr * lin.weight[:, hidden + act_dim][None, :] + lin.bias[None, :])
+    p.per_call.append(fill)
+
+    p.conv(x, w_rows(lambda: torch.cat([l.weight[:, hidden:hidden + act_dim] for l in lins], 0)), View(xw, 1, xw.shape[1]),
+           in_batch_mod=in_batch_mod)
+    ae = net.act_emb
+    e1 = p.act(1, ae[0].out_features)
+    p.conv(x, w_linear(ae[0].weight), e1, bias=_const_vec(p.packed(lambda: ae[0].bias)), act=cabi.ACT_LEAKY_RELU, in_batch_mod=in_batch_mod)
+    x_e = p.act(1, emb)
+    p.conv(e1, w_linear(ae[2].weight), x_e, bias=_const_vec(p.packed(lambda: ae[2].bias)))
+    f32 = torch.float32
+    v = View(p.buf(p.rows, 1, hidden), 1, hidden)                        # the residual chain stays exact fp32
+    p.conv(x_e, w_linear(fc0.model[0].weight, slice(0, emb)), v, bias=_vec(step0, samp0), gn=fc0.model[1], act=cabi.ACT_GELU_ERF)
+    for k, fc in enumerate((fc1, fc2)):
+        lin = fc.model[0]
+        v2 = View(p.buf(p.rows, 1, hidden), 1, hidden)
+        scale = p.buf(1, hidden)
+        scale.fill_(s ** (k + 1))
+        p.conv(v, w_rows(lambda l=lin, c=inv[k]: l.weight[:, :hidden] * c), v2, bias=cabi_vec2(steps[k], xw, offs[k]), gn=fc.model[1], act=cabi.ACT_GELU_ERF, scale=_const_vec(scale[0]), res=v)
+        v = v2
+    out = View(p.buf(p.rows, 1, act_dim), 1, act_dim)
+    return p.conv(v, w_rows(lambda: head.weight[:, :hidden] * inv[2]), out, bias=cabi_vec2(steps[2], xw, offs[2]))
+
+
+def cabi_vec2(step: torch.Tensor, sample: torch.Tensor, sample_col: int) -> cabi.Vec:
+    """step: [n_iters, W] table from column 0; sample: [rows, Wtot] table from column ``sample_col``."""
+    v = cabi.Vec()
+    v.step, v.step_stride = step.data_ptr(), step.stride(0)
+    v.sample, v.sample_stride = sample.data_ptr() + 4 * int(sample_col), sample.stride(0)
+    return v
+
+
 # =============================================================================== DiT1d
 def lower_dit(p: Program, net: nn.Module, x: View, horizon: int, has_cond: bool, in_batch_mod: int) -> View:
     d = net.d_model
@@ -743,6 +808,8 @@ def lower_denoiser(p: Program, net: nn.Module, x: View, x_shape, has_cond: bool,
         return lower_dql(p, net, x, has_cond, in_batch_mod)         # same graph: cat[x, time_mlp(t), cond] -> 3 x (Linear + Mish) -> Linear
     if name == "SfBCUNet" and len(x_shape) == 1:
         return lower_sfbc(p, net, x, has_cond, in_batch_mod)
+    if name == "PearceMlp" and len(x_shape) == 1:
+        return lower_pearce(p, net, x, has_cond, in_batch_mod)
     if name == "IDQLMlp" and len(x_shape) == 1:
         return lower_idql(p, net, x, has_cond, in_batch_mod)
     raise Unsupported(f"backbone {name} with x_shape {tuple(x_shape)}")

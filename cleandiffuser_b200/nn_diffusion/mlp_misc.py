@@ -1,10 +1,14 @@
-"""``DVInvMlp`` and ``SfBCUNet``: the remaining Mish / SiLU MLP-class action denoisers of the reference.
+"""``DVInvMlp``, ``SfBCUNet`` and ``PearceMlp``: the remaining MLP-class action denoisers of the reference.
 
 * ``DVInvMlp`` (cleandiffuser/nn_diffusion/dvinvmlp.py:9-47): ``cat[x, time_mlp(map_noise(t)), cond] -> 3 x (Linear + Mish)
   -> Linear(act_dim)`` -- DQLMlp's graph with a configurable width and a mandatory condition (two stacked observations).
 * ``SfBCUNet`` (cleandiffuser/nn_diffusion/sfbc_unet.py:9-82): a U-shaped stack of Linear residual blocks
   ``silu(W2 (silu(W1 x) + Wc c)) + skip(x)`` with ``c = t_layer(map_noise(t)) + condition``; the up path concatenates the
   down path's activations.
+
+* ``PearceMlp`` (cleandiffuser/nn_diffusion/pearcemlp.py:35-79): the Diffusion-BC MLP -- ``act_emb`` (Linear, LeakyReLU, Linear)
+  of the noisy action, three ``FCBlock``s (Linear -> GroupNorm1d(8 groups) -> exact GELU) whose inputs re-concatenate the raw
+  action and the raw time, residual connections scaled by 1/1.414, a Linear head.
 
 State-dict keys equal the reference's.
 """
@@ -14,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from .base import BaseNNDiffusion
+from ..utils import GroupNorm1d
 
 
 class DVInvMlp(BaseNNDiffusion):
@@ -77,3 +82,33 @@ class SfBCUNet(BaseNNDiffusion):
         for block in self.up_blocks:
             x = block(torch.cat([x, kept.pop()], dim=-1), c)
         return self.out_layer(x)
+
+
+class FCBlock(nn.Module):
+    def __init__(self, in_feats: int, out_feats: int):
+        super().__init__()
+        self.model = nn.Sequential(nn.Linear(in_feats, out_feats), GroupNorm1d(out_feats, 8, 4), nn.GELU())
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class PearceMlp(BaseNNDiffusion):
+    def __init__(self, act_dim: int, To: int = 1, timestep_emb_type: str = "positional", emb_dim: int = 128, hidden_dim: int = 512,
+                 timestep_emb_params: Optional[dict] = None):
+        super().__init__(emb_dim, timestep_emb_type, timestep_emb_params)
+        self.act_emb = nn.Sequential(nn.Linear(act_dim, emb_dim), nn.LeakyReLU(), nn.Linear(emb_dim, emb_dim))
+        self.fcs = nn.ModuleList([FCBlock(emb_dim * (2 + To), hidden_dim), FCBlock(hidden_dim + act_dim + 1, hidden_dim),
+                                  FCBlock(hidden_dim + act_dim + 1, hidden_dim), nn.Linear(hidden_dim + act_dim + 1, act_dim)])
+        self.To, self.emb_dim = To, emb_dim
+
+    def forward(self, x: torch.Tensor, noise: torch.Tensor, condition: Optional[torch.Tensor] = None):
+        """x (b, act_dim), noise (b,), condition (b, To, emb_dim)|None -> (b, act_dim)."""
+        x_e, t_e = self.act_emb(x), self.map_noise(noise)
+        t = noise.unsqueeze(-1)
+        if condition is None:
+            condition = torch.zeros(x.shape[0], self.To, self.emb_dim).to(x.device)
+        nn1 = self.fcs[0](torch.cat([x_e, t_e, torch.flatten(condition, 1)], -1))
+        nn2 = self.fcs[1](torch.cat([nn1 / 1.414, x, t], -1)) + nn1 / 1.414
+        nn3 = self.fcs[2](torch.cat([nn2 / 1.414, x, t], -1)) + nn2 / 1.414
+        return self.fcs[3](torch.cat([nn3, x, t], -1))

@@ -58,7 +58,9 @@ typedef enum cds_status {
 typedef enum cds_op_kind { CDS_OP_CONV = 0, CDS_OP_UPDATE = 1, CDS_OP_LNMOD = 2, CDS_OP_ATTN = 3, CDS_OP_PREP = 4,
                            CDS_OP_CAST = 5 } cds_op_kind;
 typedef enum cds_act { CDS_ACT_NONE = 0, CDS_ACT_MISH = 1, CDS_ACT_SILU = 2, CDS_ACT_GELU_TANH = 3,
-                       CDS_ACT_MISH_SILU = 4 /* silu(mish(x)): DiT's map_emb tail feeding every adaLN (dit.py:26,43,71) */ } cds_act;
+                       CDS_ACT_MISH_SILU = 4 /* silu(mish(x)): DiT's map_emb tail feeding every adaLN (dit.py:26,43,71) */,
+                       CDS_ACT_LEAKY_RELU = 5 /* negative slope 0.01 (nn.LeakyReLU default; pearcemlp.py:44) */,
+                       CDS_ACT_GELU_ERF = 6 /* exact GELU 0.5 x (1 + erf(x / sqrt 2)) (nn.GELU default; pearcemlp.py:30) */ } cds_act;
 /* math mode of CDS_OP_CONV:
  *   CDS_MATH_FP32     fp32 CUDA-core FMA (bit-faithful to the fp32 oracle up to summation order)
  *   CDS_MATH_BF16_TC  tcgen05 tensor cores, bf16 operands and bf16 inter-layer activations, fp32 TMEM accumulation

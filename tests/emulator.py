@@ -82,6 +82,11 @@ def _act(kind, x):
     if kind == cabi.ACT_MISH_SILU:
         m = _mish(x)
         return m / (1 + np.exp(-m))
+    if kind == cabi.ACT_LEAKY_RELU:
+        return np.where(x > 0, x, 0.01 * x)
+    if kind == cabi.ACT_GELU_ERF:
+        from scipy.special import erf
+        return 0.5 * x * (1 + erf(x * 0.7071067811865476))
     return x
 
 

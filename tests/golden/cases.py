@@ -50,6 +50,14 @@ NETS = {
         cls="SfBCUNet", ctor=dict(act_dim=6, emb_dim=16, hidden_dims=[32, 16]),
         x=(6,), t="float", cond=None,
         oracle=dict(fn="sfbc_unet", emb_dim=16, n_layers=2)),
+    "pearce_small": dict(
+        cls="PearceMlp", ctor=dict(act_dim=3, To=2, emb_dim=32, hidden_dim=64),
+        x=(3,), t="float", cond=(2, 32),
+        oracle=dict(fn="pearce_mlp", emb_dim=32, To=2)),
+    "pearce_uncond_long_t": dict(
+        cls="PearceMlp", ctor=dict(act_dim=6, To=1, emb_dim=16, hidden_dim=32),
+        x=(6,), t="long", cond=None,
+        oracle=dict(fn="pearce_mlp", emb_dim=16, To=1)),
     "dql_cfg1": dict(
         cls="DQLMlp", ctor=dict(obs_dim=11, act_dim=3, emb_dim=64),
         x=(3,), t="long", cond=(11,),
