@@ -230,6 +230,10 @@ def measure_other_configs(device, world, dist, math, reps=2):
                          "roofline": {"bound": "tensor", "achieved": tfl, "peak": peak, "unit": "TFLOP/s",
                                       "frac": (tfl / peak) if peak else None, "peak_source": src},
                          "engine_calls": runtime.STATS["engine_calls"] - before}
+            if wl.hbm_mb:                                # the config is HBM-bound: activations far larger than L2 between every pair of operators
+                gbs = v * wl.hbm_mb / 1e3 / world
+                out[name]["roofline_hbm"] = {"bound": "hbm", "alg_mb_per_traj": wl.hbm_mb, "achieved": gbs, "peak": peaks()[0],
+                                             "unit": "GB/s", "frac": gbs / peaks()[0]}
             log(f"{name}: {ms:.1f} ms / call, {v:,.0f} traj/s, {tfl:.0f} TFLOP/s per GPU")
             del wl, prior, cond
             torch.cuda.empty_cache()

@@ -10,6 +10,7 @@ thing measured is the thing tested.  Every builder returns a ``Workload``:
     oracle       plain-data description of the same computation for the CPU oracle (function names + keyword
                  arguments, NO import of ``oracle/`` here: only tests / bench's CPU legs resolve it)
     gflop        algorithmic GFLOP per trajectory for a full sample()
+    hbm_mb       algorithmic HBM megabytes per trajectory for a full sample() (0: not derived), see the builder
 
 Reference call sites these mirror: pipelines/diffuser_d4rl_mujoco.py:39-66,136-148 (cfg2),
 pipelines/dp_pusht.py (cfg3), pipelines/dd_d4rl_mujoco.py (cfg4), pipelines/ (consistency) cfg5.
@@ -32,6 +33,7 @@ class Workload:
     gflop: float
     cond: Optional[torch.Tensor] = None
     describe: str = ""
+    hbm_mb: float = 0.0
     extra: Dict[str, Any] = field(default_factory=dict)
 
     def sample(self, device, prior=None, cond=None, **over):
@@ -114,6 +116,10 @@ def cfg4(device, batch=2048, steps=20, seed=0, w_cfg=6.0):
              kwargs=dict(steps=steps, solver="ode_dpmsolver++_2M", schedule="linear", temperature=0.5, predict_noise=True, w_cfg=w_cfg),
              fix_mask=mask[None], cond=dict(fn="mlp_condition", act="silu", n_hidden=1)),
         gflop=20.96 * steps / 20, cond=cond,
+        # fp32 tensors every fused operator of the TF32 program reads / writes per token row and iteration: x_proj 4 (32 + 320),
+        # LN+modulate 2 x 1280, per block QKV 1280 + 3840, attention 3840 + 1280, out-proj (+LN) 4 x 1280, fc1 1280 + 5120,
+        # fc2 (+LN) 5120 + 3 x 1280, head 1280 + 116 = 66.8 KB; 100 tokens x 2 CFG branches per trajectory
+        hbm_mb=66804 * 100 * 2 * steps / 1e6,
         describe=f"DiT1d(29, d320, 10 heads, depth 2) H=100 d=29, ContinuousDiffusionSDE DPM-Solver++2M {steps} steps, w_cfg {w_cfg} (2 branches), batch {batch}")
 
 
