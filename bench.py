@@ -335,7 +335,9 @@ def main():
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
-        dist.init_process_group("nccl", device_id=torch.device(device))
+        import datetime
+        # a collective that has not completed within 3 minutes is a bug (the longest rank-0-only stretch is a few seconds)
+        dist.init_process_group("nccl", device_id=torch.device(device), timeout=datetime.timedelta(seconds=180))
 
     from cleandiffuser_b200.engine import runtime
     agent, net, mask = build_agent(device)
@@ -381,7 +383,8 @@ def main():
             extended = 0
             t_ext = time.time()
             while len(clk.rows) - row0 < 5 and time.time() - t_ext < 3.0:    # short timed regions: keep the same load running
-                step_resident()                                               # (un-timed) until a few samples exist
+                agent.sample(prior_dev, **kw)                                 # (un-timed) until a few samples exist.  NO collective
+                                                                              # here: the number of extra steps differs per rank
                 torch.cuda.synchronize()
                 extended += 1
             clocks = clk.summary(row0, None)

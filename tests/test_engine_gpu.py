@@ -382,3 +382,42 @@ def test_dit_fused_linear_layernorm_matches_the_two_launch_form(d_model, heads, 
         assert err.max().item() < TF32_MAX and err.mean().item() < TF32_MEAN, (fuse, err.max().item(), err.mean().item())
     d = (outs["1"] - outs["0"]).abs()
     assert d.max().item() < 2e-3, d.max().item()
+
+
+def test_run_range_splits_a_fused_linear_layernorm_pair(monkeypatch):
+    """`cds_plan_run_range` with a boundary BETWEEN a gated Linear and the LayerNorm fused into its launch must run the two
+    operators separately (the classifier-guidance interleave may cut a program anywhere); every split point gives the whole
+    program's result up to the summation order of the LayerNorm statistics."""
+    monkeypatch.setenv("CDS_MATH", "tf32")
+    from cleandiffuser_b200.engine.lower import Program, View, lower_denoiser
+    from cleandiffuser_b200.nn_diffusion import DiT1d
+    net = load_synth(DiT1d(9, emb_dim=32, d_model=256, n_heads=8, depth=1, timestep_emb_type="fourier"), seed=1).eval().to(DEV)
+    B, L = 5, 64
+    g = torch.Generator().manual_seed(4)
+    x, cond = torch.randn(B, L, 9, generator=g).to(DEV), torch.randn(B, 32, generator=g).to(DEV)
+    p = Program(torch.device(DEV), B, 1, cabi.MATH_TF32_TC)
+    xin = p.buf(B, L, 9)
+    xin.copy_(x)
+    pred = lower_denoiser(p, net, View(xin, L, 9), (L, 9), True, 0)
+    handle = runtime._make_handle(torch.device(DEV), p.ops, 1)
+    with torch.no_grad():
+        ctx = runtime._Ctx(torch.tensor([0.4], device=DEV), cond)
+        for fn in p.per_call:
+            fn(ctx)
+    st = torch.cuda.current_stream().cuda_stream
+    n = len(p.ops)
+    pairs = [i for i in range(n - 1) if p.ops[i].kind == cabi.OP_CONV and p.ops[i + 1].kind == cabi.OP_LNMOD
+             and p.ops[i].u.conv.scale.sample and p.ops[i].u.conv.math == cabi.MATH_TF32_TC]
+    assert len(pairs) == 2, pairs                                # out-projection + fc2 of the one block
+    assert handle.launches_per_iter() == n + 1 - len(pairs) - sum(1 for op in p.ops if op.flags & 1)   # fused pairs count once
+    handle.run(0, 1, st, False)
+    torch.cuda.synchronize()
+    whole = pred.t.clone()
+    for i in pairs:
+        pred.t.fill_(float("nan"))
+        handle.run_range(0, 0, i + 1, st)                        # ... up to and including the Linear
+        handle.run_range(0, i + 1, n - (i + 1), st)              # the LayerNorm onwards
+        torch.cuda.synchronize()
+        d = (pred.t - whole).abs().max().item()
+        assert d < 2e-3, (i, d)
+    handle.close()
