@@ -60,17 +60,6 @@ struct LinLnCfg {
   static_assert((NH * 128) % 1024 == 0, "the second weight half must start on a swizzle atom");
 };
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 template <int NH>
 __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_constant__ LinLnParams p, const int* __restrict__ iter_ptr) {
   using Cfg = LinLnCfg<NH>;
@@ -150,9 +139,10 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
     const int m = 32 * q + lane;
     for (int i = threadIdx.x; i < C; i += kLlEpiThreads) s_bias[i] = p.bias[(int64_t)(*iter_ptr) * p.bias_step_stride + i];
     ptx::named_bar_sync(1, kLlEpiThreads);
-    // three rotating 2 KB buffers per warp (32 rows x 16 fp32, SWIZZLE_64B).  Use number u works in buffer u % 3: in pass 1 the
-    // residual chunk is TMA-LOADED into it (requested one use ahead), x is computed in place and TMA-stored from it; in pass 2
-    // it is plain staging for Y.  A buffer is reloaded / rewritten only after the store issued three uses earlier has read it.
+    // three rotating 2 KB buffers per warp (32 rows x 16 fp32, SWIZZLE_64B).  Use number u works in buffer u % 3: a 16-column
+    // chunk is TMA-LOADED into it (pass 1: the residual, pass 2: the x just stored; chunks 0..2 up front, then two uses ahead),
+    // the result is computed in place and TMA-stored from it (pass 1: X, pass 2: Y).  A buffer is reloaded only after the
+    // store issued from it has read it.
     uint8_t* const stg = s_stage + warp * 6144;
     const int sw = (lane >> 1) & 3;
     const uint32_t lane_off = (uint32_t)lane * 64u;
@@ -196,7 +186,7 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
       }
       ptx::mbar_wait(&tmem_full_bar, t & 1u);
       ptx::tc_fence_after_sync();
-      // ---- pass 1: x = (acc + bias) * gate + residual -> TMEM, X; shifted row moments
+      // ---- pass 1: x = (acc + bias) * gate + residual -> X; shifted row moments
       float sh0 = 0.f, sd = 0.f, sdd = 0.f;            // pivot (the row's first x of this half), sum (x - pivot), sum (x - pivot)^2
 #pragma unroll 1
       for (int ch = 0; ch < NH / 16; ++ch, ++u) {
