@@ -269,15 +269,9 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
       ptx::tmem_ld_wait();
       accumulate(vb);
     }
-    // first chunk of pass 2 is already on its way while the halves exchange their partial sums; so is its identity-residual row
-    // (a thread walks its own trajectory's rows: one L2 round trip per 16 columns if requested where it is used)
+    // first chunk of pass 2 is already on its way while the halves exchange their partial sums
     float vbuf[2][16];
     ptx::tmem_ld_nowait<16>(t_row + (uint32_t)(lp0 * N + col0), vbuf[0]);
-    const bool add_res = p.res != nullptr;
-    float resn[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) resn[j] = 0.f;
-    if (add_res && valid) load_row<16>(p.res, (int64_t)rb * p.res_bstride + (int64_t)lp0 * p.res_lstride + n_off + col0, kActDtype, resn);
     s_part[ph][half][32 * q + lane] = make_float2(s1, s2);
     ptx::named_bar_sync(1, kPsEpiThreads);
     { const float2 o2 = s_part[ph ^ 1][half][32 * q + lane]; s1 += o2.x; s2 += o2.y; }
@@ -287,6 +281,7 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
     const float gc = -mean * ga;
 
     // ---- pass 2: normalise, affine, Mish, additive terms, store; 16-column chunks, the next chunk's TMEM read in flight
+    const bool add_res = p.res != nullptr;
     constexpr int kChunks = PH * (NH / 16);
 #pragma unroll
     for (int ci = 0; ci < kChunks; ++ci) {
@@ -298,15 +293,17 @@ conv_ps_kernel(const __grid_constant__ ConvPsParams p, const int* __restrict__ i
 #pragma unroll
       for (int k = 0; k < 4; ++k) { const float4 s = sh4[k]; addv[4 * k] = s.x; addv[4 * k + 1] = s.y; addv[4 * k + 2] = s.z; addv[4 * k + 3] = s.w; }
       if (add_res) {
+        float resv[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) addv[j] += resn[j];
+        for (int j = 0; j < 16; ++j) resv[j] = 0.f;
+        if (valid) load_row<16>(p.res, (int64_t)rb * p.res_bstride + (int64_t)lp * p.res_lstride + n_off + n0, kActDtype, resv);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) addv[j] += resv[j];
       }
       ptx::tmem_ld_wait();
       if (ci + 1 < kChunks) {
         const int lp1 = lp0 + (ci + 1) / (NH / 16), h1 = (ci + 1) % (NH / 16);
         ptx::tmem_ld_nowait<16>(t_row + (uint32_t)(lp1 * N + col0 + 16 * h1), vbuf[(ci + 1) & 1]);
-        if (add_res && valid)                           // ... and the next chunk's residual row
-          load_row<16>(p.res, (int64_t)rb * p.res_bstride + (int64_t)lp1 * p.res_lstride + n_off + col0 + 16 * h1, kActDtype, resn);
       }
       if constexpr (HAS_RES) {
         float r2[16];
