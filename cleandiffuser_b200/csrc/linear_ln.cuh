@@ -1,6 +1,7 @@
 // Fused  Linear -> gate * (.) + residual -> LayerNorm + adaLN modulate  for DiT1d's token stream (TF32 tensor-core programs).
 //
 //   X[r, :] = (A[r, :] W^T + bias) * gate[traj(r), :] + R[r, :]                   (dit.py:33-36: x + gate * f(...))
+//        or = (A[r, :] W^T + bias) + T[r mod L, :]                                (dit.py:118: x_proj(x) + pos_emb, T a (L, C) table)
 //   Y[r, :] = LayerNorm(X[r, :]) * (1 + scale[traj(r), :]) + shift[traj(r), :]    (dit.py:30-31 of the NEXT block / final layer)
 //
 // It replaces, at plan-finalize time, a CDS_OP_CONV in its "gated" form directly followed by the CDS_OP_LNMOD that reads its
@@ -34,7 +35,9 @@ struct LinLnParams {
   CUtensorMap tm_a, tm_b, tm_x, tm_y, tm_r, tm_rp, tm_xl;   // tm_xl: X as a load source (pass 2 re-reads what pass 1 stored)   // tm_rp: the residual again, box {NH, 32}, for L2 prefetches
   int rows, K, C, L;                                 // L = tokens per trajectory
   const float* bias; int64_t bias_step_stride;       // bias row of iteration i = bias + i * stride
-  const float* gate; int64_t gate_stride;            // per trajectory
+  const float* gate; int64_t gate_stride;            // per trajectory; nullptr: no gate (table form)
+  int table_period;                                  // > 0: the residual is a (period, C) TABLE indexed by row % period (x_proj + pos_emb)
+  int a_row_mod;                                     // > 0: the activation rows repeat with this period (CFG branches share x_t)
   const float* res; int64_t res_stride;              // (rows, C), elements
   const float* shift; const float* scale; int64_t mod_stride;
   float eps;
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
           ptx::mbar_wait(&empty_bar[s], ((n / Cfg::kStages) & 1u) ^ 1u);
           uint8_t* a = sm + s * Cfg::kStage;
           ptx::mbar_expect_tx(&full_bar[s], (uint32_t)Cfg::kStage);
-          ptx::tma_load_2d(a, &p.tm_a, &full_bar[s], kc * 32, tile * 128);
+          ptx::tma_load_2d(a, &p.tm_a, &full_bar[s], kc * 32, p.a_row_mod > 0 ? (tile * 128) % p.a_row_mod : tile * 128);
           ptx::tma_load_2d(a + Cfg::kStageA, &p.tm_b, &full_bar[s], kc * 32, 0);
           ptx::tma_load_2d(a + Cfg::kStageA + NH * 128, &p.tm_b, &full_bar[s], kc * 32, NH);
         }
@@ -162,15 +165,25 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
       const int64_t traj = min(grow / p.L, last_traj);
       const int sel = traj != traj_a ? 16 : 0;          // which half of the warp holds this row's values
       const int64_t traj_ld = (lane < 16) ? traj_a : min(traj_a + 1, last_traj);
-      const float* gate_ld = p.gate + traj_ld * p.gate_stride + hh * NH + (lane & 15);
+      const bool gated = p.gate != nullptr;
+      const bool table = p.table_period > 0;
+      const float* gate_ld = gated ? p.gate + traj_ld * p.gate_stride + hh * NH + (lane & 15) : p.scale;   // (never read when !gated)
       const float* scp_ld = p.scale + traj_ld * p.mod_stride + hh * NH + (lane & 15);
       const float* shp_ld = p.shift + traj_ld * p.mod_stride + hh * NH + (lane & 15);
       float gq[kLlAhead], aq[kLlAhead], dq[kLlAhead];
 #pragma unroll
       for (int j = 0; j < kLlAhead; ++j) aq[j] = dq[j] = 0.f;
 #pragma unroll
-      for (int j = 0; j < kLlAhead; ++j) gq[j] = (j < NH / 16) ? __ldg(gate_ld + 16 * j) : 0.f;
-      if (lane == 0) {                                 // residual chunks 0..2: in flight while the main loop runs
+      for (int j = 0; j < kLlAhead; ++j) gq[j] = (gated && j < NH / 16) ? __ldg(gate_ld + 16 * j) : 1.f;
+      // table form: this thread's table row (row % period), two 16-column chunks ahead in registers (the table is small and hot
+      // in L2; a thread walks its own row, so the requests are issued early rather than wide)
+      const float* trow = table ? p.res + (int64_t)((grow < p.rows ? grow : 0) % p.table_period) * p.res_stride + hh * NH : p.res;
+      float4 rq[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rq[j][k] = table ? __ldg(reinterpret_cast<const float4*>(trow + 16 * j) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == 0 && !table) {                       // residual chunks 0..2: in flight while the main loop runs
         ptx::bulk_wait_group_read<0>();
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -182,7 +195,7 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
         }
         // ... and the next tile's residual rows of this warp are pulled into L2 (they were written several launches ago)
         const int nt = tile + (int)gridDim.x;
-        if (nt < p.num_tiles) ptx::tma_prefetch_2d(&p.tm_rp, hh * NH, nt * 128 + 32 * q);
+        if (nt < p.num_tiles) ptx::tma_prefetch_2d(&p.tm_rp, hh * NH, nt * 128 + 32 * q);   // (residual form only: see the guard above)
       }
       ptx::mbar_wait(&tmem_full_bar, t & 1u);
       ptx::tc_fence_after_sync();
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
         const float gcur = gq[0];
 #pragma unroll
         for (int j = 0; j + 1 < kLlAhead; ++j) gq[j] = gq[j + 1];
-        gq[kLlAhead - 1] = (ch + kLlAhead < NH / 16) ? __ldg(gate_ld + 16 * (ch + kLlAhead)) : 0.f;
+        gq[kLlAhead - 1] = (gated && ch + kLlAhead < NH / 16) ? __ldg(gate_ld + 16 * (ch + kLlAhead)) : 1.f;
 #pragma unroll
         for (int j = 0; j + 1 < kLlAhead; ++j) { aq[j] = aq[j + 1]; dq[j] = dq[j + 1]; }
         if (ch + kLlAhead >= NH / 16) {                // pass 2's first kLlAhead chunks are requested by pass 1's last steps
@@ -204,13 +217,25 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
         }
         float v[16];
         ptx::tmem_ld<16>(t_row + (uint32_t)(16 * ch), v);
-        ptx::mbar_wait(&rbar[b], (par >> b) & 1u);
-        par ^= 1u << b;
+        float4 rt[4];
+        if (table) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { rt[k] = rq[0][k]; rq[0][k] = rq[1][k]; }
+          if (ch + 2 < NH / 16) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rq[1][k] = __ldg(reinterpret_cast<const float4*>(trow + 16 * (ch + 2)) + k);
+          }
+          if (lane == 0) ptx::bulk_wait_group_read<2>();        // the store issued from this buffer three uses ago has read it
+          __syncwarp();
+        } else {
+          ptx::mbar_wait(&rbar[b], (par >> b) & 1u);
+          par ^= 1u << b;
+        }
         const float4* b4 = reinterpret_cast<const float4*>(&s_bias[hh * NH + 16 * ch]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float4 bb = b4[k];
-          const float4 r = *reinterpret_cast<const float4*>(buf + lane_off + ((k ^ sw) << 4));
+          const float4 r = table ? rt[k] : *reinterpret_cast<const float4*>(buf + lane_off + ((k ^ sw) << 4));
           v[4 * k] = fmaf(v[4 * k] + bb.x, __shfl_sync(0xffffffffu, gcur, sel + 4 * k), r.x);
           v[4 * k + 1] = fmaf(v[4 * k + 1] + bb.y, __shfl_sync(0xffffffffu, gcur, sel + 4 * k + 1), r.y);
           v[4 * k + 2] = fmaf(v[4 * k + 2] + bb.z, __shfl_sync(0xffffffffu, gcur, sel + 4 * k + 2), r.z);
@@ -226,7 +251,7 @@ __global__ void __launch_bounds__(kLlThreads, 1) linear_ln_kernel(const __grid_c
           else o4 = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           *reinterpret_cast<float4*>(buf + lane_off + ((k ^ sw) << 4)) = o4;
         }
-        if (ch >= 1 && ch + 2 < NH / 16 && lane == 0) {
+        if (!table && ch >= 1 && ch + 2 < NH / 16 && lane == 0) {
           // the buffer of the previous step is free once its X store has read it (issued a whole step ago): residual chunk
           // ch + 2 goes there, two steps ahead of its use
           const uint32_t bp = (u + 2) % 3;
@@ -329,14 +354,20 @@ inline bool linear_ln_eligible(const cds_conv_op& c, const cds_lnmod_op& l) {
   { const char* e = getenv("CDS_FUSE_LN"); if (e && e[0] == '0') return false; }      // (read at every finalize: tests toggle it)
   if (c.math != CDS_MATH_TF32_TC || linear_ln_pick_nh(c.C_out) == 0) return false;
   if (c.taps != 1 || c.stride != 1 || c.pad != 0 || c.phases != 1 || c.L_in != 1 || c.L_out != 1) return false;
-  if (c.C_in % 32 != 0 || c.C_in < 32 || c.in_batch_mod != 0 || c.groups != 0 || c.act != CDS_ACT_NONE) return false;
+  if (c.C_in % 32 != 0 || c.C_in < 32 || c.groups != 0 || c.act != CDS_ACT_NONE) return false;
+  if (c.in_batch_mod < 0 || c.in_batch_mod % 128 != 0) return false;        // (CFG branches sharing x_t: whole 128-row tiles repeat)
   if (c.in_dtype == CDS_BF16 || c.out_dtype == CDS_BF16 || c.res_dtype == CDS_BF16) return false;
   if (c.in_bstride != c.C_in || c.out_bstride != c.C_out) return false;                       // dense rows
   if (!c.bias.step || c.bias.sample) return false;
-  if (!c.scale.sample || c.scale.step || c.shift.step || c.shift.sample) return false;
-  if (!c.res || c.res_w || c.res_batch_mod != 0 || c.res_bstride % 4 != 0) return false;
+  if (c.scale.step || c.shift.step || c.shift.sample) return false;
+  if (!c.res || c.res_w || c.res_bstride % 4 != 0) return false;
+  // two forms: gated + dense residual (out-projection, second MLP Linear) / no gate + periodic table (x_proj + pos_emb)
+  const bool gated_form = c.scale.sample && c.res_batch_mod == 0;
+  const bool table_form = !c.scale.sample && c.res_batch_mod > 0 && c.res_batch_mod == c.sample_row_div;
+  if (!gated_form && !table_form) return false;
   if (c.sample_row_div < 32) return false;             // (a warp's 32 rows then span at most two trajectories)
-  if (c.scale.sample_stride % 4 != 0 || ((uintptr_t)c.scale.sample % 16) || ((uintptr_t)c.res % 16) || ((uintptr_t)c.bias.step % 4)) return false;
+  if (gated_form && (c.scale.sample_stride % 4 != 0 || ((uintptr_t)c.scale.sample % 16))) return false;
+  if (((uintptr_t)c.res % 16) || ((uintptr_t)c.bias.step % 4)) return false;
   if (((uintptr_t)c.in % 16) || ((uintptr_t)c.w % 16) || ((uintptr_t)c.out % 16)) return false;
   // the LayerNorm that follows
   if (l.in != c.out || l.C != c.C_out || (int64_t)l.batch * l.L != (int64_t)c.batch || l.L != c.sample_row_div) return false;
@@ -366,15 +397,18 @@ inline bool linear_ln_prepare(const cds_conv_op& c, const cds_lnmod_op& l, LinLn
   p.rows = c.batch; p.K = c.C_in; p.C = c.C_out; p.L = c.sample_row_div;
   p.bias = c.bias.step; p.bias_step_stride = c.bias.step_stride;
   p.gate = c.scale.sample; p.gate_stride = c.scale.sample_stride;
+  p.table_period = c.res_batch_mod; p.a_row_mod = c.in_batch_mod;
   p.res = reinterpret_cast<const float*>(c.res); p.res_stride = c.res_bstride;
   p.shift = l.shift; p.scale = l.scale; p.mod_stride = l.mod_bstride;
   p.eps = l.eps; p.x_dtype = c.out_dtype; p.y_dtype = l.out_dtype;
   p.num_tiles = (c.batch + 127) / 128;
-  if (!linear_ln_encode_2d(&p.tm_a, c.in, (uint64_t)c.C_in, (uint64_t)c.batch, (uint64_t)c.C_in * 4, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+  const uint64_t a_rows = c.in_batch_mod > 0 ? (uint64_t)c.in_batch_mod : (uint64_t)c.batch;
+  const uint64_t r_rows = c.res_batch_mod > 0 ? (uint64_t)c.res_batch_mod : (uint64_t)c.batch;      // (table form: the maps are not used)
+  if (!linear_ln_encode_2d(&p.tm_a, c.in, (uint64_t)c.C_in, a_rows, (uint64_t)c.C_in * 4, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
   if (!linear_ln_encode_2d(&p.tm_b, c.w, (uint64_t)c.C_in, (uint64_t)c.C_out, (uint64_t)c.C_in * 4, 32, (uint32_t)L.nh, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
   if (!linear_ln_encode_2d(&p.tm_x, c.out, (uint64_t)c.C_out, (uint64_t)c.batch, (uint64_t)c.C_out * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
-  if (!linear_ln_encode_2d(&p.tm_r, c.res, (uint64_t)c.C_out, (uint64_t)c.batch, (uint64_t)c.res_bstride * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
-  if (!linear_ln_encode_2d(&p.tm_rp, c.res, (uint64_t)c.C_out, (uint64_t)c.batch, (uint64_t)c.res_bstride * 4, (uint32_t)L.nh, 32, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
+  if (!linear_ln_encode_2d(&p.tm_r, c.res, (uint64_t)c.C_out, r_rows, (uint64_t)c.res_bstride * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
+  if (!linear_ln_encode_2d(&p.tm_rp, c.res, (uint64_t)c.C_out, r_rows, (uint64_t)c.res_bstride * 4, (uint32_t)L.nh, 32, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
   p.tm_xl = p.tm_x;
   if (!linear_ln_encode_2d(&p.tm_y, l.out, (uint64_t)c.C_out, (uint64_t)c.batch, (uint64_t)c.C_out * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
   L.ok = true;
