@@ -89,6 +89,9 @@ SAMPLER_NETS = {
     "dql_tiny": dict(
         cls="DQLMlp", ctor=dict(obs_dim=4, act_dim=3, emb_dim=16),
         x=(3,), oracle=dict(fn="dql_mlp", emb_dim=16, obs_dim=4)),
+    "pearce_tiny": dict(
+        cls="PearceMlp", ctor=dict(act_dim=3, To=1, emb_dim=8, hidden_dim=32),
+        x=(3,), oracle=dict(fn="pearce_mlp", emb_dim=8, To=1)),
 }
 SAMPLER_BATCH = 6
 
@@ -153,6 +156,9 @@ def legacy_cases():
                                  temperature=1.0, extra=3, beta_schedule="cosine"),
         "ddpm_x_x0_cfg2branch": dict(net="dql_tiny", predict_noise=False, T=6, fix_mask=None, clip=False, w_cfg=1.6, cond="obs",
                                      temperature=1.0, extra=2, beta_schedule="cosine"),
+        # the Diffusion-BC pattern (pipelines/dbc_*.py): legacy DDPM over PearceMlp, observation embedding as condition, sample_x
+        "ddpm_x_pearce_dbc": dict(net="pearce_tiny", predict_noise=True, T=8, fix_mask=None, clip=True, w_cfg=1.0, cond="emb",
+                                  temperature=1.0, extra=2, beta_schedule="cosine"),
     }
 
 
