@@ -1210,8 +1210,8 @@ inline int conv_tc_pick_split(const cds_conv_op& c, int n_total, int m_tiles) {
   if (c.phases != 1 || n_total < 64) return 1;
   if (const char* ns = getenv("CDS_TC_NOSPLIT")) { if (ns[0] == '1') return 1; if (ns[0] == '2' && n_total == 128) return 1; }   // experiment
   if (n_total >= 128) return 2;
-  // TF32 programs: a 32-wide MMA reads 5 KB of shared memory per 16 clk, a 64-wide one 6 KB per 32 clk -- the kernels are bound by
-  // that bandwidth, so the 64-wide layers stay whole even when that leaves fewer tiles than CTA slots
+  // TF32 programs: two 32-wide CTAs fetch the (fp32) activation tile twice, and the kernels are bound by the L2 -> SM feed of
+  // their operand tiles, so the 64-wide layers stay whole even when that leaves fewer tiles than CTA slots
   // (cfg2, TF32: 597 vs 608 us per iteration)
   if (conv_is_tf32(c)) return 1;
   const char* e = getenv("CDS_TC_SPLIT64");

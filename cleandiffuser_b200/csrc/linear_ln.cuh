@@ -8,7 +8,7 @@
 // output (cds_api.cu: fuse_linear_ln) -- the ABI and the lowering do not know about it.  Why a kernel of its own:
 //   * LayerNorm needs the whole row, so one CTA owns all C = 2 * NH output columns of its 128 rows: two tcgen05.mma (N = NH) per
 //     32-byte K step into TMEM columns [0, NH) and [NH, 2 NH); the activation chunk is staged ONCE for both halves (the generic
-//     kernel's 160-wide column tiles re-stage it per tile), which is what the shared-memory-bound TF32 main loop cares about;
+//     kernel's 160-wide column tiles re-fetch it per tile), which is what the L2-feed-bound TF32 main loop cares about;
 //   * the separate LayerNorm launch (read X, write Y: 8 bytes per element of HBM traffic, ~230 us per call at cfg4's size)
 //     disappears: X never leaves the SM between the two.
 // Epilogue, 8 warps (TMEM lane quarter q = warp & 3, column half hh = warp >> 2), two passes over the thread's NH columns; the
