@@ -923,6 +923,39 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
           else o[j] = tc_act<ACT>(p.act, yv[YO + j]) + addv[j];
         }
       }
+      if (p.out_tma == 1 && io_vec) {
+        // like the fast / plain lanes: the warp's 32 rows x 16 columns through its swizzled staging rows and ONE bulk tensor store
+        // (a thread storing its own row reaches a third of that: profiles/r02_micro_store_patterns.txt).  This is the lane of
+        // ChiUNet1d's FiLM convs (per-trajectory scale and shift); rows beyond the batch are clipped by the TMA unit.
+        uint8_t* const stg = &s_stage[warp][0];
+        if (lane == 0) ptx::bulk_wait_group_read<0>();
+        __syncwarp();
+        if (p.out_dtype == CDS_BF16) {
+          uint32_t w[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]); w[k] = *reinterpret_cast<uint32_t*>(&h2); }
+          uint8_t* const sr = stg + lane * 32;
+          const int sw = (lane >> 2) & 1;
+          *reinterpret_cast<uint4*>(sr + ((0 ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(sr + ((1 ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+          uint8_t* const sr = stg + lane * 64;
+          const bool rnd = p.out_dtype == CDS_TF32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float4 o4 = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            if (rnd) o4 = make_float4(round_tf32(o4.x), round_tf32(o4.y), round_tf32(o4.z), round_tf32(o4.w));
+            *reinterpret_cast<float4*>(sr + ((k ^ ((lane >> 1) & 3)) << 4)) = o4;
+          }
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_3d(&p.tm_out, stg, c0, 0, (tile / nct) * (128 >> p.log2L) + ((32 * q) >> p.log2L));
+          ptx::bulk_commit_group();
+        }
+        return;
+      }
       if (!valid) return;
       const int64_t oo = (int64_t)b * p.out_bstride + (int64_t)(l * p.phases + phase) * p.out_lstride + c0;
       if (io_vec) {
