@@ -906,13 +906,28 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p, const int* __restrict__ i
           sc[4 * k] = a.x; sc[4 * k + 1] = a.y; sc[4 * k + 2] = a.z; sc[4 * k + 3] = a.w;
           sh[4 * k] = d.x; sh[4 * k + 1] = d.y; sh[4 * k + 2] = d.z; sh[4 * k + 3] = d.w;
         }
+        // per-trajectory FiLM rows: four 16-byte loads per vector when every column is a real channel and the rows are aligned
+        // (ChiUNet1d: always), element-wise otherwise
+        const bool film_vec = io_vec && (((uintptr_t)scale_smp | (uintptr_t)shift_smp) % 16 == 0);
         if (scale_smp && valid) {
+          if (film_vec) {
+            const float4* q4 = reinterpret_cast<const float4*>(scale_smp + c0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (c0 + j < p.C_out) sc[j] += __ldg(scale_smp + c0 + j);
+            for (int k = 0; k < 4; ++k) { const float4 a = __ldg(q4 + k); sc[4 * k] += a.x; sc[4 * k + 1] += a.y; sc[4 * k + 2] += a.z; sc[4 * k + 3] += a.w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (c0 + j < p.C_out) sc[j] += __ldg(scale_smp + c0 + j);
+          }
         }
         if (shift_smp && valid) {
+          if (film_vec) {
+            const float4* q4 = reinterpret_cast<const float4*>(shift_smp + c0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (c0 + j < p.C_out) sh[j] += __ldg(shift_smp + c0 + j);
+            for (int k = 0; k < 4; ++k) { const float4 a = __ldg(q4 + k); sh[4 * k] += a.x; sh[4 * k + 1] += a.y; sh[4 * k + 2] += a.z; sh[4 * k + 3] += a.w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (c0 + j < p.C_out) sh[j] += __ldg(shift_smp + c0 + j);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[j] = fmaf(tc_act<ACT>(p.act, yv[YO + j]), sc[j], sh[j]) + addv[j];
