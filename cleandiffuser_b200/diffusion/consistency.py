@@ -239,7 +239,9 @@ class ContinuousConsistencyModel(DiffusionModel):
         from ..engine import runtime
         if not (requires_grad or preserve_history) and runtime._device_ok(torch.device(self.device)):
             out = runtime.try_sample_consistency(self, model=model, xt=xt, prior=prior, sigmas=sigmas, order=order,
-                                                 cond_emb=cvec, n_samples=n_samples)
+                                                 cond_emb=cvec, n_samples=n_samples,
+                                                 sched_id=(int(sample_steps), float(self.sigma_min), float(self.sigma_max), float(self.rho),
+                                                           int(diffusion_x_sampling_steps), float(self.sigma_data)))
             if out is not None:
                 return out, log
 

@@ -160,7 +160,7 @@ class BaseDiffusionSDE(DiffusionModel):
 
     def _reverse_loop(self, *, xt, prior, model, solver, sample_steps, step_values, alphas, sigmas,
                       condition_vec_cfg, w_cfg, condition_vec_cg, w_cg, diffusion_x_sampling_steps,
-                      requires_grad, preserve_history, n_samples, log, engine_ok):
+                      requires_grad, preserve_history, n_samples, log, engine_ok, sched_id=None):
         hs, stds = S.schedule_tables(alphas, sigmas, sample_steps, self.device)
         order = S.loop_indices(sample_steps, diffusion_x_sampling_steps)
 
@@ -183,7 +183,7 @@ class BaseDiffusionSDE(DiffusionModel):
             out = runtime.try_sample(self, model=model, xt=xt, prior=prior, solver=solver,
                                      sample_steps=sample_steps, order=order, step_values=step_values,
                                      alphas=alphas, sigmas=sigmas, hs=hs, stds=stds,
-                                     cond_emb=condition_vec_cfg, w_cfg=w_cfg, n_samples=n_samples, guide=guide)
+                                     cond_emb=condition_vec_cfg, w_cfg=w_cfg, n_samples=n_samples, guide=guide, sched_id=sched_id)
             if out is not None:
                 return out
 
@@ -308,7 +308,11 @@ class DiscreteDiffusionSDE(BaseDiffusionSDE):
             alphas=self.alpha[idx], sigmas=self.sigma[idx], condition_vec_cfg=cond_vec, w_cfg=w_cfg,
             condition_vec_cg=condition_cg, w_cg=w_cg, diffusion_x_sampling_steps=diffusion_x_sampling_steps,
             requires_grad=requires_grad, preserve_history=preserve_history, n_samples=n_samples, log=log,
-            engine_ok=self._engine_candidate(requires_grad, preserve_history, w_cg, warm_start_reference))
+            engine_ok=self._engine_candidate(requires_grad, preserve_history, w_cg, warm_start_reference),
+            # what idx / alphas / sigmas are functions of (named step schedules only): lets the engine reuse its coefficient table
+            # without reading the schedule back from the device
+            sched_id=(("disc", sample_step_schedule, int(grid_len), self.alpha.data_ptr(), self.alpha._version,
+                       self.sigma.data_ptr(), self.sigma._version) if isinstance(sample_step_schedule, str) else None))
         return self._finish(xt, log, n_samples, condition_cg, w_cg)
 
 

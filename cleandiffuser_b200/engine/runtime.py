@@ -350,7 +350,7 @@ def _cond_rows(cfg_mode, cond_emb):
 
 
 def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_values, alphas, sigmas, hs, stds,
-               cond_emb, w_cfg, n_samples, guide=None, table=None, clip_in_loop=True, predict_noise=None):
+               cond_emb, w_cfg, n_samples, guide=None, table=None, clip_in_loop=True, predict_noise=None, sched_id=None):
     """``table``: optional ready-made ``(coefficient rows [n_iters, ROW], number of noise slots, int64/float32 time per iteration)``
     for samplers that are "the same update kernel with another coefficient table" (the legacy DDPM class, RectifiedFlow's Euler
     step): ``solver`` / ``alphas`` / ``sigmas`` / ``hs`` / ``stds`` / ``step_values`` are then unused.
@@ -384,11 +384,26 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
         sched_key = (solver, rows_given.numpy().tobytes(), t_cpu.numpy().tobytes())
         cached = (rows_given, int(slots_given))
     else:
-        alphas_c, sigmas_c, hs_c, stds_c = (z.detach().float().cpu() for z in (alphas, sigmas, hs, stds))
-        t_cpu = step_values.detach().cpu()
-        sched_key = (solver, sample_steps, tuple(order), alphas_c.numpy().tobytes(), sigmas_c.numpy().tobytes(),
-                     hs_c.numpy().tobytes(), stds_c.numpy().tobytes(), t_cpu.numpy().tobytes())
-        cached = agent._engine_tables.get(sched_key) if hasattr(agent, "_engine_tables") else None
+        # ``sched_id``: a hashable the caller vouches for -- everything alphas / sigmas / hs / stds / step_values are functions of.
+        # A hit skips the five device->host reads below: each of them is a stream synchronisation, which would keep the host from
+        # preparing call n + 1 while call n still runs (1-step samplers: a quarter of the wall time).
+        fast_key = None if sched_id is None else (sched_id, solver, sample_steps, tuple(order))
+        fast = agent.__dict__.setdefault("_engine_sched_ids", {}).get(fast_key) if fast_key is not None else None
+        if fast is not None:
+            sched_key, t_cpu = fast
+            cached = agent._engine_tables.get(sched_key) if hasattr(agent, "_engine_tables") else None
+        else:
+            cached = None
+        if cached is None:
+            alphas_c, sigmas_c, hs_c, stds_c = (z.detach().float().cpu() for z in (alphas, sigmas, hs, stds))
+            t_cpu = step_values.detach().cpu()
+            sched_key = (solver, sample_steps, tuple(order), alphas_c.numpy().tobytes(), sigmas_c.numpy().tobytes(),
+                         hs_c.numpy().tobytes(), stds_c.numpy().tobytes(), t_cpu.numpy().tobytes())
+            cached = agent._engine_tables.get(sched_key) if hasattr(agent, "_engine_tables") else None
+            if fast_key is not None:
+                if len(agent._engine_sched_ids) > 16:
+                    agent._engine_sched_ids.clear()
+                agent._engine_sched_ids[fast_key] = (sched_key, t_cpu)
     if cached is None:
         table = S.coeff_table(solver, order, sample_steps, alphas_c, sigmas_c, hs_c, stds_c, t_cpu.double())
         n_slots = 0
@@ -468,7 +483,7 @@ def try_sample(agent, *, model, xt, prior, solver, sample_steps, order, step_val
     return plan.x.clone()
 
 
-def try_sample_consistency(agent, *, model, xt, prior, sigmas, order, cond_emb, n_samples):
+def try_sample_consistency(agent, *, model, xt, prior, sigmas, order, cond_emb, n_samples, sched_id=None):
     """ContinuousConsistencyModel.sample on the engine: iteration 0 evaluates f at sigma_max, the following
     iterations re-noise to sigma_i and evaluate f again (consistency_model.py:401-426)."""
     if _backend() == "torch":
@@ -481,11 +496,15 @@ def try_sample_consistency(agent, *, model, xt, prior, sigmas, order, cond_emb, 
     if n_samples != batch:
         return _fallback("n_samples != prior.shape[0]")
     cfg_mode = 0 if cond_emb is None else 1
-    sig = sigmas.detach().float().cpu()
-    levels = [sig[-1]] + [sig[i] for i in order]
-    n_iters = len(levels)
+    # ``sched_id`` (see try_sample): a hit reuses the coefficient table and its device copy of the time column -- no device->host
+    # read, so the host can prepare the next call while this one runs (the 1-step sampler is 8 ms of GPU work per call)
+    cm_key = None if sched_id is None else (sched_id, tuple(order), str(device))
+    hit = agent.__dict__.setdefault("_engine_cm_tables", {}).get(cm_key) if cm_key is not None else None
+    sig = None if hit is not None else sigmas.detach().float().cpu()
+    levels = [] if hit is not None else [sig[-1]] + [sig[i] for i in order]
+    n_iters = hit[0].shape[0] if hit is not None else len(levels)
     sd, smin = agent.sigma_data, agent.sigma_min
-    table = torch.zeros((n_iters, S.ROW), dtype=torch.float32)
+    table = hit[0] if hit is not None else torch.zeros((n_iters, S.ROW), dtype=torch.float32)
     for n, s in enumerate(levels):                     # 0-d fp32 tensors, reference op order (:241-251, :423)
         table[n, S.R_K0] = float(sd ** 2 / (sd ** 2 + (s - smin) ** 2))                      # c_skip
         table[n, S.R_K1] = float((s - smin) * sd / (sd ** 2 + s ** 2).sqrt())               # c_out
@@ -528,7 +547,14 @@ def try_sample_consistency(agent, *, model, xt, prior, sigmas, order, cond_emb, 
             plan.x_max.copy_(_row(agent.x_max, x_shape, device))
         for k in range(n_slots):
             _draw_noise(plan.noise[k], xt)
-        t_all = table[:, S.R_T].to(device)             # the network sees c_noise = ln(sigma)/4 as its "time"
+        if hit is not None:
+            t_all = hit[1]
+        else:
+            t_all = table[:, S.R_T].to(device)         # the network sees c_noise = ln(sigma)/4 as its "time"
+            if cm_key is not None:
+                if len(agent._engine_cm_tables) > 16:
+                    agent._engine_cm_tables.clear()
+                agent._engine_cm_tables[cm_key] = (table, t_all)
     plan.run(t_all, cond_emb, use_graph=os.environ.get("CDS_GRAPH", "1") != "0")
     STATS["engine_calls"] += 1
     return plan.x.clone()

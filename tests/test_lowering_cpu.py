@@ -201,6 +201,40 @@ def test_table_caches_follow_the_request(golden):
     assert np.abs(run() - a0).max() > 1e-4
 
 
+def test_schedule_identity_fast_path_is_keyed_on_what_the_schedule_depends_on(golden):
+    """The discrete sampler hands the engine a ``sched_id`` (named step schedule, grid length, identity + version of the alpha /
+    sigma buffers); a repeated request must not read the schedule back from the device (on a GPU each read is a stream
+    synchronisation), a changed schedule must miss."""
+    name = "disc_dup_ddpm_x0"
+    spec = cases.sampler_cases()[name]
+    agent, inp, kw = build_agent(spec)
+
+    def run(**over):
+        tape = NoiseTape(tape_of(golden["samplers"], name))
+        with tape.active(), torch.no_grad():
+            return agent.sample(inp["prior"], **{**kw, **over})[0].numpy()
+
+    a0 = run()
+    assert len(agent._engine_sched_ids) == 1
+    (key0, (sched_key0, _)), = agent._engine_sched_ids.items()
+    reads = []
+    real_cpu = torch.Tensor.cpu
+    try:
+        torch.Tensor.cpu = lambda self, *a, **k: (reads.append(tuple(self.shape)), real_cpu(self, *a, **k))[1]
+        a1 = run()
+    finally:
+        torch.Tensor.cpu = real_cpu
+    np.testing.assert_array_equal(a1, a0)
+    assert not [r for r in reads if r == (kw["sample_steps"],) or r == (kw["sample_steps"] + 1,)], reads   # no schedule read-back
+    assert len(agent._engine_sched_ids) == 1
+    with torch.no_grad():
+        agent.alpha.mul_(0.999)                            # the schedule changes in place -> version bump -> new identity
+    a2 = run()
+    assert len(agent._engine_sched_ids) == 2 and np.abs(a2 - a0).max() > 1e-6
+    run(sample_step_schedule=lambda T, S: torch.arange(S + 1) * (T - 1) // S)       # callables carry no identity: no entry
+    assert len(agent._engine_sched_ids) == 2
+
+
 @pytest.mark.parametrize("name,math", [("disc_dup_ddpm_x0", "fp32"), ("cont_cfg2branch_2M", "fp32"), ("cont_ddim_eps", "bf16")])
 def test_lowered_sampler_two_branches(golden, name, math, monkeypatch):
     """The batch split into two independent operator chains (cds_op.flags branch bits; parallel streams on the GPU): same
