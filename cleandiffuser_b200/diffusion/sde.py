@@ -395,5 +395,15 @@ class ContinuousDiffusionSDE(BaseDiffusionSDE):
             alphas=alphas, sigmas=sigmas, condition_vec_cfg=cond_vec, w_cfg=w_cfg,
             condition_vec_cg=condition_cg, w_cg=w_cg, diffusion_x_sampling_steps=diffusion_x_sampling_steps,
             requires_grad=requires_grad, preserve_history=preserve_history, n_samples=n_samples, log=log,
-            engine_ok=self._engine_candidate(requires_grad, preserve_history, w_cg, warm_start_reference))
+            engine_ok=self._engine_candidate(requires_grad, preserve_history, w_cg, warm_start_reference),
+            sched_id=self._schedule_identity(sample_step_schedule, span))
         return self._finish(xt, log, n_samples, condition_cg, w_cg)
+
+    def _schedule_identity(self, sample_step_schedule, span):
+        """What (times, alphas, sigmas) are functions of, when that can be named: a named step schedule, the identity of the noise schedule's
+        forward function and plain-number parameters.  None otherwise (the engine then reads the schedule back and keys its table on the values)."""
+        params = self.noise_schedule_params or {}
+        if not isinstance(sample_step_schedule, str) or not all(isinstance(v, (int, float)) for v in params.values()):
+            return None
+        return ("cont", sample_step_schedule, id(self.noise_schedule_funcs["forward"]), tuple(sorted(params.items())),
+                tuple(float(v) for v in span))
