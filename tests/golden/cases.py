@@ -92,6 +92,12 @@ SAMPLER_NETS = {
     "pearce_tiny": dict(
         cls="PearceMlp", ctor=dict(act_dim=3, To=1, emb_dim=8, hidden_dim=32),
         x=(3,), oracle=dict(fn="pearce_mlp", emb_dim=8, To=1)),
+    "sfbc_tiny": dict(
+        cls="SfBCUNet", ctor=dict(act_dim=3, emb_dim=8, hidden_dims=[32, 16]),
+        x=(3,), oracle=dict(fn="sfbc_unet", emb_dim=8, n_layers=2)),
+    "dvinv_tiny": dict(
+        cls="DVInvMlp", ctor=dict(obs_dim=2, act_dim=3, emb_dim=8, hidden_dim=32),
+        x=(3,), oracle=dict(fn="dvinv_mlp", emb_dim=8)),
 }
 SAMPLER_BATCH = 6
 
@@ -127,6 +133,14 @@ def sampler_cases():
         kind="continuous", net="janner_tiny", solver="sde_dpmsolver++_1", predict_noise=False, steps=4,
         fix_mask=None, clip=True, w_cfg=0.0, cond=None, temperature=1.0, warm=0.4,
         step_schedule="cat_cos_continuous")
+    # the SfBC / Decision-Veteran patterns: continuous-time SDE sampler over the U-shaped residual MLP (condition = an embedding
+    # added to the time code) and over the inverse-dynamics MLP (condition = two stacked observations)
+    out["cont_sfbc_2M_eps"] = dict(
+        kind="continuous", net="sfbc_tiny", solver="ode_dpmsolver++_2M", predict_noise=True, steps=5,
+        fix_mask=None, clip=True, w_cfg=1.0, cond="emb", temperature=1.0, schedule="linear")
+    out["disc_dvinv_ddpm_x0"] = dict(
+        kind="discrete", net="dvinv_tiny", solver="ddpm", predict_noise=False, T=8, steps=8,
+        fix_mask=None, clip=True, w_cfg=1.0, cond="obs", temperature=1.0)
     return out
 
 
