@@ -160,7 +160,9 @@ class ContinuousEDM(DiffusionModel):
         done = False
         if not (requires_grad or preserve_history or guided) and runtime._device_ok(torch.device(self.device)):
             out = runtime.try_sample_edm(self, model=model, xt=xt, prior=prior, solver=solver, sigmas=sigmas, order=order,
-                                         cond_emb=cvec, w_cfg=w_cfg, n_samples=n_samples)
+                                         cond_emb=cvec, w_cfg=w_cfg, n_samples=n_samples,
+                                         sched_id=(int(sample_steps), float(self.sigma_min), float(top), float(self.rho),
+                                                   float(self.sigma_data)))
             if out is not None:
                 xt, done = out, True
 

@@ -560,7 +560,8 @@ def try_sample_consistency(agent, *, model, xt, prior, sigmas, order, cond_emb, 
     return plan.x.clone()
 
 
-def try_sample_edm(agent, *, model, xt, prior, solver, sigmas, order, cond_emb, w_cfg, n_samples, evals=None, clip=True):
+def try_sample_edm(agent, *, model, xt, prior, solver, sigmas, order, cond_emb, w_cfg, n_samples, evals=None, clip=True,
+                   sched_id=None):
     """ContinuousEDM.sample on the engine (newedm.py:395-431).  Every network evaluation is one engine iteration:
     ``euler``: one per reverse step; ``heun``: predictor + corrector (two evaluations) for every step but the last.
     ``sigmas``: the Karras grid (sample_steps + 1 entries, fp32), ``order``: the reverse steps i in loop order."""
@@ -578,17 +579,20 @@ def try_sample_edm(agent, *, model, xt, prior, solver, sigmas, order, cond_emb, 
         return _fallback("n_samples != prior.shape[0]")
     sd = agent.sigma_data
     given = evals is not None                    # legacy EDM: the caller lists the evaluations (sigma, kind, dt, flag, xw, dw)
-    sig = sigmas.detach().float().cpu() if not given else None
+    # ``sched_id`` (see try_sample): a hit reuses the table without reading the Karras grid back from the device
+    edm_key = None if (sched_id is None or given) else (sched_id, solver, tuple(order), str(device))
+    hit = agent.__dict__.setdefault("_engine_edm_tables", {}).get(edm_key) if edm_key is not None else None
+    sig = sigmas.detach().float().cpu() if (not given and hit is None) else None
     evals = list(evals) if given else []         # (sigma of the evaluation, kind, dt, predictor flag[, x_weight, D_weight])
-    for i in ([] if given else order):
+    for i in ([] if (given or hit is not None) else order):
         dt = sig[i] - sig[i - 1]
         heun = solver == "heun" and i > 1
         evals.append((sig[i], S.UPD_EDM, dt, 1.0 if heun else 0.0))
         if heun:
             # the corrector evaluates at t = t_i / sigma_i * sigma_{i-1} (newedm.py:421) = sigma_{i-1} exactly (x / x == 1)
             evals.append((sig[i - 1], S.UPD_EDM_HEUN, dt, 0.0))
-    n_iters = len(evals)
-    table = torch.zeros((n_iters, S.ROW), dtype=torch.float32)
+    n_iters = hit[0].shape[0] if hit is not None else len(evals)
+    table = hit[0] if hit is not None else torch.zeros((n_iters, S.ROW), dtype=torch.float32)
     for n, ev in enumerate(evals):                         # 0-d fp32 tensors, reference op order (newedm.py:128-148)
         s, kind, dt, pred_flag = ev[:4]
         if len(ev) > 4:
@@ -634,7 +638,14 @@ def try_sample_edm(agent, *, model, xt, prior, solver, sigmas, order, cond_emb, 
             plan.x_min.copy_(_row(agent.x_min, x_shape, device))
         if has_max:
             plan.x_max.copy_(_row(agent.x_max, x_shape, device))
-        t_all = table[:, S.R_T].to(device)             # the network sees c_noise = ln(sigma)/4 as its "time"
+        if hit is not None:
+            t_all = hit[1]
+        else:
+            t_all = table[:, S.R_T].to(device)         # the network sees c_noise = ln(sigma)/4 as its "time"
+            if edm_key is not None:
+                if len(agent._engine_edm_tables) > 16:
+                    agent._engine_edm_tables.clear()
+                agent._engine_edm_tables[edm_key] = (table, t_all)
     plan.run(t_all, cond_emb, use_graph=os.environ.get("CDS_GRAPH", "1") != "0")
     STATS["engine_calls"] += 1
     return plan.x.clone()
